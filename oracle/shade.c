@@ -1,0 +1,383 @@
+/* oracle/shade.c — TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Restatement of the fragment stage:
+ *   shader/src/lib.rs:37-162   fragment_transmission
+ *   shader/src/lib.rs:164-249  fragment
+ *   shader/src/lighting.rs:13-95, 127-220, 222-241, 261-313
+ *   shared-structs/src/lib.rs:43-67, 90-138
+ * plus the sampling rules the Vulkan implementation supplied in the reference
+ *  and the G-buffer decode that stands in for the
+ * rasteriser's varying interpolation.  Texture-mapped branches
+ * (`textures.* != -1`) are out of scope and rejected upstream.
+ * PARITY UNPINNED (oracle.h).
+ */
+#include "oracle.h"
+
+#include <omp.h>
+
+int orc_num_threads(void) { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { omp_set_num_threads(n); }
+
+/* ------------------------------------------------------------------ */
+/* our fp32 log2 definition (DESIGN.md "discrete decisions")           */
+/* The reference's Log2 is GLSL.std.450 (implementation-defined         */
+/* precision) on the GPU; the cluster slice is a truncation of it, so   */
+/* oracle and kernel share one exactly specified evaluation:            */
+/*   x = m * 2^e, m in (sqrt(1/2), sqrt(2)];  s = (m-1)/(m+1)           */
+/*   ln m = 2s(1 + z/3 + z^2/5 + z^3/7 + z^4/9 + z^5/11), z = s^2       */
+/* evaluated in fp32, Horner, no FMA.                                   */
+/* ------------------------------------------------------------------ */
+float orc_log2_spec(float x) {
+    uint32_t bits;
+    memcpy(&bits, &x, 4);
+    if (!(x > 0.0f) || bits >= 0x7f800000u) {
+        if (x == 0.0f) return -INFINITY;
+        if (x > 0.0f) return x; /* +inf */
+        return NAN;
+    }
+    int e = 0;
+    if (bits < 0x00800000u) { /* subnormal: scale by 2^24 */
+        x = x * 16777216.0f;
+        memcpy(&bits, &x, 4);
+        e = -24;
+    }
+    e += (int)(bits >> 23) - 127;
+    uint32_t mb = (bits & 0x007fffffu) | 0x3f800000u;
+    float m;
+    memcpy(&m, &mb, 4);
+    if (m > 1.41421354f) {
+        m = m * 0.5f;
+        e = e + 1;
+    }
+    float f = m - 1.0f;
+    float s = f / (2.0f + f);
+    float z = s * s;
+    float p = z * 0.0909090936f + 0.111111112f;
+    p = z * p + 0.142857149f;
+    p = z * p + 0.2f;
+    p = z * p + 0.333333343f;
+    float s2 = s + s;
+    float r = s2 + s2 * (z * p);
+    return (float)e + r * 1.44269502f;
+}
+
+/* shared-structs/src/lib.rs:44-52 */
+void orc_light_cluster_coefficients_new(float z_near, float z_far, uint32_t slices, tr_light_cluster_coefficients* out) {
+    out->z_near = z_near;
+    out->z_far = z_far;
+    out->num_depth_slices = slices;
+    out->scale = (float)slices / log2f(z_far / z_near);
+    out->bias = -((float)slices * log2f(z_near) / log2f(z_far / z_near));
+}
+
+/* shared-structs/src/lib.rs:54-58 */
+float orc_linear_depth(const tr_light_cluster_coefficients* c, float frag_depth) {
+    float depth_range = 2.0f * (1.0f - frag_depth) - 1.0f;
+    return 2.0f * c->z_near * c->z_far / (c->z_far + c->z_near - depth_range * (c->z_far - c->z_near));
+}
+
+/* Rust `f32 as u32`: saturating, NaN -> 0 */
+static uint32_t f32_as_u32(float v) {
+    if (!(v > 0.0f)) return 0u;
+    if (v >= 4294967296.0f) return 0xffffffffu;
+    return (uint32_t)v;
+}
+
+/* shared-structs/src/lib.rs:61-63 */
+uint32_t orc_get_depth_slice(const tr_light_cluster_coefficients* c, float frag_depth) {
+    float v = orc_log2_spec(orc_linear_depth(c, frag_depth)) * c->scale + c->bias;
+    return f32_as_u32(f_max(v, 0.0f));
+}
+
+/* shared-structs/src/lib.rs:129-138 */
+float orc_spotlight_factor(const tr_light* l, v3 direction_to_light) {
+    v3 spot_dir = v3_new(l->spotlight_direction_and_outer_angle.x, l->spotlight_direction_and_outer_angle.y,
+                         l->spotlight_direction_and_outer_angle.z);
+    float theta = v3_dot(v3_neg(direction_to_light), spot_dir);
+    float outer_angle = l->spotlight_direction_and_outer_angle.w;
+    float epsilon = l->position_and_spotlight_epsilon.w;
+    float cos_outer = (float)cos((double)outer_angle);
+    return f_max((theta - cos_outer) / epsilon, 0.0f);
+}
+
+/* ------------------------------------------------------------------ */
+/* Samplers (sampler state src/main.rs:683-705)   */
+/* ------------------------------------------------------------------ */
+static int64_t clamp_i64(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* texel-space setup shared by both samplers: p = u*size - 0.5 */
+static void bilinear_setup(float u, uint32_t size, uint32_t* i0, uint32_t* i1, float* frac) {
+    float p = u * (float)size - 0.5f;
+    if (!(p == p)) p = 0.0f; /* NaN coordinate -> texel 0 */
+    float fl = floorf(p);
+    float f = p - fl;
+    int64_t i;
+    if (fl <= -2147483648.0f) {
+        i = -2147483648LL;
+        f = 0.0f;
+    } else if (fl >= 2147483520.0f) {
+        i = 2147483520LL;
+        f = 0.0f;
+    } else {
+        i = (int64_t)fl;
+    }
+    *i0 = (uint32_t)clamp_i64(i, 0, (int64_t)size - 1);
+    *i1 = (uint32_t)clamp_i64(i + 1, 0, (int64_t)size - 1);
+    *frac = f;
+}
+
+static float lerpf(float a, float b, float t) { return a + (b - a) * t; }
+
+static v3 sample_level(const orc_pyramid* p, uint32_t level, float u, float v) {
+    uint32_t w = p->width[level], h = p->height[level];
+    const uint16_t* d = p->data[level];
+    uint32_t x0, x1, y0, y1;
+    float fx, fy;
+    bilinear_setup(u, w, &x0, &x1, &fx);
+    bilinear_setup(v, h, &y0, &y1, &fy);
+    float out[3];
+    for (int c = 0; c < 3; c++) {
+        float t00 = f16_bits_to_f32(d[((size_t)y0 * w + x0) * 4 + c]);
+        float t10 = f16_bits_to_f32(d[((size_t)y0 * w + x1) * 4 + c]);
+        float t01 = f16_bits_to_f32(d[((size_t)y1 * w + x0) * 4 + c]);
+        float t11 = f16_bits_to_f32(d[((size_t)y1 * w + x1) * 4 + c]);
+        float top = lerpf(t00, t10, fx);
+        float bot = lerpf(t01, t11, fx);
+        out[c] = lerpf(top, bot, fy);
+    }
+    return v3_new(out[0], out[1], out[2]);
+}
+
+/* framebuffer.sample_by_lod(clamp_sampler, uv, lod).rgb — shader/src/lib.rs:135-138 */
+v3 orc_sample_pyramid(const orc_pyramid* p, float u, float v, float lod) {
+    float max_lod = (float)(p->levels - 1);
+    if (!(lod > 0.0f)) lod = 0.0f;
+    if (lod > max_lod) lod = max_lod;
+    float l0f = floorf(lod);
+    uint32_t l0 = (uint32_t)l0f;
+    uint32_t l1 = l0 + 1 < p->levels ? l0 + 1 : p->levels - 1;
+    float t = lod - l0f;
+    v3 s0 = sample_level(p, l0, u, v);
+    v3 s1 = sample_level(p, l1, u, v);
+    return v3_new(lerpf(s0.x, s1.x, t), lerpf(s0.y, s1.y, t), lerpf(s0.z, s1.z, t));
+}
+
+/* textures[ggx_lut].sample(clamp_sampler, (n.v, roughness)).xy — shader/src/lib.rs:126-133;
+ * RGBA8 UNORM, one level (src/main.rs:295-330) */
+v2 orc_sample_lut(const orc_lut* lut, float n_dot_v, float roughness) {
+    uint32_t x0, x1, y0, y1;
+    float fx, fy;
+    bilinear_setup(n_dot_v, lut->width, &x0, &x1, &fx);
+    bilinear_setup(roughness, lut->height, &y0, &y1, &fy);
+    float out[2];
+    for (int c = 0; c < 2; c++) {
+        float t00 = (float)lut->rgba8[((size_t)y0 * lut->width + x0) * 4 + c] / 255.0f;
+        float t10 = (float)lut->rgba8[((size_t)y0 * lut->width + x1) * 4 + c] / 255.0f;
+        float t01 = (float)lut->rgba8[((size_t)y1 * lut->width + x0) * 4 + c] / 255.0f;
+        float t11 = (float)lut->rgba8[((size_t)y1 * lut->width + x1) * 4 + c] / 255.0f;
+        out[c] = lerpf(lerpf(t00, t10, fx), lerpf(t01, t11, fx), fy);
+    }
+    v2 r = {out[0], out[1]};
+    return r;
+}
+
+/* ------------------------------------------------------------------ */
+/* fragment stage                                                       */
+/* ------------------------------------------------------------------ */
+static v3 from_a(tr_vec3a a) { return v3_new(a.x, a.y, a.z); }
+
+/* lighting.rs:261-301 with every texture index == -1 */
+static orc_material_params get_material_params(tr_vec4 diffuse, const tr_material_info* m) {
+    orc_material_params r;
+    r.diffuse_colour = v3_new(diffuse.x, diffuse.y, diffuse.z);
+    r.metallic = m->metallic_factor;
+    r.perceptual_roughness = m->roughness_factor;
+    r.index_of_refraction = m->index_of_refraction;
+    r.specular_colour = from_a(m->specular_colour_factor);
+    r.specular_factor = m->specular_factor;
+    return r;
+}
+
+/* shader/src/lib.rs:88-98 / 205-215; robust-buffer-access semantics for an out-of-range cluster */
+static uint32_t cluster_index(v4 frag_coord, const tr_uniforms* u) {
+    uint32_t cx = f32_as_u32(frag_coord.x / u->cluster_size_in_pixels.x);
+    uint32_t cy = f32_as_u32(frag_coord.y / u->cluster_size_in_pixels.y);
+    uint32_t cz = orc_get_depth_slice(&u->light_clustering_coefficients, frag_coord.z);
+    return cz * u->num_clusters.x * u->num_clusters.y + cy * u->num_clusters.x + cx;
+}
+
+static v3 light_position(const tr_light* l) {
+    return v3_new(l->position_and_spotlight_epsilon.x, l->position_and_spotlight_epsilon.y,
+                  l->position_and_spotlight_epsilon.z);
+}
+static v3 light_emission(const tr_light* l) {
+    return v3_new(l->colour_emission_and_falloff_distance_sq.x, l->colour_emission_and_falloff_distance_sq.y,
+                  l->colour_emission_and_falloff_distance_sq.z);
+}
+
+/* shader/src/lib.rs:164-249 + lighting.rs:145-220 */
+v4 orc_fragment(v3 position, v3 normal_in, v2 uv, uint32_t material_id, v4 frag_coord, const orc_scene* s) {
+    (void)uv;
+    const tr_material_info* material = &s->materials[material_id];
+    tr_vec4 diffuse = material->diffuse_factor;
+
+    v3 view_vector = v3_sub(from_a(s->pc->view_position), position);
+    v3 view = v3_normalize(view_vector);
+    v3 normal = v3_normalize(normal_in); /* lighting.rs:229 */
+    orc_material_params mp = get_material_params(diffuse, material);
+    v3 emission = from_a(material->emissive_factor); /* lighting.rs:303-313 */
+
+    uint32_t cluster = cluster_index(frag_coord, s->uniforms);
+    uint32_t num_lights = cluster < s->n_clusters ? s->cluster_light_counts[cluster] : 0u;
+
+    v3 sun_dir = from_a(s->uniforms->sun_dir);
+    v3 sun_intensity = v3_scale(from_a(s->uniforms->sun_intensity), 1.0f); /* lighting.rs:168-173 */
+    orc_brdf_result sum = orc_basic_brdf(normal, sun_dir, sun_intensity, view, mp);
+
+    uint32_t offset = cluster * TR_MAX_LIGHTS_PER_CLUSTER;
+    for (uint32_t i = 0; i < num_lights; i++) {
+        const tr_light* light = &s->lights[s->cluster_light_indices[offset + i]];
+        v3 direction;
+        float distance, attenuation;
+        orc_light_direction_and_attenuation(position, light_position(light), &direction, &distance, &attenuation);
+        float factor = 1.0f;
+        if (light->spotlight_direction_and_outer_angle.w != 0.0f) factor *= orc_spotlight_factor(light, direction);
+        v3 emission_l = v3_scale(light_emission(light), factor);
+        orc_brdf_result r = orc_basic_brdf(normal, direction, v3_scale(emission_l, attenuation), view, mp);
+        sum.diffuse = v3_add(sum.diffuse, r.diffuse);
+        sum.specular = v3_add(sum.specular, r.specular);
+    }
+
+    v3 out = v3_add(v3_add(sum.diffuse, sum.specular), emission);
+    return v4_new(out.x, out.y, out.z, 1.0f);
+}
+
+/* shader/src/lib.rs:37-162 + lighting.rs:13-95 */
+v4 orc_fragment_transmission(v3 position, v3 normal_in, v2 uv, uint32_t material_id, float model_scale, v4 frag_coord,
+                             const orc_scene* s, const orc_pyramid* fb, const orc_lut* lut) {
+    (void)uv;
+    const tr_material_info* material = &s->materials[material_id];
+    tr_vec4 diffuse = material->diffuse_factor;
+    float transmission_factor = material->transmission_factor;
+
+    v3 view_vector = v3_sub(from_a(s->pc->view_position), position);
+    v3 view = v3_normalize(view_vector);
+    v3 normal = v3_normalize(normal_in);
+    orc_material_params mp = get_material_params(diffuse, material);
+    v3 emission = from_a(material->emissive_factor);
+
+    uint32_t cluster = cluster_index(frag_coord, s->uniforms);
+    uint32_t num_lights = cluster < s->n_clusters ? s->cluster_light_counts[cluster] : 0u;
+
+    /* lighting.rs:37-53 */
+    v3 sun_dir = from_a(s->uniforms->sun_dir);
+    v3 sun_intensity = v3_scale(from_a(s->uniforms->sun_intensity), 1.0f);
+    orc_brdf_result sum = orc_basic_brdf(normal, sun_dir, sun_intensity, view, mp);
+    v3 transmission = v3_mul(sun_intensity, orc_transmission_btdf(mp, normal, view, sun_dir));
+
+    /* lighting.rs:58-92 — note: no spotlight factor in this loop */
+    uint32_t offset = cluster * TR_MAX_LIGHTS_PER_CLUSTER;
+    for (uint32_t i = 0; i < num_lights; i++) {
+        const tr_light* light = &s->lights[s->cluster_light_indices[offset + i]];
+        v3 direction;
+        float distance, attenuation;
+        orc_light_direction_and_attenuation(position, light_position(light), &direction, &distance, &attenuation);
+        v3 emission_l = v3_scale(light_emission(light), 1.0f);
+        orc_brdf_result r = orc_basic_brdf(normal, direction, v3_scale(emission_l, attenuation), view, mp);
+        sum.diffuse = v3_add(sum.diffuse, r.diffuse);
+        sum.specular = v3_add(sum.specular, r.specular);
+        transmission = v3_add(transmission, v3_mul(v3_scale(emission_l, attenuation),
+                                                   orc_transmission_btdf(mp, normal, view, direction)));
+    }
+
+    float thickness = material->thickness_factor; /* lib.rs:120 */
+
+    orc_ibl_params ip;
+    ip.material_params = mp;
+    ip.framebuffer_size_x = s->pc->framebuffer_size.x;
+    ip.normal = normal;
+    ip.view = view;
+    memcpy(&ip.proj_view_matrix, &s->pc->proj_view, sizeof(m4));
+    ip.position = position;
+    ip.thickness = thickness;
+    ip.model_scale = model_scale;
+    ip.attenuation_distance = material->attenuation_distance;
+    ip.attenuation_colour = from_a(material->attenuation_colour);
+    transmission = v3_add(transmission, orc_ibl_volume_refraction(&ip, fb, lut)); /* lib.rs:140-155 */
+
+    v3 real_transmission = v3_scale(transmission, transmission_factor);          /* lib.rs:157 */
+    v3 diffuse_out = v3_lerp(sum.diffuse, real_transmission, transmission_factor); /* lib.rs:159 */
+    v3 out = v3_add(v3_add(diffuse_out, sum.specular), emission);                 /* lib.rs:161 */
+    return v4_new(out.x, out.y, out.z, 1.0f);
+}
+
+/* ------------------------------------------------------------------ */
+/* G-buffer decode: what the rasteriser + varying interpolation feed    */
+/* the fragment stage (ours to define; DESIGN.md "G-buffer")            */
+/* ------------------------------------------------------------------ */
+static v3 decode_position(const orc_gbuffer* g, const m4* inv_pv, uint32_t x, uint32_t y, float depth) {
+    size_t i = (size_t)y * g->width + x;
+    if (g->position) return v3_new(g->position[i * 3], g->position[i * 3 + 1], g->position[i * 3 + 2]);
+    float ndc_x = ((float)x + 0.5f) / (float)g->width * 2.0f - 1.0f;
+    float ndc_y = ((float)y + 0.5f) / (float)g->height * 2.0f - 1.0f;
+    v4 h = m4_mul_v4(inv_pv, v4_new(ndc_x, ndc_y, depth, 1.0f));
+    return v3_new(h.x / h.w, h.y / h.w, h.z / h.w);
+}
+
+static void store_px(float* f32buf, uint16_t* a, uint16_t* b, size_t i, v4 c) {
+    if (f32buf) {
+        f32buf[i * 4] = c.x; f32buf[i * 4 + 1] = c.y; f32buf[i * 4 + 2] = c.z; f32buf[i * 4 + 3] = c.w;
+    }
+    uint16_t h[4] = {f32_to_f16_bits(c.x), f32_to_f16_bits(c.y), f32_to_f16_bits(c.z), f32_to_f16_bits(c.w)};
+    if (a) memcpy(a + i * 4, h, 8);
+    if (b) memcpy(b + i * 4, h, 8);
+}
+
+void orc_shade_opaque_frame(const orc_gbuffer* g, const orc_scene* s, uint32_t y0, uint32_t y1, float* hdr_f32,
+                            uint16_t* hdr_f16, uint16_t* opaque_f16) {
+    tr_mat4 inv;
+    orc_mat4_inverse(&s->pc->proj_view, &inv);
+    m4 inv_pv;
+    memcpy(&inv_pv, &inv, sizeof(m4));
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t yy = (int64_t)y0; yy < (int64_t)y1; yy++) {
+        uint32_t y = (uint32_t)yy;
+        for (uint32_t x = 0; x < g->width; x++) {
+            size_t i = (size_t)y * g->width + x;
+            float depth = g->depth[i];
+            v4 c = v4_new(0.0f, 0.0f, 0.0f, 1.0f); /* clear colour, main.rs:1592-1602 */
+            if (depth != 0.0f) {
+                v3 pos = decode_position(g, &inv_pv, x, y, depth);
+                v3 n = v3_new(g->normal[i * 3], g->normal[i * 3 + 1], g->normal[i * 3 + 2]);
+                v2 uv = {g->uv ? g->uv[i * 2] : 0.0f, g->uv ? g->uv[i * 2 + 1] : 0.0f};
+                v4 fc = v4_new((float)x + 0.5f, (float)y + 0.5f, depth, 1.0f);
+                c = orc_fragment(pos, n, uv, g->material_id[i], fc, s);
+            }
+            store_px(hdr_f32, hdr_f16, opaque_f16, i, c);
+        }
+    }
+}
+
+void orc_shade_transmission_frame(const orc_gbuffer* g, const orc_scene* s, const orc_pyramid* fb, const orc_lut* lut,
+                                  uint32_t y0, uint32_t y1, float* hdr_f32, uint16_t* hdr_f16) {
+    tr_mat4 inv;
+    orc_mat4_inverse(&s->pc->proj_view, &inv);
+    m4 inv_pv;
+    memcpy(&inv_pv, &inv, sizeof(m4));
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t yy = (int64_t)y0; yy < (int64_t)y1; yy++) {
+        uint32_t y = (uint32_t)yy;
+        for (uint32_t x = 0; x < g->width; x++) {
+            size_t i = (size_t)y * g->width + x;
+            float depth = g->depth[i];
+            if (depth == 0.0f) continue; /* render pass LOADs hdr; uncovered pixels keep the opaque result */
+            v3 pos = decode_position(g, &inv_pv, x, y, depth);
+            v3 n = v3_new(g->normal[i * 3], g->normal[i * 3 + 1], g->normal[i * 3 + 2]);
+            v2 uv = {g->uv ? g->uv[i * 2] : 0.0f, g->uv ? g->uv[i * 2 + 1] : 0.0f};
+            v4 fc = v4_new((float)x + 0.5f, (float)y + 0.5f, depth, 1.0f);
+            float scale = g->scale ? g->scale[i] : 1.0f;
+            v4 c = orc_fragment_transmission(pos, n, uv, g->material_id[i], scale, fc, s, fb, lut);
+            store_px(hdr_f32, hdr_f16, NULL, i, c);
+        }
+    }
+}
