@@ -400,6 +400,11 @@ typedef struct {
 } tr_frame_params;
 #define TR_FRAME_SKIP_TONEMAP 1u
 #define TR_FRAME_SKIP_VISIBILITY 2u /* reuse the injected / previous G-buffer */
+TR_STATIC_ASSERT(sizeof(tr_frame_params) == 304, "tr_frame_params");
+TR_STATIC_ASSERT(offsetof(tr_frame_params, assign_lights) == 96, "tr_frame_params.assign_lights");
+TR_STATIC_ASSERT(offsetof(tr_frame_params, push_constants) == 176, "tr_frame_params.push_constants");
+TR_STATIC_ASSERT(offsetof(tr_frame_params, tonemap) == 272, "tr_frame_params.tonemap");
+TR_STATIC_ASSERT(offsetof(tr_frame_params, flags) == 300, "tr_frame_params.flags");
 TR_API int32_t tr_frame(tr_ctx* ctx, const tr_frame_params* params);
 
 /* ------------------------------------------------------------------ */
@@ -409,6 +414,8 @@ TR_API int32_t tr_set_gbuffer(tr_ctx* ctx, int32_t layer, const tr_gbuffer_plane
 TR_API int32_t tr_read_gbuffer(tr_ctx* ctx, int32_t layer, const tr_gbuffer_planes_out* planes);
 /* mip 0 of the sampled opaque pyramid, RGBA16F bits, full frame. */
 TR_API int32_t tr_set_opaque_frame(tr_ctx* ctx, const uint16_t* rgba16f);
+/* hdr_framebuffer, RGBA16F bits, full frame (e.g. to tonemap a caller-provided image). */
+TR_API int32_t tr_set_hdr(tr_ctx* ctx, const uint16_t* rgba16f);
 TR_API int32_t tr_set_cluster_lights(tr_ctx* ctx, const uint32_t* counts, const uint32_t* indices); /* [n_clusters], [n_clusters*128] */
 TR_API int32_t tr_read_visible_instances(tr_ctx* ctx, uint32_t* ids, uint32_t capacity, uint32_t* n_visible);
 TR_API int32_t tr_read_instance_counts(tr_ctx* ctx, uint32_t* counts, uint32_t capacity);

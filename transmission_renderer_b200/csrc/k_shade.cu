@@ -1,0 +1,358 @@
+// k_shade.cu — K4 opaque shading and K6 transmissive shading (sm_100a).
+//
+// Reference behaviour:
+//   K4  `fragment`              shader/src/lib.rs:164-249 + lighting.rs:145-220
+//   K6  `fragment_transmission` shader/src/lib.rs:37-162  + lighting.rs:13-95
+// B200 design (DESIGN.md "K4/K6"):
+//   * persistent CTAs, one per SM slot, walking 256-pixel tiles of the band in
+//     flattened row-major order, so every G-buffer plane of a tile is ONE
+//     contiguous run in HBM;
+//   * each plane of the next tiles is staged into shared memory by the TMA
+//     engine (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a
+//     4-deep ring, so HBM latency is hidden without needing occupancy;
+//   * lights are converted once per CTA into a compact shared-memory table;
+//     the per-pixel cluster lists (ascending light id) are walked with a
+//     warp-wide sorted merge (redux.min) so a warp stays converged while every
+//     pixel still sums its own cluster's lights in ascending id order — the
+//     same order as the oracle, which makes the result independent of tiling;
+//   * results are packed to RGBA16F and written with 128-bit stores (two
+//     pixels per store, lanes paired by shuffle): even lanes write the
+//     hdr_framebuffer, odd lanes write the sampled opaque mip 0 (the reference
+//     writes the same value to both targets, lib.rs:247-248).  With the
+//     peer-store path the odd lanes write that band into every peer GPU's
+//     mip 0 over NVLink, which is the all-gather fused into the shading kernel.
+#include "tr_internal.h"
+
+using namespace trd;
+
+namespace {
+
+constexpr int TILE = 256;  // pixels per tile == threads per CTA
+constexpr int STAGES = 4;
+constexpr int MAX_SMEM_LIGHTS = 1024;
+
+struct LightS {  // 48 B, shared-memory form of shared_structs::Light
+    float px, py, pz;
+    float er, eg, eb;
+    float sx, sy, sz;
+    float cos_outer, inv_eps;
+    uint32_t is_spot;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <bool TRANS, bool HAS_POS>
+struct StageLayout {
+    static constexpr int kDepth = 0;
+    static constexpr int kNormal = kDepth + TILE * 4;
+    static constexpr int kMat = kNormal + TILE * 12;
+    static constexpr int kScale = kMat + TILE * 4;
+    static constexpr int kPos = kScale + (TRANS ? TILE * 4 : 0);
+    static constexpr int kBytes = kPos + (HAS_POS ? TILE * 12 : 0);
+};
+
+__device__ __forceinline__ LightS make_light_s(const tr_light* lights, uint32_t i) {
+    const float4* q = reinterpret_cast<const float4*>(lights + i);
+    float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    LightS l;
+    l.px = a.x; l.py = a.y; l.pz = a.z;
+    l.er = b.x; l.eg = b.y; l.eb = b.z;
+    l.sx = c.x; l.sy = c.y; l.sz = c.z;
+    l.is_spot = c.w != 0.0f;                       // Light::is_a_spotlight, shared-structs lib.rs:125-127
+    l.cos_outer = l.is_spot ? (float)cos((double)c.w) : 0.0f;
+    l.inv_eps = l.is_spot ? 1.0f / a.w : 0.0f;     // spotlight_factor divides by epsilon, lib.rs:137
+    return l;
+}
+
+// shader/src/lib.rs:88-98 / 205-215 in the exact regime (this is a discrete decision)
+__device__ __forceinline__ uint32_t cluster_index(float fx, float fy, float depth, const tr_uniforms& u) {
+    uint32_t cx = f32_as_u32(xdiv(fx, u.cluster_size_in_pixels.x));
+    uint32_t cy = f32_as_u32(xdiv(fy, u.cluster_size_in_pixels.y));
+    const tr_light_cluster_coefficients& c = u.light_clustering_coefficients;
+    // linear_depth, shared-structs lib.rs:54-58
+    float depth_range = xsub(xmul(2.0f, xsub(1.0f, depth)), 1.0f);
+    float lin = xdiv(xmul(xmul(2.0f, c.z_near), c.z_far),
+                     xsub(xadd(c.z_far, c.z_near), xmul(depth_range, xsub(c.z_far, c.z_near))));
+    // get_depth_slice, lib.rs:61-63
+    float v = xadd(xmul(xlog2_spec(lin), c.scale), c.bias);
+    uint32_t cz = f32_as_u32(fmaxf(v, 0.0f));
+    return cz * u.num_clusters.x * u.num_clusters.y + cy * u.num_clusters.x + cx;
+}
+
+template <bool TRANS, bool HAS_POS, bool F32OUT>
+__global__ void __launch_bounds__(TILE) shade_kernel(const __grid_constant__ tr::ShadeLaunch p) {
+    using L = StageLayout<TRANS, HAS_POS>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // STAGES barriers
+    unsigned char* stage_base = smem + 128;
+    LightS* s_lights = reinterpret_cast<LightS*>(stage_base + STAGES * L::kBytes);
+
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31;
+    const uint32_t n_px = p.px_end - p.px_begin;
+    const uint32_t n_tiles = (n_px + TILE - 1) / TILE;
+    const bool lights_in_smem = p.n_lights <= MAX_SMEM_LIGHTS;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (lights_in_smem)
+        for (uint32_t i = tid; i < p.n_lights; i += TILE) s_lights[i] = make_light_s(p.lights, i);
+    __syncthreads();
+
+    auto tile_start = [&](uint32_t t) { return p.px_begin + t * TILE; };
+    auto tile_count = [&](uint32_t t) { return min((uint32_t)TILE, p.px_end - tile_start(t)); };
+    auto tile_bulk = [&](uint32_t t) { return ((tile_start(t) & 3u) == 0u) && ((tile_count(t) & 3u) == 0u); };
+
+    auto issue = [&](uint32_t t, int s) {  // thread 0 only
+        if (t >= n_tiles || !tile_bulk(t)) return;
+        const uint32_t start = tile_start(t), n = tile_count(t);
+        unsigned char* sb = stage_base + s * L::kBytes;
+        uint32_t bytes = n * (4 + 12 + 4) + (TRANS ? n * 4 : 0) + (HAS_POS ? n * 12 : 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(sb + L::kDepth, p.depth + start, n * 4, &full[s]);
+        bulk_g2s(sb + L::kNormal, p.normal + (size_t)start * 3, n * 12, &full[s]);
+        bulk_g2s(sb + L::kMat, p.material_id + start, n * 4, &full[s]);
+        if (TRANS) bulk_g2s(sb + L::kScale, p.scale + start, n * 4, &full[s]);
+        if (HAS_POS) bulk_g2s(sb + L::kPos, p.position + (size_t)start * 3, n * 12, &full[s]);
+    };
+
+    if (tid == 0)
+        for (int s = 0; s < STAGES; s++) issue(blockIdx.x + s * gridDim.x, s);
+
+    uint32_t phase_bits = 0;
+    int stage = 0;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t start = tile_start(t), n = tile_count(t);
+        unsigned char* sb = stage_base + stage * L::kBytes;
+        float* s_depth = reinterpret_cast<float*>(sb + L::kDepth);
+        float* s_normal = reinterpret_cast<float*>(sb + L::kNormal);
+        uint32_t* s_mat = reinterpret_cast<uint32_t*>(sb + L::kMat);
+        float* s_scale = reinterpret_cast<float*>(sb + L::kScale);
+        float* s_pos = reinterpret_cast<float*>(sb + L::kPos);
+
+        if (tile_bulk(t)) {
+            mbar_wait(&full[stage], (phase_bits >> stage) & 1u);
+            phase_bits ^= 1u << stage;
+        } else {  // ragged tile (unaligned start or size): plain coalesced loads
+            for (uint32_t i = tid; i < n; i += TILE) {
+                s_depth[i] = p.depth[start + i];
+                s_mat[i] = p.material_id[start + i];
+                if (TRANS) s_scale[i] = p.scale[start + i];
+            }
+            for (uint32_t i = tid; i < n * 3; i += TILE) {
+                s_normal[i] = p.normal[(size_t)start * 3 + i];
+                if (HAS_POS) s_pos[i] = p.position[(size_t)start * 3 + i];
+            }
+            __syncthreads();
+        }
+
+        // ------------------------------------------------------------ per-pixel prologue
+        const bool active = (uint32_t)tid < n;
+        const uint32_t g = start + tid;
+        const float depth = active ? s_depth[tid] : 0.0f;
+        const bool covered = active && depth != 0.0f;
+
+        PixelShading ps;
+        f3 pos = mk3(0.f, 0.f, 0.f), emission = mk3(0.f, 0.f, 0.f);
+        f3 diff = mk3(0.f, 0.f, 0.f), spec = mk3(0.f, 0.f, 0.f), trans = mk3(0.f, 0.f, 0.f);
+        const tr_material_info* mat = nullptr;
+        uint32_t my_count = 0, my_base = 0, my_i = 0;
+        float model_scale = 1.0f;
+
+        if (covered) {
+            const uint32_t py = g / p.width, px = g - py * p.width;
+            const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+            if (HAS_POS) {
+                pos = mk3(s_pos[tid * 3], s_pos[tid * 3 + 1], s_pos[tid * 3 + 2]);
+            } else {
+                // G-buffer decode (oracle: decode_position in oracle/shade.c), exact regime
+                float ndc_x = xsub(xmul(xdiv(fx, (float)p.width), 2.0f), 1.0f);
+                float ndc_y = xsub(xmul(xdiv(fy, (float)p.height), 2.0f), 1.0f);
+                f4 h = xmat4_mul(p.inv_proj_view, ndc_x, ndc_y, depth, 1.0f);
+                pos = mk3(xdiv(h.x, h.w), xdiv(h.y, h.w), xdiv(h.z, h.w));
+            }
+            mat = p.materials + s_mat[tid];
+            const float4 dfac = __ldg(reinterpret_cast<const float4*>(&mat->diffuse_factor));
+            const float4 emis = __ldg(reinterpret_cast<const float4*>(&mat->emissive_factor));
+            const float4 scol = __ldg(reinterpret_cast<const float4*>(&mat->specular_colour_factor));
+            MaterialParams mp;  // get_material_params, lighting.rs:261-301 (no textures)
+            mp.diffuse_colour = mk3(dfac.x, dfac.y, dfac.z);
+            mp.metallic = __ldg(&mat->metallic_factor);
+            mp.perceptual_roughness = __ldg(&mat->roughness_factor);
+            mp.index_of_refraction = __ldg(&mat->index_of_refraction);
+            mp.specular_colour = mk3(scol.x, scol.y, scol.z);
+            mp.specular_factor = __ldg(&mat->specular_factor);
+            emission = mk3(emis.x, emis.y, emis.z);
+
+            f3 view_pos = mk3(p.view_position[0], p.view_position[1], p.view_position[2]);
+            f3 v = xnormalize3(xsub3(view_pos, pos));                                    // lib.rs:196-197
+            f3 nrm = xnormalize3(mk3(s_normal[tid * 3], s_normal[tid * 3 + 1], s_normal[tid * 3 + 2]));  // lighting.rs:229
+            ps = make_pixel_shading(mp, nrm, v, TRANS);
+            if (TRANS) model_scale = s_scale[tid];
+
+            const uint32_t cluster = cluster_index(fx, fy, depth, p.uniforms);
+            if (cluster < p.n_clusters) {
+                my_count = __ldg(p.cluster_counts + cluster);
+                my_base = cluster * TR_MAX_LIGHTS_PER_CLUSTER;
+            }
+
+            // sun, lighting.rs:37-53 / 171-177 (factor == 1.0 without ray queries)
+            f3 sun_dir = mk3(p.uniforms.sun_dir.x, p.uniforms.sun_dir.y, p.uniforms.sun_dir.z);
+            f3 sun_int = mk3(p.uniforms.sun_intensity.x, p.uniforms.sun_intensity.y, p.uniforms.sun_intensity.z);
+            brdf_light(ps, sun_dir, sun_int, diff, spec);
+            if (TRANS) trans = mul3(sun_int, btdf_light(ps, sun_dir));
+        }
+
+        // ------------------------------------------------------------ clustered lights: warp-wide sorted merge
+        uint32_t next = my_i < my_count ? __ldg(p.cluster_indices + my_base + my_i) : 0xffffffffu;
+        while (true) {
+            const uint32_t m = __reduce_min_sync(0xffffffffu, next);
+            if (m == 0xffffffffu) break;
+            LightS l;
+            if (lights_in_smem) l = s_lights[m];
+            else l = make_light_s(p.lights, m);
+            if (next == m) {
+                f3 dir;
+                float att;
+                light_direction_and_attenuation(pos, mk3(l.px, l.py, l.pz), dir, att);
+                float factor = att;
+                if (!TRANS && l.is_spot) {  // lighting.rs:201-203; the transmissive loop has no spotlight factor (:58-92)
+                    float theta = -dot3(dir, mk3(l.sx, l.sy, l.sz));
+                    factor *= fmaxf((theta - l.cos_outer) * l.inv_eps, 0.0f);
+                }
+                f3 li = scale3(mk3(l.er, l.eg, l.eb), factor);
+                brdf_light(ps, dir, li, diff, spec);
+                if (TRANS) trans = add3(trans, mul3(li, btdf_light(ps, dir)));
+                my_i++;
+                next = my_i < my_count ? __ldg(p.cluster_indices + my_base + my_i) : 0xffffffffu;
+            }
+        }
+
+        // ------------------------------------------------------------ epilogue
+        float4 out = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // clear colour, main.rs:1592-1602
+        if (covered) {
+            if (TRANS) {
+                const float4 acol = __ldg(reinterpret_cast<const float4*>(&mat->attenuation_colour));
+                IblVolumeRefractionParams ip;
+                ip.material_params.diffuse_colour = ps.base;
+                ip.material_params.metallic = 0.0f;
+                ip.material_params.perceptual_roughness = __ldg(&mat->roughness_factor);
+                ip.material_params.index_of_refraction = __ldg(&mat->index_of_refraction);
+                ip.material_params.specular_colour = mk3(0.f, 0.f, 0.f);
+                ip.material_params.specular_factor = 0.0f;
+                ip.normal = ps.n;
+                ip.view = ps.v;
+                ip.position = pos;
+                ip.thickness = __ldg(&mat->thickness_factor);            // lib.rs:120
+                ip.model_scale = model_scale;
+                ip.attenuation_distance = __ldg(&mat->attenuation_distance);
+                ip.attenuation_colour = mk3(acol.x, acol.y, acol.z);
+                trans = add3(trans, ibl_volume_refraction(ip, p.proj_view, p.log2_size_x, p.pyramid, p.lut, ps.f0, ps.df));
+                const float tf = __ldg(&mat->transmission_factor);
+                f3 real_t = scale3(trans, tf);                              // lib.rs:157
+                diff = lerp3(diff, real_t, tf);                             // lib.rs:159
+            }
+            out.x = diff.x + spec.x + emission.x;                           // lib.rs:161 / 239
+            out.y = diff.y + spec.y + emission.y;
+            out.z = diff.z + spec.z + emission.z;
+        }
+
+        const uint2 packed = pack_rgba16f(out.x, out.y, out.z, out.w);
+        if (!TRANS) {
+            // 128-bit paired stores: even lanes -> hdr, odd lanes -> sampled opaque target(s)
+            const uint32_t other_x = __shfl_xor_sync(0xffffffffu, packed.x, 1);
+            const uint32_t other_y = __shfl_xor_sync(0xffffffffu, packed.y, 1);
+            const bool vec_ok = (start & 1u) == 0u;
+            if (active) {
+                if (F32OUT) p.hdr_f32[g] = out;
+                const bool has_partner = vec_ok && (((lane & 1u) != 0u) || ((uint32_t)tid + 1u < n));
+                if (has_partner) {
+                    if ((lane & 1u) == 0u) {
+                        *reinterpret_cast<uint4*>(p.hdr + g) = make_uint4(packed.x, packed.y, other_x, other_y);
+                    } else {
+                        const uint4 v = make_uint4(other_x, other_y, packed.x, packed.y);
+#pragma unroll 1
+                        for (int k = 0; k < p.n_opaque; k++) *reinterpret_cast<uint4*>(p.opaque[k] + g - 1) = v;
+                    }
+                } else {
+                    p.hdr[g] = packed;
+#pragma unroll 1
+                    for (int k = 0; k < p.n_opaque; k++) p.opaque[k][g] = packed;
+                }
+            }
+        } else {
+            if (covered) {  // the transmission render pass LOADs hdr; only covered pixels are written
+                if (F32OUT) p.hdr_f32[g] = out;
+                p.hdr[g] = packed;
+            }
+        }
+
+        __syncthreads();  // every thread is done with this stage's shared memory
+        if (tid == 0) issue(t + STAGES * gridDim.x, stage);
+        stage = stage + 1 == STAGES ? 0 : stage + 1;
+    }
+}
+
+template <bool TRANS, bool HAS_POS, bool F32OUT>
+int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
+    using L = StageLayout<TRANS, HAS_POS>;
+    const uint32_t n_px = p.px_end - p.px_begin;
+    if (n_px == 0) return TR_OK;
+    const uint32_t n_tiles = (n_px + TILE - 1) / TILE;
+    const uint32_t n_smem_lights = p.n_lights <= (uint32_t)MAX_SMEM_LIGHTS ? p.n_lights : 0u;
+    const size_t smem = 128 + (size_t)STAGES * L::kBytes + (size_t)n_smem_lights * sizeof(LightS);
+    auto kern = shade_kernel<TRANS, HAS_POS, F32OUT>;
+    TR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE, smem));
+    if (per_sm < 1) return tr::fail(TR_ERR_CUDA, "shade kernel does not fit on an SM (smem %zu)", smem);
+    uint32_t grid = (uint32_t)(sm_count * per_sm);
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<grid, TILE, smem, s>>>(p);
+    TR_CUDA(cudaGetLastError());
+    return TR_OK;
+}
+
+template <bool TRANS>
+int32_t launch_any(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
+    const bool pos = p.position != nullptr, f32 = p.hdr_f32 != nullptr;
+    if (pos && f32) return launch_variant<TRANS, true, true>(p, sm_count, s);
+    if (pos) return launch_variant<TRANS, true, false>(p, sm_count, s);
+    if (f32) return launch_variant<TRANS, false, true>(p, sm_count, s);
+    return launch_variant<TRANS, false, false>(p, sm_count, s);
+}
+
+}  // namespace
+
+namespace tr {
+int32_t launch_shade_opaque(const ShadeLaunch& p, int sm_count, cudaStream_t s) { return launch_any<false>(p, sm_count, s); }
+int32_t launch_shade_transmission(const ShadeLaunch& p, int sm_count, cudaStream_t s) { return launch_any<true>(p, sm_count, s); }
+}  // namespace tr

@@ -1,0 +1,291 @@
+// tr_device_pbr.cuh — the glam-pbr function contracts as sm_100a device code.
+//
+// Contracts kept (reference: /root/reference/glam-pbr/src/lib.rs):
+//   basic_brdf                :377-423     transmission_btdf       :200-233
+//   ibl_volume_refraction     :292-354     light_direction_and_attenuation :12-23
+//   d_ggx :101-109  v_smith_ggx_correlated :114-133  fresnel_schlick :137-139
+//   calculate_combined_f0/f90 :425-435     IndexOfRefraction::to_dielectric_f0 :192-195
+// Re-designed for the GPU: everything that does not depend on the light is
+// hoisted into a per-pixel `PixelShading` record (built once, reused for the
+// sun and every clustered light), the n.h chain runs in the exact regime and the
+// rest in the fast regime (see tr_device_math.cuh).
+#pragma once
+
+#include "tr_device_math.cuh"
+
+namespace trd {
+
+#define TR_F32_EPSILON 1.1920929e-7f
+#define TR_PI 3.14159265358979323846f
+#define TR_FRAC_1_PI 0.318309886183790671538f
+
+struct MaterialParams {  // glam-pbr lib.rs:171-179
+    f3 diffuse_colour;
+    float metallic;
+    float perceptual_roughness;
+    float index_of_refraction;
+    f3 specular_colour;
+    float specular_factor;
+};
+
+struct BrdfResult {  // glam-pbr lib.rs:437-441
+    f3 diffuse, specular;
+};
+
+TRD float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+// IndexOfRefraction::to_dielectric_f0, lib.rs:192-195
+TRD float to_dielectric_f0(float ior) {
+    float root = (ior - 1.0f) * frcp(ior + 1.0f);
+    return root * root;
+}
+
+// Light-independent part of basic_brdf / transmission_btdf for one pixel.
+struct PixelShading {
+    f3 n, v;            // unit normal / view (exact regime)
+    float nov;          // Dot::new(normal, view), clamped (lib.rs:92-99)
+    f3 f0, df;          // combined f0 and (f90 - f0)           (lib.rs:425-435)
+    f3 c_diff_pi;       // lerp(base, 0, metallic) / pi         (lib.rs:404, 359)
+    f3 base;            // diffuse_colour
+    float a2, a2m1;     // alpha^2 and alpha^2 - 1 (exact), alpha = r^2  (lib.rs:104-106)
+    float one_m_a2;     // 1 - alpha^2                                   (lib.rs:122-124)
+    float nov2_term;    // nov^2 (1 - a2) + a2
+    // transmission lobe: alpha_t = alpha * clamp(2 ior - 2, 0, 1)       (lib.rs:144-148, 209)
+    float at2, at2m1, one_m_at2, nov2_term_t;
+};
+
+TRD PixelShading make_pixel_shading(const MaterialParams& m, f3 n, f3 v, bool with_transmission) {
+    PixelShading s;
+    s.n = n;
+    s.v = v;
+    s.nov = fmaxf(xdot3(n, v), TR_F32_EPSILON);
+    float d0 = to_dielectric_f0(m.index_of_refraction);
+    f3 dielectric = scale3(scale3(m.specular_colour, d0), m.specular_factor);
+    s.f0 = lerp3(dielectric, m.diffuse_colour, m.metallic);
+    f3 f90 = lerp3(splat3(m.specular_factor), splat3(1.0f), m.metallic);
+    s.df = sub3(f90, s.f0);
+    s.base = m.diffuse_colour;
+    s.c_diff_pi = scale3(lerp3(m.diffuse_colour, splat3(0.0f), m.metallic), TR_FRAC_1_PI);
+    float alpha = xmul(m.perceptual_roughness, m.perceptual_roughness);
+    s.a2 = xmul(alpha, alpha);
+    s.a2m1 = xsub(s.a2, 1.0f);
+    s.one_m_a2 = 1.0f - s.a2;
+    s.nov2_term = fmaf(s.nov * s.nov, s.one_m_a2, s.a2);
+    if (with_transmission) {
+        float c = xsub(xmul(m.index_of_refraction, 2.0f), 2.0f);
+        c = fminf(fmaxf(c, 0.0f), 1.0f);
+        float at = xmul(alpha, c);
+        s.at2 = xmul(at, at);
+        s.at2m1 = xsub(s.at2, 1.0f);
+        s.one_m_at2 = 1.0f - s.at2;
+        s.nov2_term_t = fmaf(s.nov * s.nov, s.one_m_at2, s.at2);
+    } else {
+        s.at2 = s.at2m1 = s.one_m_at2 = s.nov2_term_t = 0.0f;
+    }
+    return s;
+}
+
+// d_ggx * v_smith_ggx_correlated for one (noh, nol) — lib.rs:101-133.
+// `noh` must come from the exact chain; f is evaluated exactly, the rest fast.
+TRD float ggx_d_times_v(float noh, float nol, float nov, float a2, float a2m1, float one_m_a2, float nov2_term) {
+    float f = xadd(xmul(xmul(noh, noh), a2m1), 1.0f);
+    float d = a2 * frcp(TR_PI * f * f);
+    float ggx_v = nol * fsqrt(nov2_term);
+    float ggx_l = nov * fsqrt(fmaf(nol * nol, one_m_a2, a2));
+    float ggx = ggx_v + ggx_l;
+    float vis = ggx > 0.0f ? 0.5f * frcp(ggx) : 0.0f;
+    return d * vis;
+}
+
+// fresnel_schlick, lib.rs:137-139: f0 + (f90 - f0) * (1 - v.h)^5
+TRD f3 fresnel_schlick(float voh, f3 f0, f3 df) {
+    float x = 1.0f - voh;
+    float x2 = x * x;
+    float p = x2 * x2 * x;
+    return fma3(df, p, f0);
+}
+
+// One light through basic_brdf (lib.rs:377-423).  `l` is the unit light direction from the exact chain.
+TRD void brdf_light(const PixelShading& s, f3 l, f3 light_intensity, f3& diffuse_acc, f3& specular_acc) {
+    f3 h = xnormalize3(xadd3(s.v, l));                          // Halfway::new, lib.rs:64-68
+    float noh = fmaxf(xdot3(s.n, h), TR_F32_EPSILON);
+    // the clamped dots stay exact too: near the silhouette (n.l, n.v -> 0) the visibility term divides by them
+    float nol = fmaxf(xdot3(s.n, l), TR_F32_EPSILON);
+    float voh = fmaxf(xdot3(s.v, h), TR_F32_EPSILON);
+    f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
+    f3 li = scale3(light_intensity, nol);
+    float kd = 1.0f - max_element3(fresnel);                    // diffuse_brdf, lib.rs:356-360
+    float dv = ggx_d_times_v(noh, nol, s.nov, s.a2, s.a2m1, s.one_m_a2, s.nov2_term);
+    diffuse_acc = add3(diffuse_acc, mul3(li, scale3(s.c_diff_pi, kd)));
+    specular_acc = add3(specular_acc, mul3(li, scale3(fresnel, dv)));
+}
+
+// One light through transmission_btdf (lib.rs:200-233), unweighted.
+TRD f3 btdf_light(const PixelShading& s, f3 l) {
+    // light + 2 n dot(-light, n), lib.rs:211
+    f3 lm = xnormalize3(xadd3(l, xscale3(xscale3(s.n, 2.0f), -xdot3(l, s.n))));
+    f3 h = xnormalize3(xadd3(s.v, lm));
+    float noh = fmaxf(xdot3(s.n, h), TR_F32_EPSILON);
+    float voh = fmaxf(xdot3(s.v, h), TR_F32_EPSILON);
+    float nolm = fmaxf(xdot3(s.n, lm), TR_F32_EPSILON);
+    float dv = ggx_d_times_v(noh, nolm, s.nov, s.at2, s.at2m1, s.one_m_at2, s.nov2_term_t);
+    f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
+    f3 one_m_f = mk3(1.0f - fresnel.x, 1.0f - fresnel.y, 1.0f - fresnel.z);
+    return mul3(scale3(one_m_f, dv), s.base);
+}
+
+// light_direction_and_attenuation, lib.rs:12-23 (direction exact, attenuation fast)
+TRD void light_direction_and_attenuation(f3 fragment_position, f3 light_position, f3& direction, float& attenuation) {
+    f3 vec = xsub3(light_position, fragment_position);
+    float d2 = xdot3(vec, vec);
+    float dist = xsqrt(d2);
+    direction = xdivs3(vec, dist);
+    attenuation = frcp(d2);
+}
+
+// ---- contract-shaped wrappers (used by the tr_eval_* batch evaluators) ----
+struct BasicBrdfParams {  // lib.rs:163-169
+    f3 normal, light, light_intensity, view;
+    MaterialParams material_params;
+};
+
+TRD BrdfResult basic_brdf(const BasicBrdfParams& p) {
+    PixelShading s = make_pixel_shading(p.material_params, p.normal, p.view, false);
+    BrdfResult r;
+    r.diffuse = splat3(0.0f);
+    r.specular = splat3(0.0f);
+    brdf_light(s, p.light, p.light_intensity, r.diffuse, r.specular);
+    return r;
+}
+
+TRD f3 transmission_btdf(const MaterialParams& m, f3 normal, f3 view, f3 light) {
+    PixelShading s = make_pixel_shading(m, normal, view, true);
+    return btdf_light(s, light);
+}
+
+// ---- sampled images (oracle: oracle/shade.c) ----
+struct PyramidDesc {
+    const uint2* base;      // RGBA16F texels, all levels in one allocation
+    uint32_t levels;
+    uint32_t w[16], h[16];
+    uint32_t offset[16];    // texel offset of each level
+};
+struct LutDesc {
+    const uchar2* rg;       // R,G of the RGBA8 UNORM LUT
+    uint32_t w, h;
+};
+
+TRD void bilinear_setup(float u, uint32_t size, uint32_t& i0, uint32_t& i1, float& frac) {
+    float p = xsub(xmul(u, (float)size), 0.5f);
+    if (!(p == p)) p = 0.0f;
+    float fl = floorf(p);
+    float f = xsub(p, fl);
+    int i;
+    if (fl <= -2147483648.0f) { i = INT_MIN; f = 0.0f; }
+    else if (fl >= 2147483520.0f) { i = 2147483520; f = 0.0f; }
+    else i = (int)fl;
+    int hi = (int)size - 1;
+    i0 = (uint32_t)min(max(i, 0), hi);
+    int ip1 = i >= 2147483520 ? i : i + 1;
+    i1 = (uint32_t)min(max(ip1, 0), hi);
+    frac = f;
+}
+
+TRD f3 sample_level(const PyramidDesc& p, uint32_t level, float u, float v) {
+    uint32_t w = p.w[level], h = p.h[level];
+    const uint2* d = p.base + p.offset[level];
+    uint32_t x0, x1, y0, y1;
+    float fx, fy;
+    bilinear_setup(u, w, x0, x1, fx);
+    bilinear_setup(v, h, y0, y1, fy);
+    f4 t00 = unpack_rgba16f(__ldg(d + (size_t)y0 * w + x0));
+    f4 t10 = unpack_rgba16f(__ldg(d + (size_t)y0 * w + x1));
+    f4 t01 = unpack_rgba16f(__ldg(d + (size_t)y1 * w + x0));
+    f4 t11 = unpack_rgba16f(__ldg(d + (size_t)y1 * w + x1));
+    f3 top = lerp3(mk3(t00.x, t00.y, t00.z), mk3(t10.x, t10.y, t10.z), fx);
+    f3 bot = lerp3(mk3(t01.x, t01.y, t01.z), mk3(t11.x, t11.y, t11.z), fx);
+    return lerp3(top, bot, fy);
+}
+
+// framebuffer.sample_by_lod(clamp_sampler, uv, lod).rgb — shader/src/lib.rs:135-138
+TRD f3 sample_pyramid(const PyramidDesc& p, float u, float v, float lod) {
+    float max_lod = (float)(p.levels - 1);
+    if (!(lod > 0.0f)) lod = 0.0f;
+    if (lod > max_lod) lod = max_lod;
+    float l0f = floorf(lod);
+    uint32_t l0 = (uint32_t)l0f;
+    uint32_t l1 = l0 + 1 < p.levels ? l0 + 1 : p.levels - 1;
+    float t = lod - l0f;
+    f3 s0 = sample_level(p, l0, u, v);
+    f3 s1 = sample_level(p, l1, u, v);
+    return lerp3(s0, s1, t);
+}
+
+// textures[ggx_lut].sample(clamp_sampler, (n.v, roughness)).xy — shader/src/lib.rs:126-133
+TRD float2 sample_lut(const LutDesc& lut, float nov, float roughness) {
+    uint32_t x0, x1, y0, y1;
+    float fx, fy;
+    bilinear_setup(nov, lut.w, x0, x1, fx);
+    bilinear_setup(roughness, lut.h, y0, y1, fy);
+    uchar2 t00 = __ldg(lut.rg + (size_t)y0 * lut.w + x0);
+    uchar2 t10 = __ldg(lut.rg + (size_t)y0 * lut.w + x1);
+    uchar2 t01 = __ldg(lut.rg + (size_t)y1 * lut.w + x0);
+    uchar2 t11 = __ldg(lut.rg + (size_t)y1 * lut.w + x1);
+    const float k = 1.0f / 255.0f;
+    float ax = fmaf((float)t10.x * k - (float)t00.x * k, fx, (float)t00.x * k);
+    float bx = fmaf((float)t11.x * k - (float)t01.x * k, fx, (float)t01.x * k);
+    float ay = fmaf((float)t10.y * k - (float)t00.y * k, fx, (float)t00.y * k);
+    float by = fmaf((float)t11.y * k - (float)t01.y * k, fx, (float)t01.y * k);
+    return make_float2(fmaf(bx - ax, fy, ax), fmaf(by - ay, fy, ay));
+}
+
+struct IblVolumeRefractionParams {  // lib.rs:235-246; proj_view and log2(size_x) are per-launch constants
+    MaterialParams material_params;
+    f3 normal, view, position;
+    float thickness, model_scale, attenuation_distance;
+    f3 attenuation_colour;
+};
+
+// ibl_volume_refraction, lib.rs:292-354.  The FSamp/GSamp closures of the reference are the
+// pyramid / LUT descriptors here.  `f0`/`df` may be passed pre-computed by the caller.
+TRD f3 ibl_volume_refraction(const IblVolumeRefractionParams& p, const mat4& proj_view, float log2_size_x,
+                             const PyramidDesc& fb, const LutDesc& lut, f3 f0, f3 df) {
+    const MaterialParams& m = p.material_params;
+    // refract(-view, normal, ior), lib.rs:248-256
+    float eta = frcp(m.index_of_refraction);
+    f3 incident = neg3(p.view);
+    float ndi = dot3(p.normal, incident);
+    float k = 1.0f - eta * eta * (1.0f - ndi * ndi);
+    float t = fmaf(eta, ndi, fsqrt(k));
+    f3 refr = sub3(scale3(incident, eta), scale3(p.normal, t));
+    // get_volume_transmission_ray, lib.rs:258-268
+    float ray_length = p.thickness * p.model_scale;
+    f3 ray = scale3(normalize3(refr), ray_length);
+    f3 exit_p = add3(p.position, ray);
+    // project, lib.rs:330-332
+    float dx = fmaf(proj_view.c[3][0], 1.0f, fmaf(proj_view.c[2][0], exit_p.z, fmaf(proj_view.c[1][0], exit_p.y, proj_view.c[0][0] * exit_p.x)));
+    float dy = fmaf(proj_view.c[3][1], 1.0f, fmaf(proj_view.c[2][1], exit_p.z, fmaf(proj_view.c[1][1], exit_p.y, proj_view.c[0][1] * exit_p.x)));
+    float dw = fmaf(proj_view.c[3][3], 1.0f, fmaf(proj_view.c[2][3], exit_p.z, fmaf(proj_view.c[1][3], exit_p.y, proj_view.c[0][3] * exit_p.x)));
+    float inv_w = 1.0f / dw;
+    float tu = (dx * inv_w + 1.0f) * 0.5f;
+    float tv = (dy * inv_w + 1.0f) * 0.5f;
+    // lod, lib.rs:334-335 (PerceptualRoughness::apply_ior :158-160)
+    float lod = log2_size_x * (m.perceptual_roughness * clamp01(m.index_of_refraction * 2.0f - 2.0f));
+    f3 transmitted = sample_pyramid(fb, tu, tv, lod);
+    // apply_volume_attenuation, lib.rs:275-290
+    f3 attenuated = transmitted;
+    if (p.attenuation_distance != __int_as_float(0x7f800000)) {
+        float s = ray_length / p.attenuation_distance;
+        attenuated.x *= expf(logf(p.attenuation_colour.x) * s);
+        attenuated.y *= expf(logf(p.attenuation_colour.y) * s);
+        attenuated.z *= expf(logf(p.attenuation_colour.z) * s);
+    }
+    float nov = dot3(p.normal, p.view);  // unclamped, lib.rs:345
+    float2 brdf = sample_lut(lut, nov, m.perceptual_roughness);
+    f3 f90 = add3(f0, df);
+    f3 spec = add3(scale3(f0, brdf.x), scale3(f90, brdf.y));
+    f3 one_m = mk3(1.0f - spec.x, 1.0f - spec.y, 1.0f - spec.z);
+    return mul3(mul3(one_m, attenuated), m.diffuse_colour);
+}
+
+}  // namespace trd

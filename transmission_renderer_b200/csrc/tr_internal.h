@@ -1,0 +1,145 @@
+// tr_internal.h — context object and kernel launch prototypes behind include/tr_abi.h.
+// The context stands in for what the reference spreads over Pipelines,
+// DescriptorSets, DrawBuffers, LightBuffers and the framebuffer images
+// (src/pipelines.rs, src/descriptor_sets.rs, src/main.rs:383-504, 2381-2588).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/tr_abi.h"
+#include "tr_device_pbr.cuh"
+
+namespace tr {
+
+int32_t fail(int32_t status, const char* fmt, ...);
+#define TR_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return tr::fail(_e == cudaErrorMemoryAllocation ? TR_ERR_OOM : TR_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                           \
+    } while (0)
+#define TR_TRY(expr)                  \
+    do {                              \
+        int32_t _s = (expr);          \
+        if (_s != TR_OK) return _s;   \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int32_t ensure(size_t n);  // grow-only
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct GLayer {
+    DevBuf depth, normal, uv, material_id, scale, position;
+    bool has_position = false;
+    bool valid = false;
+};
+
+constexpr int kMaxLevels = 16;
+constexpr int kMaxPeers = 8;
+
+enum Pass { P_CULL = 0, P_LIGHTS, P_VIS, P_OPAQUE, P_GATHER, P_MIPS, P_TRANS, P_TONEMAP, P_COUNT };
+
+}  // namespace tr
+
+struct tr_ctx {
+    int device = 0;
+    uint32_t width = 0, height = 0, band_y0 = 0, band_y1 = 0, flags = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    int sm_count = 148;
+
+    tr::DevBuf instances, primitives, materials, lights;
+    uint32_t n_instances = 0, n_primitives = 0, n_materials = 0, n_lights = 0;
+    tr_uniforms uniforms{};
+    bool have_uniforms = false;
+    tr::DevBuf lut;
+    uint32_t lut_w = 0, lut_h = 0;
+    tr::DevBuf mesh_pos, mesh_nrm, mesh_uv, mesh_idx;
+    uint32_t n_vertices = 0, n_indices = 0;
+
+    // cull outputs (frustum_culling + demultiplex_draws)
+    tr::DevBuf visible_ids, cull_scalars, draws[4], tri_prefix, work_prefix;
+    uint32_t* d_instance_counts = nullptr;  // views into cull_scalars (state block of K1)
+    uint32_t* d_cull_scalars = nullptr;     // [0] n_visible [1] visible triangles [2..5] draw_counts
+    bool tri_prefix_valid = false;
+    bool cull_valid = false;
+
+    // clustered lights
+    tr::DevBuf cluster_aabbs, cluster_counts, cluster_indices;
+    uint32_t n_clusters = 0;
+    bool clusters_valid = false, cluster_lights_valid = false;
+
+    // frame targets
+    tr::GLayer layer[2];
+    tr::DevBuf vis[2], big_queue;
+    tr::DevBuf hdr, hdr_f32, pyramid, srgb8, mip_counter;
+    uint32_t levels = 0, level_w[tr::kMaxLevels] = {}, level_h[tr::kMaxLevels] = {}, level_off[tr::kMaxLevels] = {};
+    bool opaque_valid = false, mips_valid = false, hdr_valid = false, srgb_valid = false;
+
+    // timing (profiling.rs zone taxonomy)
+    bool timing = false;
+    cudaEvent_t ev_begin[tr::P_COUNT] = {}, ev_end[tr::P_COUNT] = {};
+    bool ev_used[tr::P_COUNT] = {};
+
+    // multi-GPU
+    int rank = 0, n_ranks = 1;
+    void* nccl_comm = nullptr;
+    void* peer_mip0[tr::kMaxPeers] = {};  // peer mip-0 bases (self included) for the peer-store path
+    bool peers_attached = false;
+};
+
+namespace tr {
+
+// ---- kernel launchers (each in its own .cu) ---------------------------------
+struct ShadeLaunch {
+    uint32_t width, height, px_begin, px_end;
+    const float* depth;
+    const float* normal;
+    const uint32_t* material_id;
+    const float* scale;     // transmissive layer
+    const float* position;  // optional
+    const tr_material_info* materials;
+    const tr_light* lights;
+    uint32_t n_lights;
+    const uint32_t* cluster_counts;
+    const uint32_t* cluster_indices;
+    uint32_t n_clusters;
+    tr_uniforms uniforms;
+    trd::mat4 proj_view, inv_proj_view;
+    float view_position[3];
+    uint32_t framebuffer_size_x;
+    float log2_size_x;
+    uint2* hdr;                    // RGBA16F
+    float4* hdr_f32;               // optional
+    uint2* opaque[kMaxPeers];      // sampled opaque mip 0 on this GPU [0] and, for the peer-store path, on every peer
+    int n_opaque;
+    trd::PyramidDesc pyramid;
+    trd::LutDesc lut;
+};
+
+int32_t launch_shade_opaque(const ShadeLaunch& p, int sm_count, cudaStream_t s);
+int32_t launch_shade_transmission(const ShadeLaunch& p, int sm_count, cudaStream_t s);
+int32_t launch_generate_mips(uint2* pyramid, uint32_t levels, const uint32_t* w, const uint32_t* h, const uint32_t* off,
+                             uint32_t* counter, int sm_count, cudaStream_t s);
+int32_t launch_tonemap(const uint2* hdr, uchar4* out, uint32_t px_begin, uint32_t px_end,
+                       const tr_baked_lottes_tonemapper_params& params, int sm_count, cudaStream_t s);
+int32_t launch_cull(tr_ctx* c, const tr_culling_push_constants& pc);
+int32_t launch_build_clusters(tr_ctx* c, const tr_write_cluster_data_push_constants& pc);
+int32_t launch_assign_lights(tr_ctx* c, const tr_assign_lights_push_constants& pc);
+int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc);
+int32_t launch_eval_basic_brdf(uint32_t n, const tr_basic_brdf_params* in, tr_brdf_result* out, cudaStream_t s);
+int32_t launch_eval_transmission_btdf(uint32_t n, const tr_transmission_btdf_params* in, tr_vec3* out, cudaStream_t s);
+int32_t launch_eval_ibl(uint32_t n, const trd::mat4& pv, const tr_ibl_volume_refraction_params* in, tr_vec3* out,
+                        const trd::PyramidDesc& pyr, const trd::LutDesc& lut, cudaStream_t s);
+
+void mat4_inverse_f64(const tr_mat4& m, tr_mat4* out);
+int32_t ensure_layer(tr_ctx* c, int layer, bool with_position);
+
+}  // namespace tr

@@ -1,0 +1,402 @@
+"""Procedural inputs for the BASELINE.json configs (glTF-Sample-Models is unavailable offline, so
+these stand in for src/model_loading.rs).  Everything is generated from a
+counter-based hash (splitmix64) so the same seed gives the same bytes everywhere.
+
+These are INPUT generators (host side), not part of the measured path.
+"""
+import math
+
+import numpy as np
+
+from . import abi, host
+
+f32 = np.float32
+U64 = np.uint64
+
+
+def splitmix64(x):
+    x = (np.asarray(x, dtype=U64) + U64(0x9E3779B97F4A7C15))
+    with np.errstate(over="ignore"):
+        z = x
+        z = (z ^ (z >> U64(30))) * U64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> U64(27))) * U64(0x94D049BB133111EB)
+        z = z ^ (z >> U64(31))
+    return z
+
+
+def hash01(seed, index):
+    """uniform float32 in [0,1) with a 24-bit mantissa, from splitmix64(seed ^ index)."""
+    z = splitmix64(U64(seed) ^ np.asarray(index, dtype=U64))
+    return ((z >> U64(40)).astype(np.float64) / float(1 << 24)).astype(f32)
+
+
+# --------------------------------------------------------------------------- meshes
+def uv_sphere(segments=32, rings=16):
+    """Unit UV sphere, CCW seen from outside (glTF front face)."""
+    pos, nrm, uv = [], [], []
+    for r in range(rings + 1):
+        th = math.pi * r / rings
+        for s in range(segments + 1):
+            ph = 2 * math.pi * s / segments
+            p = (math.sin(th) * math.cos(ph), math.cos(th), math.sin(th) * math.sin(ph))
+            pos.append(p)
+            nrm.append(p)
+            uv.append((s / segments, r / rings))
+    idx = []
+    for r in range(rings):
+        for s in range(segments):
+            a = r * (segments + 1) + s
+            b = a + segments + 1
+            if r != 0:
+                idx += [a, a + 1, b]
+            if r != rings - 1:
+                idx += [a + 1, b + 1, b]
+    return (np.array(pos, f32), np.array(nrm, f32), np.array(uv, f32), np.array(idx, np.uint32))
+
+
+def box_mesh():
+    pos, nrm, uv, idx = [], [], [], []
+    faces = [((1, 0, 0), (0, 1, 0), (0, 0, 1)), ((-1, 0, 0), (0, 0, 1), (0, 1, 0)), ((0, 1, 0), (0, 0, 1), (1, 0, 0)),
+             ((0, -1, 0), (1, 0, 0), (0, 0, 1)), ((0, 0, 1), (1, 0, 0), (0, 1, 0)), ((0, 0, -1), (0, 1, 0), (1, 0, 0))]
+    for n, u, v in faces:
+        n, u, v = np.array(n, f32), np.array(u, f32), np.array(v, f32)
+        base = len(pos)
+        for (a, b) in ((-1, -1), (1, -1), (1, 1), (-1, 1)):
+            pos.append(n + a * u + b * v)
+            nrm.append(n)
+            uv.append(((a + 1) / 2, (b + 1) / 2))
+        idx += [base, base + 1, base + 2, base, base + 2, base + 3]
+    return np.array(pos, f32), np.array(nrm, f32), np.array(uv, f32), np.array(idx, np.uint32)
+
+
+def quad_mesh(size=1.0):
+    """Ground quad in the xz plane facing +y."""
+    pos = np.array([(-size, 0, -size), (-size, 0, size), (size, 0, size), (size, 0, -size)], f32)
+    nrm = np.tile(np.array([(0, 1, 0)], f32), (4, 1))
+    uv = np.array([(0, 0), (0, 1), (1, 1), (1, 0)], f32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    return pos, nrm, uv, idx
+
+
+def torus_knot(p=2, q=3, n_u=512, n_v=64, tube=0.22, displacement=0.15, seed=0x5EED0003):
+    """Displaced torus knot: the "dragon-like" transmissive mesh of config 3."""
+    us = np.arange(n_u, dtype=np.float64) / n_u * 2 * math.pi
+    def centre(t):
+        r = 0.6 + 0.25 * np.cos(q * t)
+        return np.stack([r * np.cos(p * t), 0.35 * np.sin(q * t), r * np.sin(p * t)], -1)
+    c = centre(us)
+    d = centre(us + 1e-4) - c
+    T = d / np.linalg.norm(d, axis=1, keepdims=True)
+    up = np.array([0.0, 1.0, 0.0])
+    N = np.cross(T, up)
+    N /= np.linalg.norm(N, axis=1, keepdims=True)
+    B = np.cross(T, N)
+    vs = np.arange(n_v, dtype=np.float64) / n_v * 2 * math.pi
+    # smooth pseudo-fbm displacement from a few hashed harmonics
+    amp = np.zeros((n_u, n_v))
+    for k in range(1, 5):
+        a, b2, ph = hash01(seed, 3 * k), hash01(seed, 3 * k + 1), hash01(seed, 3 * k + 2)
+        amp += (0.5 ** k) * np.sin(k * (3 * us[:, None] + 2 * vs[None, :]) * (1 + float(a)) + 6.28 * float(ph)) * (0.5 + float(b2))
+    rad = tube * (1.0 + displacement / tube * 0.5 * amp)
+    ring = np.cos(vs)[None, :, None] * N[:, None, :] + np.sin(vs)[None, :, None] * B[:, None, :]
+    pos = c[:, None, :] + rad[:, :, None] * ring
+    pos = pos.reshape(-1, 3)
+    idx = []
+    for i in range(n_u):
+        for j in range(n_v):
+            a = i * n_v + j
+            b = ((i + 1) % n_u) * n_v + j
+            a1 = i * n_v + (j + 1) % n_v
+            b1 = ((i + 1) % n_u) * n_v + (j + 1) % n_v
+            idx += [a, a1, b, a1, b1, b]
+    idx = np.array(idx, np.uint32)
+    # smooth vertex normals from the faces
+    tri = idx.reshape(-1, 3)
+    fn = np.cross(pos[tri[:, 1]] - pos[tri[:, 0]], pos[tri[:, 2]] - pos[tri[:, 0]])
+    nrm = np.zeros_like(pos)
+    for k in range(3):
+        np.add.at(nrm, tri[:, k], fn)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+    # orient outward (away from the tube centre line)
+    out = pos - np.repeat(c, n_v, axis=0)
+    flip = np.sum(nrm * out, axis=1) < 0
+    if flip.mean() > 0.5:
+        nrm = -nrm
+        idx = idx.reshape(-1, 3)[:, [0, 2, 1]].reshape(-1)
+    uv = np.stack([np.repeat(np.arange(n_u) / n_u, n_v), np.tile(np.arange(n_v) / n_v, n_u)], -1)
+    return pos.astype(f32), nrm.astype(f32), uv.astype(f32), idx.astype(np.uint32)
+
+
+class MeshSet:
+    """Concatenated vertex/index arrays + one PrimitiveInfo per mesh (ModelStagingBuffers, main.rs:2495-2560)."""
+
+    def __init__(self):
+        self.pos, self.nrm, self.uv, self.idx, self.prims = [], [], [], [], []
+        self.n_vertices = 0
+        self.n_indices = 0
+
+    def add(self, mesh, draw_buffer_index):
+        pos, nrm, uv, idx = mesh
+        lo, hi = pos.min(axis=0), pos.max(axis=0)
+        centre = ((lo + hi) / 2).astype(f32)                         # model_loading.rs:148-155
+        radius = f32(np.linalg.norm((hi - lo).astype(np.float64)) / 2)
+        p = np.zeros(1, dtype=abi.primitive_info)
+        p["packed_bounding_sphere"][0] = (*centre, radius)
+        p["draw_buffer_index"] = draw_buffer_index
+        p["index_count"] = len(idx)
+        p["first_index"] = self.n_indices
+        p["first_instance"] = len(self.prims)
+        self.pos.append(pos)
+        self.nrm.append(nrm)
+        self.uv.append(uv)
+        self.idx.append(idx + np.uint32(self.n_vertices))
+        self.prims.append(p)
+        self.n_vertices += len(pos)
+        self.n_indices += len(idx)
+        return len(self.prims) - 1
+
+    def arrays(self):
+        return dict(positions=np.concatenate(self.pos), normals=np.concatenate(self.nrm), uvs=np.concatenate(self.uv),
+                    indices=np.concatenate(self.idx)), np.concatenate(self.prims)
+
+
+def make_instance(translation, scale, rotation, primitive_id, material_id):
+    i = np.zeros(1, dtype=abi.instance)
+    i["translation_and_scale"][0] = (*translation, scale)
+    i["rotation"][0] = rotation
+    i["primitive_id"] = primitive_id
+    i["material_id"] = material_id
+    return i
+
+
+# --------------------------------------------------------------------------- cameras
+class Camera:
+    def __init__(self, width, height, position=(0.0, 3.0, 1.0), yaw_deg=0.0, pitch_deg=-15.0):
+        self.width, self.height = width, height
+        self.position = np.asarray(position, f32)
+        self.view, self.rotation = host.camera_from_yaw_pitch(position, yaw_deg, pitch_deg)  # main.rs:514-526
+        self.perspective = host.perspective_matrix_reversed(width, height)
+        self.proj_view = (self.perspective.astype(f32) @ self.view.astype(f32)).astype(f32)   # main.rs:1188-1195
+
+    def push_constants(self):
+        return host.make_push_constants(self.proj_view, self.position, self.width, self.height)
+
+    def culling(self):
+        return host.make_culling_push_constants(self.view, self.perspective)
+
+    def write_cluster_data(self):
+        return host.make_write_cluster_data_push_constants(self.perspective, self.width, self.height)
+
+    def assign_lights(self):
+        return host.make_assign_lights_push_constants(self.view, self.rotation)
+
+    def frame_params(self, tonemap=None, flags=0):
+        f = np.zeros(1, dtype=abi.frame_params)
+        f["culling"] = self.culling()
+        f["assign_lights"] = self.assign_lights()
+        f["push_constants"] = self.push_constants()
+        f["tonemap"] = host.default_tonemap_params() if tonemap is None else tonemap
+        f["flags"] = flags
+        return f
+
+
+# --------------------------------------------------------------------------- config 1 (synthetic G-buffer)
+def procedural_opaque_frame(width, height, seed=0x5EED0001, checker=32):
+    """rgb = 4 * hash01(x, y, c) * checker(32 px), alpha 1 -> float32 (h, w, 4)."""
+    y, x = np.mgrid[0:height, 0:width]
+    img = np.ones((height, width, 4), dtype=f32)
+    chk = (((x // checker) + (y // checker)) & 1).astype(f32)
+    for c in range(3):
+        idx = (y.astype(np.uint64) * np.uint64(width) + x.astype(np.uint64)) * np.uint64(3) + np.uint64(c)
+        img[..., c] = f32(4.0) * hash01(seed, idx) * (f32(0.25) + f32(0.75) * chk)
+    return img
+
+
+def config1(size=512, roughness=0.25, lights=()):
+    """BASELINE configs[0]: BRDF + transmission_btdf + ibl_volume_refraction over a synthetic size^2 G-buffer,
+    one directional light (the sun), roughness 0.25 (SURVEY.md 8d "Config 1")."""
+    w = h = size
+    cam = Camera(w, h, (0.0, 3.0, 1.0), 0.0, -15.0)
+    y, x = np.mgrid[0:h, 0:w]
+    sx = ((x + 0.5) / w * 2 - 1).astype(f32)
+    sy = ((y + 0.5) / h * 2 - 1).astype(f32)
+    r2 = sx * sx + sy * sy
+    inside = r2 < 1.0
+    # keep the normals off the exact silhouette (n.v -> 0 makes the BTDF's visibility term singular)
+    nz = np.maximum(np.sqrt(np.maximum(1.0 - r2, 0.0)), 0.2).astype(f32)
+    # camera-facing basis so the disc is a sphere seen from the camera
+    right = cam.view[0, :3]
+    up = cam.view[1, :3]
+    back = cam.view[2, :3]
+    n_local = np.where(inside[..., None], np.stack([sx, -sy, nz], -1), np.array([0, 0, 1], f32))
+    n_local = n_local / np.linalg.norm(n_local, axis=-1, keepdims=True)
+    normal = (n_local[..., 0:1] * right + n_local[..., 1:2] * up + n_local[..., 2:3] * back).astype(f32)
+    centre = np.array([0.0, 2.0, 0.0], f32)
+    position = (centre + normal).astype(f32)
+    # depth of the projected position (frag_coord.z), reversed-Z
+    ph = np.concatenate([position, np.ones((h, w, 1), f32)], -1) @ cam.proj_view.T
+    depth = (ph[..., 2] / ph[..., 3]).astype(f32)
+    assert depth.min() > 0 and depth.max() < 1
+    material = abi.default_material(1)
+    material["diffuse_factor"] = (0.8, 0.8, 0.8, 1.0)
+    material["metallic_factor"] = 0.0
+    material["roughness_factor"] = roughness
+    material["index_of_refraction"] = 1.5
+    material["transmission_factor"] = 1.0
+    material["thickness_factor"] = 1.0
+    material["attenuation_distance"] = 1.0
+    material["attenuation_colour"] = (0.9, 0.4, 0.2, 0.0)
+    gbuffer = dict(depth=depth, normal=normal, uv=np.zeros((h, w, 2), f32), material_id=np.zeros((h, w), np.uint32),
+                   scale=np.ones((h, w), f32), position=position)
+    lights = np.concatenate(lights) if len(lights) else np.zeros(0, dtype=abi.light)
+    return dict(camera=cam, gbuffer=gbuffer, materials=material, lights=lights, uniforms=host.make_uniforms(w, h),
+                opaque=procedural_opaque_frame(w, h))
+
+
+# --------------------------------------------------------------------------- analytic sphere G-buffer (no rasteriser needed)
+def raycast_spheres(cam, centres, radii, material_ids, scale_plane=False):
+    """Exact ray/sphere G-buffer (nearest hit) — used to exercise K4/K6 independently of K3."""
+    w, h = cam.width, cam.height
+    inv = np.linalg.inv(cam.proj_view.astype(np.float64))
+    y, x = np.mgrid[0:h, 0:w]
+    ndc = np.stack([(x + 0.5) / w * 2 - 1, (y + 0.5) / h * 2 - 1, np.full((h, w), 0.5), np.ones((h, w))], -1)
+    pw = ndc @ inv.T
+    pw = pw[..., :3] / pw[..., 3:4]
+    o = cam.position.astype(np.float64)
+    d = pw - o
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    best_t = np.full((h, w), np.inf)
+    best = np.full((h, w), -1, dtype=np.int64)
+    for i, (c, r) in enumerate(zip(np.asarray(centres, np.float64), radii)):
+        oc = o - c
+        b = d @ oc
+        disc = b * b - (oc @ oc - r * r)
+        t = -b - np.sqrt(np.maximum(disc, 0))
+        hit = (disc > 0) & (t > 0.02) & (t < best_t)
+        best_t = np.where(hit, t, best_t)
+        best = np.where(hit, i, best)
+    covered = best >= 0
+    pos = o + d * np.where(covered, best_t, 0)[..., None]
+    cidx = np.maximum(best, 0)
+    nrm = (pos - np.asarray(centres, np.float64)[cidx]) / np.asarray(radii, np.float64)[cidx][..., None]
+    ph = np.concatenate([pos, np.ones((h, w, 1))], -1) @ cam.proj_view.astype(np.float64).T
+    depth = np.where(covered, ph[..., 2] / ph[..., 3], 0.0).astype(f32)
+    g = dict(depth=depth, normal=np.where(covered[..., None], nrm, 0).astype(f32), uv=np.zeros((h, w, 2), f32),
+             material_id=np.where(covered, np.asarray(material_ids, np.int64)[cidx], 0xFFFFFFFF).astype(np.uint32),
+             scale=np.ones((h, w), f32) if scale_plane else None, position=None)
+    return g
+
+
+def hashed_materials(n, seed, transmissive=False, roughness_range=(0.1, 0.9)):
+    m = abi.default_material(n)
+    i = np.arange(n, dtype=np.uint64) * np.uint64(8)
+    lo, hi = roughness_range
+    m["roughness_factor"] = f32(lo) + f32(hi - lo) * hash01(seed, i)
+    m["metallic_factor"] = (hash01(seed, i + np.uint64(1)) > 0.5).astype(f32) * (0.0 if transmissive else 1.0)
+    m["diffuse_factor"][:, 0] = f32(0.2) + f32(0.8) * hash01(seed, i + np.uint64(2))
+    m["diffuse_factor"][:, 1] = f32(0.2) + f32(0.8) * hash01(seed, i + np.uint64(3))
+    m["diffuse_factor"][:, 2] = f32(0.2) + f32(0.8) * hash01(seed, i + np.uint64(4))
+    if transmissive:
+        m["transmission_factor"] = 1.0
+        m["thickness_factor"] = f32(0.2) + f32(0.6) * hash01(seed, i + np.uint64(5))
+        m["attenuation_distance"] = f32(0.3) + f32(1.0) * hash01(seed, i + np.uint64(6))
+        m["attenuation_colour"][:, 0] = f32(0.3) + f32(0.7) * hash01(seed, i + np.uint64(7))
+        m["attenuation_colour"][:, 1] = f32(0.3) + f32(0.7) * hash01(seed ^ 0xABC, i)
+        m["attenuation_colour"][:, 2] = f32(0.3) + f32(0.7) * hash01(seed ^ 0xABC, i + np.uint64(1))
+    return m
+
+
+def config2_lights():
+    """The reference's two point lights (main.rs:450-453) + two more (SURVEY.md 8d "Config 2")."""
+    return np.concatenate([
+        host.light_new_point((0.0, 0.8, 0.0), (1, 0, 0), 5.0),
+        host.light_new_point((8.0, 0.8, 0.0), (0, 1, 0), 10.0),
+        host.light_new_point((-4.0, 2.0, 2.0), (1, 1, 1), 20.0),
+        host.light_new_point((4.0, 3.0, -2.0), (0.2, 0.3, 1.0), 20.0),
+    ])
+
+
+def hashed_point_lights(n, seed, box=((-30, 0.5, -30), (30, 10, 30)), intensity=(5.0, 50.0)):
+    ls = []
+    lo, hi = np.asarray(box[0], f32), np.asarray(box[1], f32)
+    for i in range(n):
+        u = hash01(seed, np.arange(8, dtype=np.uint64) + np.uint64(16 * i))
+        pos = lo + (hi - lo) * u[:3]
+        col = f32(0.3) + f32(0.7) * u[3:6]
+        inten = f32(intensity[0]) + f32(intensity[1] - intensity[0]) * u[6]
+        ls.append(host.light_new_point(pos, col, float(inten)))
+    return np.concatenate(ls) if ls else np.zeros(0, dtype=abi.light)
+
+
+# --------------------------------------------------------------------------- full scenes for the rasterised path
+def sphere_grid_scene(width, height, seed=0x5EED0002, grid=8, radius=0.4, transmissive_knot=False, ground=True):
+    """Configs 2/3: grid x grid UV spheres in front of the camera (+ ground quad, + displaced torus knot)."""
+    cam = Camera(width, height, (0.0, 3.0, 6.0), 0.0, -15.0)
+    meshes = MeshSet()
+    sphere = meshes.add(uv_sphere(32, 16), 0)
+    quad = meshes.add(quad_mesh(1.0), 0) if ground else None
+    knot = meshes.add(torus_knot(n_u=512 if transmissive_knot else 8, n_v=64 if transmissive_knot else 4), 2) if transmissive_knot else None
+    n_s = grid * grid
+    mats = [hashed_materials(n_s, seed)]
+    inst = []
+    for j in range(grid):
+        for i in range(grid):
+            k = j * grid + i
+            pos = ((i - (grid - 1) / 2) * 1.1, 0.5 + (j % 3) * 0.9 + 0.0, -(j * 1.1))
+            inst.append(make_instance(pos, radius, (0, 0, 0, 1), sphere, k))
+    n_mat = n_s
+    if ground:
+        g = abi.default_material(1)
+        g["diffuse_factor"] = (0.5, 0.5, 0.55, 1.0)
+        g["metallic_factor"] = 0.0
+        g["roughness_factor"] = 0.7
+        mats.append(g)
+        inst.append(make_instance((0.0, 0.0, -4.0), 30.0, (0, 0, 0, 1), quad, n_mat))
+        n_mat += 1
+    if transmissive_knot:
+        t = abi.default_material(1)
+        t["diffuse_factor"] = (1.0, 1.0, 1.0, 1.0)
+        t["metallic_factor"] = 0.0
+        t["roughness_factor"] = 0.25
+        t["transmission_factor"] = 1.0
+        t["thickness_factor"] = 0.5
+        t["attenuation_distance"] = 0.5
+        t["attenuation_colour"] = (0.9, 0.4, 0.2, 0.0)
+        mats.append(t)
+        inst.append(make_instance((0.0, 2.2, 2.2), 1.6, (0.0, 0.0, 0.0, 1.0), knot, n_mat))
+        n_mat += 1
+    mesh, prims = meshes.arrays()
+    return dict(camera=cam, mesh=mesh, primitives=prims, instances=np.concatenate(inst), materials=np.concatenate(mats),
+                lights=config2_lights(), uniforms=host.make_uniforms(width, height))
+
+
+def instanced_scene(width, height, n_instances=10000, n_lights=64, seed=0x5EED0004, transmissive_fraction=0.3,
+                    yaw_deg=0.0):
+    """Config 4/5: n instances of 8 primitive types in a 60x20x60 box around the camera, 30 % frosted glass,
+    hashed point lights with intensity in [5, 50] (falloff radius 10-32 m)."""
+    cam = Camera(width, height, (0.0, 6.0, 0.0), yaw_deg, -10.0)
+    meshes = MeshSet()
+    base = [uv_sphere(24, 12), box_mesh(), uv_sphere(16, 8), torus_knot(n_u=96, n_v=12, seed=seed)]
+    prim_opaque = [meshes.add(m, 0) for m in base]
+    prim_trans = [meshes.add(m, 2) for m in base]
+    n_mat_o, n_mat_t = 64, 32
+    mats = np.concatenate([hashed_materials(n_mat_o, seed), hashed_materials(n_mat_t, seed ^ 0x77, True, (0.15, 0.5))])
+    k = np.arange(n_instances, dtype=np.uint64) * np.uint64(16)
+    u = [hash01(seed, k + np.uint64(j)) for j in range(12)]
+    inst = np.zeros(n_instances, dtype=abi.instance)
+    inst["translation_and_scale"][:, 0] = (u[0] - f32(0.5)) * f32(60.0)
+    inst["translation_and_scale"][:, 1] = u[1] * f32(20.0) - f32(2.0)
+    inst["translation_and_scale"][:, 2] = (u[2] - f32(0.5)) * f32(60.0)
+    inst["translation_and_scale"][:, 3] = f32(0.25) + f32(1.75) * u[3]
+    q = np.stack([u[4] - f32(0.5), u[5] - f32(0.5), u[6] - f32(0.5), u[7] - f32(0.5)], -1).astype(np.float64)
+    q /= np.maximum(np.linalg.norm(q, axis=1, keepdims=True), 1e-9)
+    inst["rotation"] = q.astype(f32)
+    is_t = u[8] < f32(transmissive_fraction)
+    shape = np.minimum((u[9] * f32(4)).astype(np.int64), 3)
+    inst["primitive_id"] = np.where(is_t, np.asarray(prim_trans)[shape], np.asarray(prim_opaque)[shape])
+    inst["material_id"] = np.where(is_t, n_mat_o + np.minimum((u[10] * f32(n_mat_t)).astype(np.int64), n_mat_t - 1),
+                                   np.minimum((u[10] * f32(n_mat_o)).astype(np.int64), n_mat_o - 1))
+    mesh, prims = meshes.arrays()
+    lights = hashed_point_lights(n_lights, seed ^ 0x11, box=((-30, 0.5, -30), (30, 12, 30)))
+    return dict(camera=cam, mesh=mesh, primitives=prims, instances=inst, materials=mats, lights=lights,
+                uniforms=host.make_uniforms(width, height))
