@@ -461,6 +461,15 @@ TR_API int32_t tr_peer_attach(tr_ctx* ctx, int32_t rank, int32_t n_ranks, const 
 enum { TR_BUF_OPAQUE_MIP0 = 0, TR_BUF_HDR = 1, TR_BUF_SRGB8 = 2, TR_BUF_HDR_F32 = 3 };
 TR_API int32_t tr_device_buffer(tr_ctx* ctx, int32_t what, void** device_ptr, size_t* bytes);
 
+/* ------------------------------------------------------------------ */
+/* Diagnostics (benchmark support; not part of the reference surface)  */
+/* ------------------------------------------------------------------ */
+/* kernels launched by this library in this process so far */
+TR_API int32_t tr_launch_count(uint64_t* out);
+/* measured roofline denominators on the context's GPU: dependent-FFMA chains / STREAM-style copy */
+TR_API int32_t tr_measure_fp32_peak(tr_ctx* ctx, float* tflops);
+TR_API int32_t tr_measure_hbm_copy(tr_ctx* ctx, float* gbs);
+
 #ifdef __cplusplus
 }
 #endif

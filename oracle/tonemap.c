@@ -10,6 +10,9 @@
  * Defined behaviour for black pixels: the reference divides by
  * max_element(color) (tonemapping.rs:16-17), 0/0 for a black pixel; we divide
  * by max(max_element, FLT_MIN) so black stays black.
+ * Defined behaviour for non-finite / negative input: an RGBA16F store overflows to +inf above
+ * 65504 and the reference's formula then evaluates inf/inf; we clamp each input component to
+ * [0, 65504] and map NaN to 0 before tonemapping.
  * PARITY UNPINNED (oracle.h).
  */
 #include "oracle.h"
@@ -22,8 +25,14 @@ static float tonemap_inner(float x, const tr_baked_lottes_tonemapper_params* p) 
     return z / (powf(z, p->d) * p->b + p->c);
 }
 
+static float sanitize(float x) {
+    if (!(x > 0.0f)) return 0.0f; /* negative, -0, NaN */
+    return x > 65504.0f ? 65504.0f : x;
+}
+
 /* tonemapping.rs:14-25 */
 v3 orc_lottes_tonemap(v3 color, const tr_baked_lottes_tonemapper_params* p) {
+    color = v3_new(sanitize(color.x), sanitize(color.y), sanitize(color.z));
     float max = f_max(v3_max_element(color), FLT_MIN);
     v3 ratio = v3_divs(color, max);
     float tonemapped_max = tonemap_inner(max, p);

@@ -16,8 +16,9 @@ def rel_l2(got, ref):
     # non-finite values (fp16 overflow at singular silhouette pixels) must coincide
     bad = np.isfinite(ref) != np.isfinite(got)
     assert bad.mean() < 1e-5, f"non-finite mismatch on {bad.sum()} values"
+    diff = got[ok] - ref[ok]
     den = np.linalg.norm(ref[ok])
-    return float(np.linalg.norm((got - ref)[ok]) / den) if den > 0 else float(np.linalg.norm((got - ref)[ok]))
+    return float(np.linalg.norm(diff) / den) if den > 0 else float(np.linalg.norm(diff))
 
 
 def oracle_scene(pc, uniforms, materials, lights, counts, indices):

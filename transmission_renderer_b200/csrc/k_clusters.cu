@@ -153,6 +153,7 @@ int32_t launch_build_clusters(tr_ctx* c, const tr_write_cluster_data_push_consta
     TR_TRY(c->cluster_aabbs.ensure((size_t)c->n_clusters * sizeof(tr_cluster_aabb)));
     p.out = c->cluster_aabbs.as<tr_cluster_aabb>();
     cluster_aabb_kernel<<<(c->n_clusters + 127) / 128, 128, 0, c->stream>>>(p);
+    count_launches(1);
     TR_CUDA(cudaGetLastError());
     c->clusters_valid = true;
     return TR_OK;
@@ -172,6 +173,7 @@ int32_t launch_assign_lights(tr_ctx* c, const tr_assign_lights_push_constants& p
     p.indices = c->cluster_indices.as<uint32_t>();
     const uint32_t threads = 256, warps_per_block = threads / 32;
     assign_lights_kernel<<<(c->n_clusters + warps_per_block - 1) / warps_per_block, threads, 0, c->stream>>>(p);
+    count_launches(1);
     TR_CUDA(cudaGetLastError());
     c->cluster_lights_valid = true;
     return TR_OK;

@@ -222,6 +222,7 @@ int32_t launch_cull(tr_ctx* c, const tr_culling_push_constants& pc) {
     p.work_prefix = c->work_prefix.as<uint32_t>();
     p.scalars = reinterpret_cast<uint32_t*>(st + scalars_off);
     cull_kernel<<<n_blocks, CULL_THREADS, 0, c->stream>>>(p);
+    count_launches(2);
     TR_CUDA(cudaGetLastError());
 
     DemuxParams d;

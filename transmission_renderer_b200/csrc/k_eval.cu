@@ -65,12 +65,14 @@ namespace tr {
 int32_t launch_eval_basic_brdf(uint32_t n, const tr_basic_brdf_params* in, tr_brdf_result* out, cudaStream_t s) {
     if (!n) return TR_OK;
     eval_basic_brdf_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, in, out);
+    count_launches(1);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
 int32_t launch_eval_transmission_btdf(uint32_t n, const tr_transmission_btdf_params* in, tr_vec3* out, cudaStream_t s) {
     if (!n) return TR_OK;
     eval_btdf_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, in, out);
+    count_launches(1);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
@@ -78,6 +80,7 @@ int32_t launch_eval_ibl(uint32_t n, const trd::mat4& pv, const tr_ibl_volume_ref
                         const trd::PyramidDesc& pyr, const trd::LutDesc& lut, cudaStream_t s) {
     if (!n) return TR_OK;
     eval_ibl_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, pv, in, out, pyr, lut);
+    count_launches(1);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }

@@ -204,6 +204,7 @@ int32_t launch_generate_mips(uint2* pyramid, uint32_t levels, const uint32_t* w,
     dim3 grid(1, 1, 1);
     if (n_local >= 1) grid = dim3((w[0] + 63) / 64, (h[0] + 63) / 64, 1);
     mip_kernel<<<grid, 256, 0, s>>>(p);
+    count_launches(1);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }

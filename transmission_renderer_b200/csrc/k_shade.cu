@@ -337,6 +337,7 @@ int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
     uint32_t grid = (uint32_t)(sm_count * per_sm);
     if (grid > n_tiles) grid = n_tiles;
     kern<<<grid, TILE, smem, s>>>(p);
+    tr::count_launches(1);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }

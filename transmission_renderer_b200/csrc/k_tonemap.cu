@@ -1,7 +1,8 @@
 // k_tonemap.cu — K7: Lottes tonemap + sRGB8 encode (sm_100a).
 // Reference: shader/src/tonemapping.rs:9-26, fragment_tonemap shader/src/lib.rs:683-697,
 // swapchain format B8G8R8A8_SRGB src/main.rs:175 (the sRGB OETF + UNORM8 store was fixed function).
-// Black pixels: divide by max(max_element, FLT_MIN) (defined behaviour, see oracle/tonemap.c).
+// Black pixels: divide by max(max_element, FLT_MIN); inputs are clamped to [0, 65504] and NaN -> 0
+// (fp16 overflow / NaN have no defined result in the reference; see oracle/tonemap.c).
 // HBM-bound: 8 B read + 4 B written per pixel; 4 pixels per thread, 128-bit loads and stores.
 #include <float.h>
 
@@ -21,6 +22,9 @@ __device__ __forceinline__ uint32_t srgb8(float c) {
 
 __device__ __forceinline__ uint32_t tonemap_px(uint2 v, const tr_baked_lottes_tonemapper_params& p) {
     f4 c = unpack_rgba16f(v);
+    c.x = c.x > 0.0f ? fminf(c.x, 65504.0f) : 0.0f;
+    c.y = c.y > 0.0f ? fminf(c.y, 65504.0f) : 0.0f;
+    c.z = c.z > 0.0f ? fminf(c.z, 65504.0f) : 0.0f;
     float mx = fmaxf(fmaxf(c.x, fmaxf(c.y, c.z)), FLT_MIN);
     float inv = 1.0f / mx;
     float z = fpow(mx, p.a);                                  // tonemap_inner, tonemapping.rs:9-12
@@ -72,6 +76,7 @@ int32_t launch_tonemap(const uint2* hdr, uchar4* out, uint32_t px_begin, uint32_
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
     tonemap_kernel<<<blocks, 256, 0, s>>>(hdr, reinterpret_cast<uint32_t*>(out), px_begin, px_end, params);
+    count_launches(1);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -13,6 +14,8 @@
 namespace tr {
 
 static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int32_t fail(int32_t status, const char* fmt, ...) {
     va_list ap;
@@ -791,6 +794,12 @@ int32_t tr_eval_ibl_volume_refraction(tr_ctx* c, uint32_t n, const tr_mat4* proj
     return eval_batch(c, n, params, out, [&](const tr_ibl_volume_refraction_params* i, tr_vec3* o) {
         return launch_eval_ibl(n, pv, i, o, pyr, lut, c->stream);
     });
+}
+
+int32_t tr_launch_count(uint64_t* out) {
+    if (!out) return fail(TR_ERR_INVALID_ARG, "tr_launch_count: null");
+    *out = tr::g_launches.load();
+    return TR_OK;
 }
 
 int32_t tr_device_buffer(tr_ctx* c, int32_t what, void** device_ptr, size_t* bytes) {

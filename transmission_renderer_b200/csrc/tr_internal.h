@@ -15,6 +15,7 @@
 namespace tr {
 
 int32_t fail(int32_t status, const char* fmt, ...);
+void count_launches(int n);  // process-wide count of kernels this library launched (tr_launch_count)
 #define TR_CUDA(expr)                                                                              \
     do {                                                                                           \
         cudaError_t _e = (expr);                                                                   \

@@ -296,3 +296,20 @@ class Renderer:
         ptr, nbytes = C.c_void_p(), C.c_size_t(0)
         _check(_lib().tr_device_buffer(self._ctx, C.c_int32(what), C.byref(ptr), C.byref(nbytes)))
         return ptr.value, nbytes.value
+
+    # -- diagnostics -----------------------------------------------------------------------------------
+    @staticmethod
+    def launch_count():
+        n = C.c_uint64(0)
+        _check(_lib().tr_launch_count(C.byref(n)))
+        return n.value
+
+    def measure_fp32_peak(self):
+        v = C.c_float(0)
+        _check(_lib().tr_measure_fp32_peak(self._ctx, C.byref(v)))
+        return v.value
+
+    def measure_hbm_copy(self):
+        v = C.c_float(0)
+        _check(_lib().tr_measure_hbm_copy(self._ctx, C.byref(v)))
+        return v.value
