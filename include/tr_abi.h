@@ -435,6 +435,10 @@ typedef struct {
 } tr_frame_times;
 TR_API int32_t tr_enable_timing(tr_ctx* ctx, int32_t enable);
 TR_API int32_t tr_read_frame_times(tr_ctx* ctx, tr_frame_times* out);
+/* per-pass device time summed over the tr_frame calls since tr_enable_timing / the previous call
+ * (at most the last 128 frames are kept); the reference streams the same zones to Tracy once per
+ * frame (src/profiling.rs:101-131). */
+TR_API int32_t tr_read_pass_totals(tr_ctx* ctx, tr_frame_times* sum, uint32_t* n_frames);
 
 /* ------------------------------------------------------------------ */
 /* glam-pbr contract batch evaluators (device arithmetic, host buffers) */

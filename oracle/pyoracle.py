@@ -343,3 +343,48 @@ def visibility(mesh, instances, primitives, visible_ids, push_constants, y0=0, y
                          _p(b["scale"]))
     a["scale"] = None
     return a, b
+
+
+class ShadePathRunner:
+    """The per-pixel shade path (fragment -> mip chain -> fragment_transmission -> tonemap) over rows
+    [y0, y1) with every buffer preallocated, so a caller can time just the oracle's arithmetic.
+    Used by bench.py's cpu_baseline / --impl reference legs (the CPU baseline is this port, all host
+    threads via OpenMP)."""
+
+    def __init__(self, g0, g1, scene, lut_rgba8, tonemap_params, opaque_full16=None):
+        pc = scene["push_constants"]
+        self.w, self.h = int(pc["framebuffer_size"][0, 0]), int(pc["framebuffer_size"][0, 1])
+        w, h = self.w, self.h
+        self._g0, self._k0 = _gbuffer_struct(g0, w, h)
+        self._g1, self._k1 = _gbuffer_struct(g1, w, h) if g1 is not None else (None, None)
+        self._s, self._ks = _scene_struct(scene)
+        self.hdr32 = np.zeros((h, w, 4), np.float32)
+        self.hdr16 = np.zeros((h, w, 4), np.uint16)
+        # rows outside the sampled band come from `opaque_full16` when given (e.g. the GPU's opaque frame)
+        self.levels = [np.zeros((h, w, 4), np.uint16) if opaque_full16 is None else np.array(opaque_full16, np.uint16, copy=True)]
+        for _ in range(1, mip_levels_for_size(w, h)):
+            sh, sw = self.levels[-1].shape[:2]
+            self.levels.append(np.zeros((max(1, sh // 2), max(1, sw // 2), 4), np.uint16))
+        self._pyr, self._kp = make_pyramid_struct(self.levels)
+        self._lut, self._kl = make_lut_struct(lut_rgba8)
+        self._tm = _c(tonemap_params, abi.baked_lottes_tonemapper_params)
+        self.srgb8 = np.zeros((h, w, 4), np.uint8)
+
+    def opaque(self, y0, y1):
+        lib().orc_shade_opaque_frame(C.byref(self._g0), C.byref(self._s), C.c_uint32(y0), C.c_uint32(y1), _p(self.hdr32),
+                                     _p(self.hdr16), _p(self.levels[0]))
+
+    def mips(self):
+        for l in range(1, len(self.levels)):
+            src, dst = self.levels[l - 1], self.levels[l]
+            lib().orc_downsample_level(_p(src), C.c_uint32(src.shape[1]), C.c_uint32(src.shape[0]), _p(dst),
+                                       C.c_uint32(dst.shape[1]), C.c_uint32(dst.shape[0]))
+
+    def transmission(self, y0, y1):
+        if self._g1 is not None:
+            lib().orc_shade_transmission_frame(C.byref(self._g1), C.byref(self._s), C.byref(self._pyr), C.byref(self._lut),
+                                               C.c_uint32(y0), C.c_uint32(y1), _p(self.hdr32), _p(self.hdr16))
+
+    def tonemap(self, y0, y1):
+        lib().orc_tonemap_frame(_p(self.hdr16), C.c_uint32(self.w), C.c_uint32(self.h), C.c_uint32(y0), C.c_uint32(y1),
+                                _p(self._tm), _p(self.srgb8))

@@ -136,14 +136,40 @@ static trd::LutDesc lut_desc(const tr_ctx* c) {
     return d;
 }
 
+static int slot_of(const tr_ctx* c) { return (int)(c->timing_frame % kTimingRing); }
 static void pass_begin(tr_ctx* c, int pass) {
     if (!c->timing) return;
-    cudaEventRecord(c->ev_begin[pass], c->stream);
-    c->ev_used[pass] = true;
+    const int slot = (int)(c->timing_frame % kTimingRing);
+    cudaEventRecord(c->ev_begin[slot][pass], c->stream);
+    c->ev_used[slot][pass] = true;
 }
 static void pass_end(tr_ctx* c, int pass) {
     if (!c->timing) return;
-    cudaEventRecord(c->ev_end[pass], c->stream);
+    cudaEventRecord(c->ev_end[slot_of(c)][pass], c->stream);
+}
+static void timing_next_frame(tr_ctx* c) {
+    if (!c->timing) return;
+    c->timing_frame++;
+    if (c->timing_frame - c->timing_first >= (uint64_t)kTimingRing) c->timing_first = c->timing_frame - kTimingRing + 1;
+    const int slot = slot_of(c);
+    for (int i = 0; i < P_COUNT; i++) c->ev_used[slot][i] = false;
+}
+static int32_t sum_frame_times(tr_ctx* c, int slot, tr_frame_times* out) {
+    float* dst[P_COUNT] = {&out->cull_ms, &out->assign_lights_ms, &out->visibility_ms, &out->shade_opaque_ms,
+                           &out->allgather_ms, &out->mips_ms, &out->shade_transmission_ms, &out->tonemap_ms};
+    int first = -1, last = -1;
+    for (int i = 0; i < P_COUNT; i++) {
+        if (!c->ev_used[slot][i]) continue;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, c->ev_begin[slot][i], c->ev_end[slot][i]) == cudaSuccess) *dst[i] += ms;
+        if (first < 0) first = i;
+        last = i;
+    }
+    if (first >= 0) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, c->ev_begin[slot][first], c->ev_end[slot][last]) == cudaSuccess) out->total_ms += ms;
+    }
+    return first >= 0 ? 1 : 0;
 }
 
 static int32_t check_pc(const tr_ctx* c, const tr_push_constants* pc, const char* who) {
@@ -256,10 +282,6 @@ int32_t tr_create(const tr_config* config, tr_ctx** out_ctx) {
         return fail(TR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     c->stream = c->own_stream;
-    for (int i = 0; i < P_COUNT; i++) {
-        cudaEventCreate(&c->ev_begin[i]);
-        cudaEventCreate(&c->ev_end[i]);
-    }
     int32_t s = alloc_frame(c);
     if (s != TR_OK) {
         tr_destroy(c);
@@ -284,9 +306,15 @@ int32_t tr_destroy(tr_ctx* c) {
         GLayer& g = c->layer[l];
         g.depth.release(); g.normal.release(); g.uv.release(); g.material_id.release(); g.scale.release(); g.position.release();
     }
-    for (int i = 0; i < P_COUNT; i++) {
-        if (c->ev_begin[i]) cudaEventDestroy(c->ev_begin[i]);
-        if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
+    if (c->ev_begin) {
+        for (int f = 0; f < kTimingRing; f++)
+            for (int i = 0; i < P_COUNT; i++) {
+                cudaEventDestroy(c->ev_begin[f][i]);
+                cudaEventDestroy(c->ev_end[f][i]);
+            }
+        delete[] c->ev_begin;
+        delete[] c->ev_end;
+        delete[] c->ev_used;
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -530,7 +558,7 @@ int32_t tr_tonemap(tr_ctx* c, const tr_baked_lottes_tonemapper_params* params) {
 int32_t tr_frame(tr_ctx* c, const tr_frame_params* f) {
     TR_CHECK_CTX(c);
     if (!f) return fail(TR_ERR_INVALID_ARG, "tr_frame: null");
-    for (int i = 0; i < P_COUNT; i++) c->ev_used[i] = false;
+    timing_next_frame(c);
     if (!(f->flags & TR_FRAME_SKIP_VISIBILITY)) {
         TR_TRY(tr_cull(c, &f->culling));
     }
@@ -547,26 +575,42 @@ int32_t tr_frame(tr_ctx* c, const tr_frame_params* f) {
 
 int32_t tr_enable_timing(tr_ctx* c, int32_t enable) {
     TR_CHECK_CTX(c);
+    if (enable && !c->ev_begin) {
+        c->ev_begin = new (std::nothrow) cudaEvent_t[kTimingRing][P_COUNT];
+        c->ev_end = new (std::nothrow) cudaEvent_t[kTimingRing][P_COUNT];
+        c->ev_used = new (std::nothrow) bool[kTimingRing][P_COUNT]();
+        if (!c->ev_begin || !c->ev_end || !c->ev_used) return fail(TR_ERR_OOM, "tr_enable_timing: host allocation failed");
+        for (int f = 0; f < kTimingRing; f++)
+            for (int i = 0; i < P_COUNT; i++) {
+                TR_CUDA(cudaEventCreate(&c->ev_begin[f][i]));
+                TR_CUDA(cudaEventCreate(&c->ev_end[f][i]));
+            }
+    }
     c->timing = enable != 0;
+    c->timing_first = c->timing_frame + 1;  // totals restart at the next tr_frame
     return TR_OK;
 }
 
 int32_t tr_read_frame_times(tr_ctx* c, tr_frame_times* out) {
     TR_CHECK_CTX(c);
     if (!out) return fail(TR_ERR_INVALID_ARG, "tr_read_frame_times: null");
+    if (!c->ev_begin) return fail(TR_ERR_STATE, "tr_read_frame_times: timing was never enabled (tr_enable_timing)");
     TR_CUDA(cudaStreamSynchronize(c->stream));
-    float* dst[P_COUNT] = {&out->cull_ms, &out->assign_lights_ms, &out->visibility_ms, &out->shade_opaque_ms,
-                           &out->allgather_ms, &out->mips_ms, &out->shade_transmission_ms, &out->tonemap_ms};
     memset(out, 0, sizeof(*out));
-    int first = -1, last = -1;
-    for (int i = 0; i < P_COUNT; i++) {
-        if (!c->ev_used[i]) continue;
-        float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, c->ev_begin[i], c->ev_end[i]) == cudaSuccess) *dst[i] = ms;
-        if (first < 0) first = i;
-        last = i;
-    }
-    if (first >= 0) cudaEventElapsedTime(&out->total_ms, c->ev_begin[first], c->ev_end[last]);
+    sum_frame_times(c, slot_of(c), out);
+    return TR_OK;
+}
+
+int32_t tr_read_pass_totals(tr_ctx* c, tr_frame_times* sum, uint32_t* n_frames) {
+    TR_CHECK_CTX(c);
+    if (!sum || !n_frames) return fail(TR_ERR_INVALID_ARG, "tr_read_pass_totals: null");
+    if (!c->ev_begin) return fail(TR_ERR_STATE, "tr_read_pass_totals: timing was never enabled (tr_enable_timing)");
+    TR_CUDA(cudaStreamSynchronize(c->stream));
+    memset(sum, 0, sizeof(*sum));
+    uint32_t n = 0;
+    for (uint64_t f = c->timing_first; f <= c->timing_frame; f++) n += (uint32_t)sum_frame_times(c, (int)(f % kTimingRing), sum);
+    *n_frames = n;
+    c->timing_first = c->timing_frame + 1;
     return TR_OK;
 }
 

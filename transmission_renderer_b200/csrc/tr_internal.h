@@ -45,6 +45,7 @@ struct GLayer {
 
 constexpr int kMaxLevels = 16;
 constexpr int kMaxPeers = 8;
+constexpr int kTimingRing = 128;  // frames of per-pass event pairs kept (tr_read_pass_totals)
 
 enum Pass { P_CULL = 0, P_LIGHTS, P_VIS, P_OPAQUE, P_GATHER, P_MIPS, P_TRANS, P_TONEMAP, P_COUNT };
 
@@ -86,8 +87,9 @@ struct tr_ctx {
 
     // timing (profiling.rs zone taxonomy)
     bool timing = false;
-    cudaEvent_t ev_begin[tr::P_COUNT] = {}, ev_end[tr::P_COUNT] = {};
-    bool ev_used[tr::P_COUNT] = {};
+    cudaEvent_t (*ev_begin)[tr::P_COUNT] = nullptr, (*ev_end)[tr::P_COUNT] = nullptr;  // [kTimingRing][P_COUNT], lazily created
+    bool (*ev_used)[tr::P_COUNT] = nullptr;
+    uint64_t timing_frame = 0, timing_first = 0;  // current frame number / first frame not yet summed
 
     // multi-GPU
     int rank = 0, n_ranks = 1;

@@ -149,6 +149,13 @@ class Renderer:
         _check(_lib().tr_read_frame_times(self._ctx, _p(t)))
         return {k: float(t[k][0]) for k in t.dtype.names}
 
+    def pass_totals(self):
+        """(sum of per-pass ms over the frames since enable_timing / the last call, number of frames)."""
+        t = np.zeros(1, dtype=abi.frame_times)
+        n = C.c_uint32(0)
+        _check(_lib().tr_read_pass_totals(self._ctx, _p(t), C.byref(n)))
+        return {k: float(t[k][0]) for k in t.dtype.names}, n.value
+
     # -- parity hooks ------------------------------------------------------------------------
     def set_gbuffer(self, layer, gbuffer):
         npx = self.width * self.height

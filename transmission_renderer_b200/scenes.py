@@ -371,9 +371,14 @@ def sphere_grid_scene(width, height, seed=0x5EED0002, grid=8, radius=0.4, transm
 
 
 def instanced_scene(width, height, n_instances=10000, n_lights=64, seed=0x5EED0004, transmissive_fraction=0.3,
-                    yaw_deg=0.0):
+                    yaw_deg=0.0, layout="shells"):
     """Config 4/5: n instances of 8 primitive types in a 60x20x60 box around the camera, 30 % frosted glass,
-    hashed point lights with intensity in [5, 50] (falloff radius 10-32 m)."""
+    hashed point lights with intensity in [5, 50] (falloff radius 10-32 m).
+
+    layout="box"    positions stay uniform in the box (an instance next to the camera then hides everything).
+    layout="shells" positions are remapped radially about the camera: frosted glass into the 5-25 m shell,
+                    opaque instances beyond 10 m — both layers then cover ~96 % of the frame, the "2 full
+                    screens of fragments" worst case the reference's readme names (readme.md:74)."""
     cam = Camera(width, height, (0.0, 6.0, 0.0), yaw_deg, -10.0)
     meshes = MeshSet()
     base = [uv_sphere(24, 12), box_mesh(), uv_sphere(16, 8), torus_knot(n_u=96, n_v=12, seed=seed)]
@@ -388,10 +393,19 @@ def instanced_scene(width, height, n_instances=10000, n_lights=64, seed=0x5EED00
     inst["translation_and_scale"][:, 1] = u[1] * f32(20.0) - f32(2.0)
     inst["translation_and_scale"][:, 2] = (u[2] - f32(0.5)) * f32(60.0)
     inst["translation_and_scale"][:, 3] = f32(0.25) + f32(1.75) * u[3]
+    is_t = u[8] < f32(transmissive_fraction)
+    if layout == "shells":
+        c = np.asarray(cam.position, np.float64)
+        d = inst["translation_and_scale"][:, :3].astype(np.float64) - c
+        r = np.linalg.norm(d, axis=1)
+        r_max = float(np.sqrt(30.0 ** 2 + 14.0 ** 2 + 30.0 ** 2))
+        new_r = np.where(is_t, 5.0 + 20.0 * (r / r_max), r * (1.0 - 10.0 / r_max) + 10.0)
+        inst["translation_and_scale"][:, :3] = (c + d / np.maximum(r, 1e-6)[:, None] * new_r[:, None]).astype(f32)
+    elif layout != "box":
+        raise ValueError(layout)
     q = np.stack([u[4] - f32(0.5), u[5] - f32(0.5), u[6] - f32(0.5), u[7] - f32(0.5)], -1).astype(np.float64)
     q /= np.maximum(np.linalg.norm(q, axis=1, keepdims=True), 1e-9)
     inst["rotation"] = q.astype(f32)
-    is_t = u[8] < f32(transmissive_fraction)
     shape = np.minimum((u[9] * f32(4)).astype(np.int64), 3)
     inst["primitive_id"] = np.where(is_t, np.asarray(prim_trans)[shape], np.asarray(prim_opaque)[shape])
     inst["material_id"] = np.where(is_t, n_mat_o + np.minimum((u[10] * f32(n_mat_t)).astype(np.int64), n_mat_t - 1),
