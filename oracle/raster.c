@@ -106,9 +106,10 @@ static int eval_pixel(const tri_setup* s, int px, int py, float l[3], float* dep
     }
     double S = (E[0] + E[1]) + E[2];
     if (!(S > 0.0)) return 0;
-    l[0] = (float)(E[0] / S);
-    l[1] = (float)(E[1] / S);
-    l[2] = (float)(E[2] / S);
+    double r = 1.0 / S; /* one reciprocal, three products: the rule the CUDA kernel evaluates too */
+    l[0] = (float)(E[0] * r);
+    l[1] = (float)(E[1] * r);
+    l[2] = (float)(E[2] * r);
     float zq = (l[0] * s->Z[0] + l[1] * s->Z[1]) + l[2] * s->Z[2];
     float wq = (l[0] * s->W[0] + l[1] * s->W[1]) + l[2] * s->W[2];
     float d = zq / wq;

@@ -23,10 +23,9 @@ using namespace trd;
 
 namespace {
 
-constexpr int RASTER_THREADS = 128;
-constexpr int SMALL_BBOX_PIXELS = 256;
-constexpr int BIG_TILE = 64;
-constexpr uint32_t QUEUE_CAPACITY = 1u << 20;
+constexpr int TS = 64;               // tile edge in pixels
+constexpr int TILE_THREADS = 256;    // 8 warps per tile CTA
+constexpr uint32_t BIN_CAPACITY = 1u << 24;  // (triangle, tile) pairs per frame
 
 struct VisParams {
     const float* positions;
@@ -41,8 +40,18 @@ struct VisParams {
     mat4 proj_view;
     uint32_t width, height, y0, y1;
     unsigned long long* vis[2];
-    uint4* queue;                 // (slot, tri, tile_x | tile_y << 16, layer)
-    uint32_t* queue_count;        // [2]: per layer
+    // sort-middle binning state
+    uint32_t tiles_x, tiles_y, tile_row0, n_tiles;  // tile grid of the band; lists = 2 layers x n_tiles
+    uint32_t* bin_count;          // [2 * n_tiles]
+    uint32_t* bin_start;          // [2 * n_tiles + 1]
+    uint32_t* bin_cursor;         // [2 * n_tiles]
+    uint2* bin_entries;           // (slot, tri), grouped by list
+    uint32_t bin_capacity;
+    uint4* records;               // surviving triangles: (slot, tri, tile range, layer)
+    uint32_t rec_capacity;
+    uint32_t* rec_count;
+    uint32_t* tile_ticket;
+    uint32_t* status;             // bit 0: record overflow, bit 1: bin overflow
     // resolve outputs
     float* depth[2];
     float* normal[2];
@@ -142,25 +151,16 @@ __device__ __forceinline__ bool eval_pixel(const TriSetup& s, int px, int py, fl
     }
     const double S = dadd(dadd(E[0], E[1]), E[2]);
     if (!(S > 0.0)) return false;
-    l[0] = __double2float_rn(__ddiv_rn(E[0], S));
-    l[1] = __double2float_rn(__ddiv_rn(E[1], S));
-    l[2] = __double2float_rn(__ddiv_rn(E[2], S));
+    const double r = __ddiv_rn(1.0, S);
+    l[0] = __double2float_rn(dmul(E[0], r));
+    l[1] = __double2float_rn(dmul(E[1], r));
+    l[2] = __double2float_rn(dmul(E[2], r));
     const float zq = xadd(xadd(xmul(l[0], s.Z[0]), xmul(l[1], s.Z[1])), xmul(l[2], s.Z[2]));
     const float wq = xadd(xadd(xmul(l[0], s.W[0]), xmul(l[1], s.W[1])), xmul(l[2], s.W[2]));
     const float d = xdiv(zq, wq);
     if (!(d > 0.0f) || d > 1.0f) return false;
     depth = d;
     return true;
-}
-
-__device__ __forceinline__ void plot(const VisParams& p, int layer, int px, int py, float d, uint32_t gtid) {
-    const size_t i = (size_t)py * p.width + px;
-    if (layer == 1) {  // depth GREATER against the opaque depth already in the shared depth buffer
-        const float dop = __uint_as_float((uint32_t)(p.vis[0][i] >> 32));
-        if (!(d > dop)) return;
-    }
-    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xffffffffu - gtid);
-    if (p.vis[layer][i] < key) atomicMax(p.vis[layer] + i, key);
 }
 
 // conservative: can the tile [x0,x1] x [y0,y1] (pixel indices) contain a covered pixel centre?
@@ -177,71 +177,327 @@ __device__ __forceinline__ bool tile_may_overlap(const TriSetup& s, int x0, int 
     return true;
 }
 
-template <int LAYER>
-__global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const __grid_constant__ VisParams p) {
-    const uint32_t n_visible = p.scalars[0], total = p.scalars[1];
-    const uint32_t bucket = LAYER == 0 ? 0u : 2u;
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
-        // slot = largest s with work_prefix[s] <= w
-        uint32_t lo = 0, hi = n_visible;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(p.work_prefix + mid) <= w) lo = mid; else hi = mid;
+__device__ __forceinline__ uint32_t find_slot(const VisParams& p, uint32_t w, uint32_t n_visible) {
+    uint32_t lo = 0, hi = n_visible;  // largest slot with work_prefix[slot] <= w
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(p.work_prefix + mid) <= w) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// the bin lists a triangle goes to: every tile of its bounding box, edge-tested when the box spans > 4 tiles
+template <typename F>
+__device__ __forceinline__ void for_each_bin(const VisParams& p, const TriSetup* s, uint32_t range, int layer, F f) {
+    const int tx0 = range & 0xff, tx1 = (range >> 8) & 0xff, ty0 = (range >> 16) & 0xff, ty1 = range >> 24;
+    const bool test = (tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4;
+    for (int ty = ty0; ty <= ty1; ty++)
+        for (int tx = tx0; tx <= tx1; tx++) {
+            if (test) {
+                const int x0 = max(tx * TS, s->x_lo), x1 = min(tx * TS + TS - 1, s->x_hi);
+                const int y0 = max((ty + (int)p.tile_row0) * TS, s->y_lo), y1 = min((ty + (int)p.tile_row0) * TS + TS - 1, s->y_hi);
+                if (!tile_may_overlap(*s, x0, y0, x1, y1)) continue;
+            }
+            f((uint32_t)layer * p.n_tiles + (uint32_t)ty * p.tiles_x + (uint32_t)tx);
         }
-        const uint32_t slot = lo, tri = w - __ldg(p.work_prefix + slot);
-        const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
-        const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
-        if (__ldg(&prim->draw_buffer_index) != bucket) continue;
+}
+
+// ---- pass A1: set up every triangle of the visible instances once, keep the survivors (front-facing,
+// on-screen, inside the band) as compact records and count them into the per-tile bin lists.
+__global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ VisParams p) {
+    const uint32_t n_visible = p.scalars[0], total = p.scalars[1];
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < total; base += gridDim.x * blockDim.x) {
+        const uint32_t w = base + lane;
+        bool keep = false;
+        uint32_t slot = 0, tri = 0, range = 0, layer = 0;
         TriSetup s;
-        if (!setup_triangle(p, inst, prim, tri, s)) continue;
-        const int bw = s.x_hi - s.x_lo + 1, bh = s.y_hi - s.y_lo + 1;
-        if ((long long)bw * bh <= SMALL_BBOX_PIXELS) {
-            for (int py = s.y_lo; py <= s.y_hi; py++)
-                for (int px = s.x_lo; px <= s.x_hi; px++) {
-                    float l[3], d;
-                    if (eval_pixel(s, px, py, l, d)) plot(p, LAYER, px, py, d, w);
-                }
-        } else {
-            const int tx0 = s.x_lo / BIG_TILE, tx1 = s.x_hi / BIG_TILE, ty0 = s.y_lo / BIG_TILE, ty1 = s.y_hi / BIG_TILE;
-            for (int ty = ty0; ty <= ty1; ty++)
-                for (int tx = tx0; tx <= tx1; tx++) {
-                    const int x0 = max(tx * BIG_TILE, s.x_lo), x1 = min(tx * BIG_TILE + BIG_TILE - 1, s.x_hi);
-                    const int y0 = max(ty * BIG_TILE, s.y_lo), y1 = min(ty * BIG_TILE + BIG_TILE - 1, s.y_hi);
-                    if (!tile_may_overlap(s, x0, y0, x1, y1)) continue;
-                    const uint32_t q = atomicAdd(p.queue_count + LAYER, 1u);
-                    if (q < QUEUE_CAPACITY) {
-                        p.queue[(size_t)LAYER * QUEUE_CAPACITY + q] = make_uint4(slot, tri, (uint32_t)tx | ((uint32_t)ty << 16), w);
-                    } else {  // queue full: rasterise the tile here (slow but always correct)
-                        for (int py = y0; py <= y1; py++)
-                            for (int px = x0; px <= x1; px++) {
-                                float l[3], d;
-                                if (eval_pixel(s, px, py, l, d)) plot(p, LAYER, px, py, d, w);
-                            }
-                    }
-                }
+        if (w < total) {
+            slot = find_slot(p, w, n_visible);
+            tri = w - __ldg(p.work_prefix + slot);
+            const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
+            const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+            const uint32_t bucket = __ldg(&prim->draw_buffer_index);
+            layer = bucket == 0u ? 0u : 1u;
+            if ((bucket == 0u || bucket == 2u) && setup_triangle(p, inst, prim, tri, s)) {
+                keep = true;
+                range = (uint32_t)(s.x_lo / TS) | ((uint32_t)(s.x_hi / TS) << 8) |
+                        ((uint32_t)(s.y_lo / TS - (int)p.tile_row0) << 16) | ((uint32_t)(s.y_hi / TS - (int)p.tile_row0) << 24);
+                for_each_bin(p, &s, range, (int)layer, [&](uint32_t list) { atomicAdd(p.bin_count + list, 1u); });
+            }
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        if (mask) {
+            uint32_t first = 0;
+            if (lane == 0) first = atomicAdd(p.rec_count, (uint32_t)__popc(mask));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (keep) {
+                const uint32_t r = first + __popc(mask & ((1u << lane) - 1u));
+                if (r < p.rec_capacity) p.records[r] = make_uint4(slot, tri, range, layer);
+                else atomicOr(p.status, 1u);
+            }
         }
     }
 }
 
-template <int LAYER>
-__global__ void __launch_bounds__(256) raster_tiles_kernel(const __grid_constant__ VisParams p) {
-    const uint32_t n_items = min(p.queue_count[LAYER], QUEUE_CAPACITY);
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += warps) {
-        const uint4 q = p.queue[(size_t)LAYER * QUEUE_CAPACITY + item];
-        const tr_instance* inst = p.instances + __ldg(p.visible_ids + q.x);
-        const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+// ---- pass A2: exclusive scan of the bin counts (one CTA; <= 2 * 255 * 255 lists)
+__global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ VisParams p) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t n = 2u * p.n_tiles, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t chunk = 0; chunk < n; chunk += 1024) {
+        const uint32_t i = chunk + tid;
+        const uint32_t v = i < n ? p.bin_count[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t off = s_carry, tot = 0;
+        for (uint32_t k = 0; k < 32; k++) {
+            if (k < warp) off += s_warp[k];
+            tot += s_warp[k];
+        }
+        if (i < n) {
+            p.bin_start[i] = off + incl - v;
+            p.bin_cursor[i] = off + incl - v;
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        p.bin_start[n] = s_carry;
+        if (s_carry > p.bin_capacity) atomicOr(p.status, 2u);
+    }
+}
+
+// ---- pass A3: scatter the surviving triangles into their bin lists
+__global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ VisParams p) {
+    const uint32_t n = min(*p.rec_count, p.rec_capacity);
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const uint4 rec = p.records[r];
+        const int tx0 = rec.z & 0xff, tx1 = (rec.z >> 8) & 0xff, ty0 = (rec.z >> 16) & 0xff, ty1 = rec.z >> 24;
         TriSetup s;
-        if (!setup_triangle(p, inst, prim, q.y, s)) continue;
-        const int tx = q.z & 0xffff, ty = q.z >> 16;
-        const int x0 = max(tx * BIG_TILE, s.x_lo), x1 = min(tx * BIG_TILE + BIG_TILE - 1, s.x_hi);
-        const int y0 = max(ty * BIG_TILE, s.y_lo), y1 = min(ty * BIG_TILE + BIG_TILE - 1, s.y_hi);
-        const int tw = x1 - x0 + 1, n = tw * (y1 - y0 + 1);
-        for (int i = lane; i < n; i += 32) {
-            const int py = y0 + i / tw, px = x0 + i % tw;
-            float l[3], d;
-            if (eval_pixel(s, px, py, l, d)) plot(p, LAYER, px, py, d, q.w);
+        if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4) {  // the edge test needs the set-up again (rare: large triangles only)
+            const tr_instance* inst = p.instances + __ldg(p.visible_ids + rec.x);
+            const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+            setup_triangle(p, inst, prim, rec.y, s);
+        }
+        for_each_bin(p, &s, rec.z, (int)rec.w, [&](uint32_t list) {
+            const uint32_t pos = atomicAdd(p.bin_cursor + list, 1u);
+            if (pos < p.bin_capacity) p.bin_entries[pos] = make_uint2(rec.x, rec.y);
+        });
+    }
+}
+
+// ---- pass B: one CTA per (layer, 64x64 tile): the tile's depth/id words live in shared memory.
+// Each warp takes 32 triangles of the bin list at a time: lane i sets triangle i up and parks an fp32
+// "coarse" form and the exact double form in shared memory; then the warp walks the pixels of all 32
+// bounding boxes together (perfect balance whatever the box sizes).  A pixel is dropped by fp32 edge
+// functions with a rigorous error bound or by a conservative fp32 depth plane against the tile's current
+// depth; the survivors are queued and evaluated 32 at a time with the exact double rule (eval_pixel).
+struct WarpRecs {
+    double A[3][32], B[3][32], C[3][32];
+    float ea[3][32], eb[3][32], ec[3][32], ebound[3][32];
+    float d0[32], gx[32], gy[32], margin[32];
+    float Z[3][32], W[3][32];
+    uint32_t gtid[32];
+    uint32_t box[32];   // x_lo | y_lo << 6 | (bw - 1) << 12
+    uint32_t off[33];
+    uint32_t queue[64];
+};
+
+__device__ __forceinline__ void exact_sample(const VisParams& p, const WarpRecs& wr, unsigned long long* keys, uint32_t q,
+                                             int tile_x0, int tile_y0) {
+    const uint32_t j = q & 31u, lx = (q >> 5) & 63u, ly = (q >> 11) & 63u;
+    TriSetup s;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        s.A[i] = wr.A[i][j];
+        s.B[i] = wr.B[i][j];
+        s.C[i] = wr.C[i][j];
+        s.Z[i] = wr.Z[i][j];
+        s.W[i] = wr.W[i][j];
+    }
+    float l[3], d;
+    if (!eval_pixel(s, tile_x0 + (int)lx, tile_y0 + (int)ly, l, d)) return;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xffffffffu - wr.gtid[j]);
+    unsigned long long* k = keys + ly * TS + lx;
+    if (*reinterpret_cast<volatile unsigned long long*>(k) < key) atomicMax(k, key);
+}
+
+__global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __grid_constant__ VisParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    WarpRecs* recs = reinterpret_cast<WarpRecs*>(smem_raw + TS * TS * 8);
+    __shared__ uint32_t s_item, s_cursor;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WarpRecs& wr = recs[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            s_item = atomicAdd(p.tile_ticket, 1u);
+            s_cursor = 0;
+        }
+        for (uint32_t i = tid; i < TS * TS; i += TILE_THREADS) keys[i] = 0ull;
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= 2u * p.n_tiles) break;
+        const uint32_t layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
+        const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        const int tile_x0 = (int)tx * TS, tile_y0 = (int)(ty + p.tile_row0) * TS;
+        const uint32_t begin = min(p.bin_start[item], p.bin_capacity), end = min(p.bin_start[item + 1], p.bin_capacity);
+        const uint32_t count = end - begin;
+
+        while (true) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_cursor, 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= count) break;
+
+            // ---- lane i: set triangle i up, park both forms in shared memory
+            uint32_t n_samples = 0;
+            if (base + lane < count) {
+                const uint2 e = p.bin_entries[begin + base + lane];
+                const tr_instance* inst = p.instances + __ldg(p.visible_ids + e.x);
+                const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+                TriSetup s;
+                if (setup_triangle(p, inst, prim, e.y, s)) {
+                    const int x_lo = max(s.x_lo, tile_x0) - tile_x0, x_hi = min(s.x_hi, tile_x0 + TS - 1) - tile_x0;
+                    const int y_lo = max(s.y_lo, tile_y0) - tile_y0, y_hi = min(s.y_hi, tile_y0 + TS - 1) - tile_y0;
+                    if (x_lo <= x_hi && y_lo <= y_hi) {
+                        const int bw = x_hi - x_lo + 1;
+                        n_samples = (uint32_t)(bw * (y_hi - y_lo + 1));
+                        wr.box[lane] = (uint32_t)x_lo | ((uint32_t)y_lo << 6) | ((uint32_t)(bw - 1) << 12);
+                        wr.gtid[lane] = __ldg(p.work_prefix + e.x) + e.y;
+                        const double X0 = (double)tile_x0 + 0.5, Y0 = (double)tile_y0 + 0.5;
+                        double cl[3], n_a = 0.0, n_b = 0.0, n_c = 0.0, det = 0.0, absdet = 0.0;
+                        float max_z = 0.0f, min_w = s.W[0];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            wr.A[i][lane] = s.A[i];
+                            wr.B[i][lane] = s.B[i];
+                            wr.C[i][lane] = s.C[i];
+                            wr.Z[i][lane] = s.Z[i];
+                            wr.W[i][lane] = s.W[i];
+                            cl[i] = s.A[i] * X0 + s.B[i] * Y0 + s.C[i];  // edge value at the tile's first pixel centre
+                            const float fa = (float)s.A[i], fb = (float)s.B[i], fc = (float)cl[i];
+                            wr.ea[i][lane] = fa;
+                            wr.eb[i][lane] = fb;
+                            wr.ec[i][lane] = fc;
+                            // |fp32 edge value - double edge value| <= 2^-21 (64(|A|+|B|) + |c|) with a 2x reserve, plus the
+                            // rounding of the double evaluation itself (absolute coordinates)
+                            const double m = 64.0 * (fabs(s.A[i]) + fabs(s.B[i])) + fabs(cl[i]);
+                            const double m_abs = 16384.0 * (fabs(s.A[i]) + fabs(s.B[i])) + fabs(s.C[i]);
+                            wr.ebound[i][lane] = (float)(m * 4.76837158203125e-7 + m_abs * 1e-15) * 1.0001f;
+                            n_a += s.A[i] * (double)s.Z[i];
+                            n_b += s.B[i] * (double)s.Z[i];
+                            n_c += cl[i] * (double)s.Z[i];
+                            det += cl[i] * (double)s.W[i];
+                            absdet += fabs(cl[i] * (double)s.W[i]);
+                            max_z = fmaxf(max_z, fabsf(s.Z[i]));
+                            min_w = fminf(min_w, s.W[i]);
+                        }
+                        // conservative depth plane: depth(x, y) = sum_i E_i Z_i / sum_i E_i W_i and the denominator is constant
+                        float d0 = 0.0f, gx = 0.0f, gy = 0.0f, mg = __int_as_float(0x7f800000);
+                        if (min_w > 0.0f && det > 0.0 && absdet < det * 1048576.0) {
+                            const double r = 1.0 / det;
+                            d0 = (float)(n_c * r);
+                            gx = (float)(n_a * r);
+                            gy = (float)(n_b * r);
+                            mg = (fabsf(d0) + 64.0f * (fabsf(gx) + fabsf(gy))) * 1.9073486e-6f + (max_z / min_w) * 9.536743e-7f;
+                            if (!(mg == mg)) mg = __int_as_float(0x7f800000);
+                        }
+                        wr.d0[lane] = d0;
+                        wr.gx[lane] = gx;
+                        wr.gy[lane] = gy;
+                        wr.margin[lane] = mg;
+                    }
+                }
+            }
+            uint32_t incl = n_samples;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += o;
+            }
+            wr.off[lane + 1] = incl;
+            if (lane == 0) wr.off[0] = 0;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+
+            // ---- coarse walk over the pixels of all 32 boxes
+            uint32_t j = 0xffffffffu, j_end = 0, j_off = 0, qn = 0;
+            float a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0, t0 = 0, t1 = 0, t2 = 0;
+            float pd0 = 0, pgx = 0, pgy = 0, pmg = 0;
+            uint32_t bx = 0, by = 0, bw = 1, magic = 0;
+            for (uint32_t sbase = 0; sbase < total; sbase += 32) {
+                const uint32_t sidx = sbase + lane;
+                bool survive = false;
+                uint32_t q = 0;
+                if (sidx < total) {
+                    if (sidx >= j_end) {
+                        do {
+                            j++;
+                            j_end = wr.off[j + 1];
+                        } while (sidx >= j_end);
+                        j_off = wr.off[j];
+                        a0 = wr.ea[0][j]; a1 = wr.ea[1][j]; a2 = wr.ea[2][j];
+                        b0 = wr.eb[0][j]; b1 = wr.eb[1][j]; b2 = wr.eb[2][j];
+                        c0 = wr.ec[0][j]; c1 = wr.ec[1][j]; c2 = wr.ec[2][j];
+                        t0 = wr.ebound[0][j]; t1 = wr.ebound[1][j]; t2 = wr.ebound[2][j];
+                        pd0 = wr.d0[j]; pgx = wr.gx[j]; pgy = wr.gy[j]; pmg = wr.margin[j];
+                        const uint32_t box = wr.box[j];
+                        bx = box & 63u;
+                        by = (box >> 6) & 63u;
+                        bw = (box >> 12) + 1u;
+                        magic = (1048576u + bw - 1u) / bw;
+                    }
+                    const uint32_t k = sidx - j_off;
+                    const uint32_t ry = (k * magic) >> 20;
+                    const uint32_t lx = bx + (k - ry * bw), ly = by + ry;
+                    const float fx = (float)lx, fy = (float)ly;
+                    const float e0 = fmaf(a0, fx, fmaf(b0, fy, c0));
+                    const float e1 = fmaf(a1, fx, fmaf(b1, fy, c1));
+                    const float e2 = fmaf(a2, fx, fmaf(b2, fy, c2));
+                    if (!(e0 < -t0 || e1 < -t1 || e2 < -t2)) {
+                        const float cur = __uint_as_float(reinterpret_cast<volatile uint32_t*>(keys)[(ly * TS + lx) * 2 + 1]);
+                        const float dz = fmaf(pgx, fx, fmaf(pgy, fy, pd0));
+                        survive = !(dz + pmg < cur);
+                        q = j | (lx << 5) | (ly << 11);
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, survive);
+                if (survive) wr.queue[qn + __popc(m & lt_mask)] = q;
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32u) {
+                    const uint32_t mine = wr.queue[lane];
+                    const uint32_t spill = lane + 32u < qn ? wr.queue[lane + 32u] : 0u;
+                    __syncwarp();
+                    wr.queue[lane] = spill;
+                    qn -= 32u;
+                    exact_sample(p, wr, keys, mine, tile_x0, tile_y0);
+                    __syncwarp();
+                }
+            }
+            if (lane < qn) exact_sample(p, wr, keys, wr.queue[lane], tile_x0, tile_y0);
+            __syncwarp();
+        }
+
+        __syncthreads();
+        unsigned long long* out = p.vis[layer];
+        for (uint32_t i = tid; i < TS * TS; i += TILE_THREADS) {
+            const int px = tile_x0 + (int)(i & (TS - 1)), py = tile_y0 + (int)(i / TS);
+            if (px < (int)p.width && py >= (int)p.y0 && py < (int)p.y1) out[(size_t)py * p.width + px] = keys[i];
         }
     }
 }
@@ -253,7 +509,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Vi
         const uint32_t py = i / p.width, px = i - py * p.width;
 #pragma unroll
         for (int layer = 0; layer < 2; layer++) {
-            const unsigned long long key = p.vis[layer][i];
+            unsigned long long key = p.vis[layer][i];
+            // depth GREATER against the opaque depth of the shared depth buffer, applied to the nearest
+            // transmissive fragment (if that one is hidden, every other one is too)
+            if (layer == 1 && !(__uint_as_float((uint32_t)(key >> 32)) > __uint_as_float((uint32_t)(p.vis[0][i] >> 32)))) key = 0ull;
             if (key == 0ull) {
                 p.depth[layer][i] = 0.0f;
                 p.normal[layer][(size_t)i * 3] = 0.0f; p.normal[layer][(size_t)i * 3 + 1] = 0.0f; p.normal[layer][(size_t)i * 3 + 2] = 0.0f;
@@ -262,7 +521,6 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Vi
                 if (layer == 1) p.scale1[i] = 0.0f;
                 continue;
             }
-            p.vis[layer][i] = 0ull;  // clear for the next frame
             const uint32_t w = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
             uint32_t lo = 0, hi = n_visible;
             while (hi - lo > 1) {
@@ -305,17 +563,48 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     if (!c->n_indices) return fail(TR_ERR_STATE, "tr_visibility: no mesh (tr_set_mesh)");
     const size_t npx = (size_t)c->width * c->height;
     for (int l = 0; l < 2; l++) {
-        const bool fresh = c->vis[l].bytes < npx * 8;
         TR_TRY(c->vis[l].ensure(npx * 8));
-        if (fresh) TR_CUDA(cudaMemsetAsync(c->vis[l].p, 0, npx * 8, c->stream));
         TR_TRY(ensure_layer(c, l, false));
     }
-    const size_t queue_bytes = (size_t)2 * QUEUE_CAPACITY * sizeof(uint4);
-    TR_TRY(c->big_queue.ensure(queue_bytes + 16));
-    uint32_t* qcount = reinterpret_cast<uint32_t*>(c->big_queue.as<unsigned char>() + queue_bytes);
-    TR_CUDA(cudaMemsetAsync(qcount, 0, 8, c->stream));
-
+    if (!c->tri_bound_valid) {  // upper bound of the work list: every instance visible
+        uint64_t n = 0;
+        for (uint32_t pid : c->h_inst_prim) {
+            if (pid >= c->h_prim_tris.size()) return fail(TR_ERR_INVALID_ARG, "tr_visibility: an instance names primitive %u of %zu", pid, c->h_prim_tris.size());
+            n += c->h_prim_tris[pid];
+        }
+        if (n >= (1ull << 31)) return fail(TR_ERR_UNSUPPORTED, "tr_visibility: more than 2^31 triangles");
+        c->max_triangles = n;
+        c->tri_bound_valid = true;
+    }
     VisParams p{};
+    p.tiles_x = (c->width + TS - 1) / TS;
+    p.tile_row0 = c->band_y0 / TS;
+    p.tiles_y = (c->band_y1 - 1) / TS - p.tile_row0 + 1;
+    p.n_tiles = p.tiles_x * p.tiles_y;
+    if (p.tiles_x > 256 || p.tiles_y > 256) return fail(TR_ERR_UNSUPPORTED, "tr_visibility: frame larger than 16384 pixels on a side");
+    p.bin_capacity = BIN_CAPACITY;
+    p.rec_capacity = (uint32_t)(c->max_triangles ? c->max_triangles : 1);
+    TR_TRY(c->bin_entries.ensure((size_t)p.bin_capacity * sizeof(uint2)));
+    TR_TRY(c->tri_records.ensure((size_t)p.rec_capacity * sizeof(uint4)));
+    // state block: [bin_count 2T][rec_count, ticket, pad, pad][bin_start 2T+1][bin_cursor 2T]; the first two parts are zeroed per frame
+    const size_t n_lists = (size_t)2 * p.n_tiles;
+    const size_t zero_bytes = (n_lists + 4) * 4;
+    TR_TRY(c->bin_state.ensure(zero_bytes + (2 * n_lists + 1) * 4));
+    if (!c->dev_status.p) {
+        TR_TRY(c->dev_status.ensure(16));
+        TR_CUDA(cudaMemsetAsync(c->dev_status.p, 0, 16, c->stream));
+    }
+    TR_CUDA(cudaMemsetAsync(c->bin_state.p, 0, zero_bytes, c->stream));
+    uint32_t* st = c->bin_state.as<uint32_t>();
+    p.bin_count = st;
+    p.rec_count = st + n_lists;
+    p.tile_ticket = st + n_lists + 1;
+    p.bin_start = st + n_lists + 4;
+    p.bin_cursor = p.bin_start + n_lists + 1;
+    p.bin_entries = c->bin_entries.as<uint2>();
+    p.records = c->tri_records.as<uint4>();
+    p.status = c->dev_status.as<uint32_t>();
+
     p.positions = c->mesh_pos.as<float>();
     p.normals = c->mesh_nrm.as<float>();
     p.uvs = c->mesh_uv.as<float>();
@@ -330,8 +619,6 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.height = c->height;
     p.y0 = c->band_y0;
     p.y1 = c->band_y1;
-    p.queue = c->big_queue.as<uint4>();
-    p.queue_count = qcount;
     for (int l = 0; l < 2; l++) {
         p.vis[l] = c->vis[l].as<unsigned long long>();
         p.depth[l] = c->layer[l].depth.as<float>();
@@ -341,11 +628,22 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     }
     p.scale1 = c->layer[1].scale.as<float>();
 
-    const int grid = c->sm_count * 8;
-    raster_kernel<0><<<grid, RASTER_THREADS, 0, c->stream>>>(p);
-    raster_tiles_kernel<0><<<c->sm_count * 4, 256, 0, c->stream>>>(p);
-    raster_kernel<1><<<grid, RASTER_THREADS, 0, c->stream>>>(p);
-    raster_tiles_kernel<1><<<c->sm_count * 4, 256, 0, c->stream>>>(p);
+    const size_t tile_smem = (size_t)TS * TS * 8 + (size_t)(TILE_THREADS / 32) * sizeof(WarpRecs);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TR_CUDA(cudaFuncSetAttribute(raster_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+        attr_set = true;
+    }
+    int per_sm = 0;
+    TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_tiles_kernel, TILE_THREADS, tile_smem));
+    if (per_sm < 1) return fail(TR_ERR_CUDA, "raster_tiles_kernel does not fit on an SM (smem %zu)", tile_smem);
+    uint32_t tile_grid = (uint32_t)(c->sm_count * per_sm);
+    if (tile_grid > 2 * p.n_tiles) tile_grid = 2 * p.n_tiles;
+
+    bin_count_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
+    bin_scan_kernel<<<1, 1024, 0, c->stream>>>(p);
+    bin_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
+    raster_tiles_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
     resolve_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
     count_launches(5);
     TR_CUDA(cudaGetLastError());

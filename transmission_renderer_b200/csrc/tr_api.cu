@@ -232,6 +232,17 @@ static int32_t fill_shade(tr_ctx* c, const tr_push_constants* pc, int layer, Sha
     return TR_OK;
 }
 
+int32_t check_device_status(tr_ctx* c, const char* who) {
+    if (!c->dev_status.p) return TR_OK;
+    uint32_t bits = 0;
+    TR_CUDA(cudaMemcpyAsync(&bits, c->dev_status.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(cudaStreamSynchronize(c->stream));
+    if (bits == 0) return TR_OK;
+    cudaMemsetAsync(c->dev_status.p, 0, 4, c->stream);
+    return fail(TR_ERR_STATE, "%s: the visibility pass overflowed its work lists (bits %u: 1 = triangle records, 2 = tile bins); "
+                              "the G-buffer of that frame is incomplete", who, bits);
+}
+
 int32_t comm_allgather_opaque(tr_ctx* c);  // tr_comm.cu
 void comm_release(tr_ctx* c);
 
@@ -298,8 +309,8 @@ int32_t tr_destroy(tr_ctx* c) {
     comm_release(c);
     DevBuf* bufs[] = {&c->instances, &c->primitives, &c->materials, &c->lights, &c->lut, &c->mesh_pos, &c->mesh_nrm,
                       &c->mesh_uv, &c->mesh_idx, &c->visible_ids, &c->cull_scalars, &c->draws[0], &c->draws[1],
-                      &c->draws[2], &c->draws[3], &c->tri_prefix, &c->work_prefix, &c->cluster_aabbs, &c->cluster_counts,
-                      &c->cluster_indices, &c->vis[0], &c->vis[1], &c->big_queue, &c->hdr, &c->hdr_f32, &c->pyramid,
+                      &c->draws[2], &c->draws[3], &c->work_prefix, &c->cluster_aabbs, &c->cluster_counts,
+                      &c->cluster_indices, &c->vis[0], &c->vis[1], &c->bin_entries, &c->bin_state, &c->tri_records, &c->dev_status, &c->hdr, &c->hdr_f32, &c->pyramid,
                       &c->srgb8, &c->mip_counter};
     for (DevBuf* b : bufs) b->release();
     for (int l = 0; l < 2; l++) {
@@ -350,7 +361,7 @@ int32_t tr_set_stream(tr_ctx* c, void* cuda_stream) {
 int32_t tr_sync(tr_ctx* c) {
     TR_CHECK_CTX(c);
     TR_CUDA(cudaStreamSynchronize(c->stream));
-    return TR_OK;
+    return check_device_status(c, "tr_sync");
 }
 
 // ------------------------------------------------------------------ uploads
@@ -366,7 +377,9 @@ int32_t tr_set_instances(tr_ctx* c, const tr_instance* instances, uint32_t n) {
     if (n >= (1u << 24)) return fail(TR_ERR_UNSUPPORTED, "tr_set_instances: at most 2^24-1 instances");
     TR_TRY(upload(c, c->instances, instances, (size_t)n * sizeof(tr_instance)));
     c->n_instances = n;
-    c->tri_prefix_valid = false;
+    c->h_inst_prim.resize(n);
+    for (uint32_t i = 0; i < n; i++) c->h_inst_prim[i] = instances[i].primitive_id;
+    c->tri_bound_valid = false;
     c->cull_valid = false;
     return TR_OK;
 }
@@ -380,7 +393,9 @@ int32_t tr_set_primitives(tr_ctx* c, const tr_primitive_info* prims, uint32_t n)
                         i, prims[i].draw_buffer_index);
     TR_TRY(upload(c, c->primitives, prims, (size_t)n * sizeof(tr_primitive_info)));
     c->n_primitives = n;
-    c->tri_prefix_valid = false;
+    c->h_prim_tris.resize(n);
+    for (uint32_t i = 0; i < n; i++) c->h_prim_tris[i] = prims[i].index_count / 3u;
+    c->tri_bound_valid = false;
     c->cull_valid = false;
     return TR_OK;
 }
@@ -645,6 +660,7 @@ int32_t tr_read_gbuffer(tr_ctx* c, int32_t layer, const tr_gbuffer_planes_out* g
     if (!L.valid) return fail(TR_ERR_STATE, "tr_read_gbuffer: layer %d has no G-buffer", layer);
     const size_t npx = (size_t)c->width * c->height;
     TR_CUDA(cudaStreamSynchronize(c->stream));
+    TR_TRY(check_device_status(c, "tr_read_gbuffer"));
     if (g->depth) TR_CUDA(cudaMemcpy(g->depth, L.depth.p, npx * 4, cudaMemcpyDeviceToHost));
     if (g->normal) TR_CUDA(cudaMemcpy(g->normal, L.normal.p, npx * 12, cudaMemcpyDeviceToHost));
     if (g->uv) TR_CUDA(cudaMemcpy(g->uv, L.uv.p, npx * 8, cudaMemcpyDeviceToHost));

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/tr_abi.h"
 #include "tr_device_pbr.cuh"
@@ -67,10 +68,12 @@ struct tr_ctx {
     uint32_t n_vertices = 0, n_indices = 0;
 
     // cull outputs (frustum_culling + demultiplex_draws)
-    tr::DevBuf visible_ids, cull_scalars, draws[4], tri_prefix, work_prefix;
+    tr::DevBuf visible_ids, cull_scalars, draws[4], work_prefix;
     uint32_t* d_instance_counts = nullptr;  // views into cull_scalars (state block of K1)
     uint32_t* d_cull_scalars = nullptr;     // [0] n_visible [1] visible triangles [2..5] draw_counts
-    bool tri_prefix_valid = false;
+    std::vector<uint32_t> h_prim_tris, h_inst_prim;  // host copies: triangles per primitive, primitive of each instance
+    uint64_t max_triangles = 0;                      // upper bound of the visibility work list
+    bool tri_bound_valid = false;
     bool cull_valid = false;
 
     // clustered lights
@@ -80,7 +83,7 @@ struct tr_ctx {
 
     // frame targets
     tr::GLayer layer[2];
-    tr::DevBuf vis[2], big_queue;
+    tr::DevBuf vis[2], bin_entries, bin_state, tri_records, dev_status;  // sort-middle rasteriser state (k_visibility.cu)
     tr::DevBuf hdr, hdr_f32, pyramid, srgb8, mip_counter;
     uint32_t levels = 0, level_w[tr::kMaxLevels] = {}, level_h[tr::kMaxLevels] = {}, level_off[tr::kMaxLevels] = {};
     bool opaque_valid = false, mips_valid = false, hdr_valid = false, srgb_valid = false;
@@ -142,6 +145,7 @@ int32_t launch_eval_transmission_btdf(uint32_t n, const tr_transmission_btdf_par
 int32_t launch_eval_ibl(uint32_t n, const trd::mat4& pv, const tr_ibl_volume_refraction_params* in, tr_vec3* out,
                         const trd::PyramidDesc& pyr, const trd::LutDesc& lut, cudaStream_t s);
 
+int32_t check_device_status(tr_ctx* c, const char* who);  // sticky device-side error bits -> TR_ERR_STATE
 void mat4_inverse_f64(const tr_mat4& m, tr_mat4* out);
 int32_t ensure_layer(tr_ctx* c, int layer, bool with_position);
 
