@@ -18,6 +18,7 @@
  */
 #include "oracle.h"
 
+#include <math.h>
 #include <stdlib.h>
 
 typedef struct {
@@ -72,16 +73,57 @@ static int setup_triangle(const orc_mesh* mesh, const tr_instance* inst, const t
         s->B[i] = (double)s->W[a] * rx[b] - (double)rx[a] * s->W[b];
         s->C[i] = (double)rx[a] * ry[b] - (double)ry[a] * rx[b];
     }
-    /* bounding box (conservative); any vertex at/behind the camera plane => whole band */
+    /* Vulkan clip volume: w > 0 and z <= w.  A triangle with every vertex at/behind the camera plane has no
+     * fragment (eval_pixel requires w > 0). */
+    if (!(s->W[0] > 0.0f) && !(s->W[1] > 0.0f) && !(s->W[2] > 0.0f)) return 0;
+    /* bounding box (conservative) */
     int x_lo = 0, x_hi = (int)width - 1, y_lo = (int)y0, y_hi = (int)y1 - 1;
+    float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY, pad = 0.0f;
+    int whole = 0;
     if (s->W[0] > 0.0f && s->W[1] > 0.0f && s->W[2] > 0.0f) {
-        float px[3], py[3];
         for (int k = 0; k < 3; k++) {
-            px[k] = rx[k] / s->W[k];
-            py[k] = ry[k] / s->W[k];
+            float px = rx[k] / s->W[k], py = ry[k] / s->W[k];
+            mnx = f_min(mnx, px); mxx = f_max(mxx, px);
+            mny = f_min(mny, py); mxy = f_max(mxy, py);
         }
-        float mnx = f_min(px[0], f_min(px[1], px[2])), mxx = f_max(px[0], f_max(px[1], px[2]));
-        float mny = f_min(py[0], f_min(py[1], py[2])), mxy = f_max(py[0], f_max(py[1], py[2]));
+    } else {
+        /* the triangle crosses the camera plane: bound the part inside the near plane (z <= w), whose corners
+         * are the kept vertices and the edge/near-plane intersections; one pixel of padding */
+        float nd[3];
+        int inside = 0;
+        for (int k = 0; k < 3; k++) {
+            nd[k] = s->W[k] - s->Z[k];
+            if (nd[k] >= 0.0f) inside++;
+        }
+        if (inside == 0) return 0;
+        pad = 1.0f;
+        for (int k = 0; k < 3; k++) {
+            int j = (k + 1) % 3;
+            if (nd[k] >= 0.0f) {
+                if (!(s->W[k] > 0.0f)) whole = 1;
+                else {
+                    float px = rx[k] / s->W[k], py = ry[k] / s->W[k];
+                    mnx = f_min(mnx, px); mxx = f_max(mxx, px);
+                    mny = f_min(mny, py); mxy = f_max(mxy, py);
+                }
+            }
+            if ((nd[k] >= 0.0f) != (nd[j] >= 0.0f)) {
+                int a = nd[k] >= 0.0f ? k : j, b = nd[k] >= 0.0f ? j : k; /* a inside, b outside */
+                float t = nd[a] / (nd[a] - nd[b]);
+                float cx = rx[a] + t * (rx[b] - rx[a]);
+                float cy = ry[a] + t * (ry[b] - ry[a]);
+                float cw = s->W[a] + t * (s->W[b] - s->W[a]);
+                if (!(cw > 0.0f)) whole = 1;
+                else {
+                    float px = cx / cw, py = cy / cw;
+                    mnx = f_min(mnx, px); mxx = f_max(mxx, px);
+                    mny = f_min(mny, py); mxy = f_max(mxy, py);
+                }
+            }
+        }
+    }
+    if (!whole) {
+        mnx -= pad; mny -= pad; mxx += pad; mxy += pad;
         if (!(mxx >= 0.0f) || !(mnx <= (float)width) || !(mxy >= (float)y0) || !(mny <= (float)y1)) return 0;
         float fx_lo = floorf(mnx - 0.5f), fx_hi = ceilf(mxx - 0.5f);
         float fy_lo = floorf(mny - 0.5f), fy_hi = ceilf(mxy - 0.5f);
@@ -112,8 +154,9 @@ static int eval_pixel(const tri_setup* s, int px, int py, float l[3], float* dep
     l[2] = (float)(E[2] * r);
     float zq = (l[0] * s->Z[0] + l[1] * s->Z[1]) + l[2] * s->Z[2];
     float wq = (l[0] * s->W[0] + l[1] * s->W[1]) + l[2] * s->W[2];
+    if (!(wq > 0.0f)) return 0;             /* Vulkan clip volume: w > 0 ... */
     float d = zq / wq;
-    if (!(d > 0.0f) || d > 1.0f) return 0; /* Vulkan clip volume 0 <= z <= w; depth 0 is "empty" */
+    if (!(d > 0.0f) || d > 1.0f) return 0; /* ... and 0 <= z <= w; depth 0 is "empty" */
     *depth = d;
     return 1;
 }

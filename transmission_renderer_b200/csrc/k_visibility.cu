@@ -116,16 +116,62 @@ __device__ __forceinline__ bool setup_triangle(const VisParams& p, const tr_inst
         s.B[i] = dsub(dmul(s.W[a], rx[b]), dmul(rx[a], s.W[b]));
         s.C[i] = dsub(dmul(rx[a], ry[b]), dmul(ry[a], rx[b]));
     }
+    // Vulkan clip volume: w > 0 and z <= w.  Every vertex at/behind the camera plane => no fragment.
+    if (!(s.W[0] > 0.0f) && !(s.W[1] > 0.0f) && !(s.W[2] > 0.0f)) return false;
     int x_lo = 0, x_hi = (int)p.width - 1, y_lo = (int)p.y0, y_hi = (int)p.y1 - 1;
+    const float inf = __int_as_float(0x7f800000);
+    float mnx = inf, mxx = -inf, mny = inf, mxy = -inf, pad = 0.0f;
+    bool whole = false;
     if (s.W[0] > 0.0f && s.W[1] > 0.0f && s.W[2] > 0.0f) {
-        float px[3], py[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            px[k] = xdiv(rx[k], s.W[k]);
-            py[k] = xdiv(ry[k], s.W[k]);
+            const float px = xdiv(rx[k], s.W[k]), py = xdiv(ry[k], s.W[k]);
+            mnx = rmin(mnx, px); mxx = rmax(mxx, px);
+            mny = rmin(mny, py); mxy = rmax(mxy, py);
         }
-        const float mnx = rmin(px[0], rmin(px[1], px[2])), mxx = rmax(px[0], rmax(px[1], px[2]));
-        const float mny = rmin(py[0], rmin(py[1], py[2])), mxy = rmax(py[0], rmax(py[1], py[2]));
+    } else {
+        // crosses the camera plane: bound the part inside the near plane (z <= w) — oracle/raster.c setup_triangle
+        float nd[3];
+        int inside = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            nd[k] = xsub(s.W[k], s.Z[k]);
+            if (nd[k] >= 0.0f) inside++;
+        }
+        if (inside == 0) return false;
+        pad = 1.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int j = (k + 1) % 3;
+            if (nd[k] >= 0.0f) {
+                if (!(s.W[k] > 0.0f)) whole = true;
+                else {
+                    const float px = xdiv(rx[k], s.W[k]), py = xdiv(ry[k], s.W[k]);
+                    mnx = rmin(mnx, px); mxx = rmax(mxx, px);
+                    mny = rmin(mny, py); mxy = rmax(mxy, py);
+                }
+            }
+            if ((nd[k] >= 0.0f) != (nd[j] >= 0.0f)) {
+                const bool k_in = nd[k] >= 0.0f;
+                const float na = k_in ? nd[k] : nd[j], nb = k_in ? nd[j] : nd[k];
+                const float rxa = k_in ? rx[k] : rx[j], rxb = k_in ? rx[j] : rx[k];
+                const float rya = k_in ? ry[k] : ry[j], ryb = k_in ? ry[j] : ry[k];
+                const float wa = k_in ? s.W[k] : s.W[j], wb = k_in ? s.W[j] : s.W[k];
+                const float t = xdiv(na, xsub(na, nb));
+                const float cx = xadd(rxa, xmul(t, xsub(rxb, rxa)));
+                const float cy = xadd(rya, xmul(t, xsub(ryb, rya)));
+                const float cw = xadd(wa, xmul(t, xsub(wb, wa)));
+                if (!(cw > 0.0f)) whole = true;
+                else {
+                    const float px = xdiv(cx, cw), py = xdiv(cy, cw);
+                    mnx = rmin(mnx, px); mxx = rmax(mxx, px);
+                    mny = rmin(mny, py); mxy = rmax(mxy, py);
+                }
+            }
+        }
+    }
+    if (!whole) {
+        mnx = xsub(mnx, pad); mny = xsub(mny, pad); mxx = xadd(mxx, pad); mxy = xadd(mxy, pad);
         if (!(mxx >= 0.0f) || !(mnx <= (float)p.width) || !(mxy >= (float)p.y0) || !(mny <= (float)p.y1)) return false;
         const float fx_lo = floorf(xsub(mnx, 0.5f)), fx_hi = ceilf(xsub(mxx, 0.5f));
         const float fy_lo = floorf(xsub(mny, 0.5f)), fy_hi = ceilf(xsub(mxy, 0.5f));
@@ -157,6 +203,7 @@ __device__ __forceinline__ bool eval_pixel(const TriSetup& s, int px, int py, fl
     l[2] = __double2float_rn(dmul(E[2], r));
     const float zq = xadd(xadd(xmul(l[0], s.Z[0]), xmul(l[1], s.Z[1])), xmul(l[2], s.Z[2]));
     const float wq = xadd(xadd(xmul(l[0], s.W[0]), xmul(l[1], s.W[1])), xmul(l[2], s.W[2]));
+    if (!(wq > 0.0f)) return false;
     const float d = xdiv(zq, wq);
     if (!(d > 0.0f) || d > 1.0f) return false;
     depth = d;
@@ -186,20 +233,58 @@ __device__ __forceinline__ uint32_t find_slot(const VisParams& p, uint32_t w, ui
     return lo;
 }
 
-// the bin lists a triangle goes to: every tile of its bounding box, edge-tested when the box spans > 4 tiles
+// The bin lists a triangle goes to: every tile of its bounding box, edge-tested when the box spans more than
+// 4 tiles.  Called by all 32 lanes of a warp together: boxes of up to 16 tiles are walked by their own lane,
+// larger ones (a triangle crossing the camera plane spans the whole band) by the whole warp, one tile per
+// lane, so that no single thread ever walks thousands of tiles.
 template <typename F>
-__device__ __forceinline__ void for_each_bin(const VisParams& p, const TriSetup* s, uint32_t range, int layer, F f) {
+__device__ __forceinline__ void bin_triangle(const VisParams& p, bool keep, const TriSetup& s, uint32_t range, uint32_t layer,
+                                             uint2 payload, F f) {
+    const uint32_t lane = threadIdx.x & 31;
     const int tx0 = range & 0xff, tx1 = (range >> 8) & 0xff, ty0 = (range >> 16) & 0xff, ty1 = range >> 24;
-    const bool test = (tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4;
-    for (int ty = ty0; ty <= ty1; ty++)
-        for (int tx = tx0; tx <= tx1; tx++) {
-            if (test) {
-                const int x0 = max(tx * TS, s->x_lo), x1 = min(tx * TS + TS - 1, s->x_hi);
-                const int y0 = max((ty + (int)p.tile_row0) * TS, s->y_lo), y1 = min((ty + (int)p.tile_row0) * TS + TS - 1, s->y_hi);
-                if (!tile_may_overlap(*s, x0, y0, x1, y1)) continue;
-            }
-            f((uint32_t)layer * p.n_tiles + (uint32_t)ty * p.tiles_x + (uint32_t)tx);
+    const int ntx = tx1 - tx0 + 1, n_tiles = ntx * (ty1 - ty0 + 1);
+    auto visit = [&](const TriSetup& t, int tx, int ty, bool test, uint32_t lay, uint2 pl) {
+        if (test) {
+            const int x0 = max(tx * TS, t.x_lo), x1 = min(tx * TS + TS - 1, t.x_hi);
+            const int y0 = max((ty + (int)p.tile_row0) * TS, t.y_lo), y1 = min((ty + (int)p.tile_row0) * TS + TS - 1, t.y_hi);
+            if (!tile_may_overlap(t, x0, y0, x1, y1)) return;
         }
+        f(lay * p.n_tiles + (uint32_t)ty * p.tiles_x + (uint32_t)tx, pl);
+    };
+    if (keep && n_tiles <= 16)
+        for (int ty = ty0; ty <= ty1; ty++)
+            for (int tx = tx0; tx <= tx1; tx++) visit(s, tx, ty, n_tiles > 4, layer, payload);
+    uint32_t big = __ballot_sync(0xffffffffu, keep && n_tiles > 16);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        TriSetup t;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            t.A[i] = __shfl_sync(0xffffffffu, s.A[i], src);
+            t.B[i] = __shfl_sync(0xffffffffu, s.B[i], src);
+            t.C[i] = __shfl_sync(0xffffffffu, s.C[i], src);
+        }
+        t.x_lo = __shfl_sync(0xffffffffu, s.x_lo, src);
+        t.x_hi = __shfl_sync(0xffffffffu, s.x_hi, src);
+        t.y_lo = __shfl_sync(0xffffffffu, s.y_lo, src);
+        t.y_hi = __shfl_sync(0xffffffffu, s.y_hi, src);
+        const uint32_t r = __shfl_sync(0xffffffffu, range, src), lay = __shfl_sync(0xffffffffu, layer, src);
+        const uint2 pl = make_uint2(__shfl_sync(0xffffffffu, payload.x, src), __shfl_sync(0xffffffffu, payload.y, src));
+        const int bx0 = r & 0xff, bx1 = (r >> 8) & 0xff, by0 = (r >> 16) & 0xff, by1 = r >> 24;
+        const int bnx = bx1 - bx0 + 1, bn = bnx * (by1 - by0 + 1);
+        for (int i = (int)lane; i < bn; i += 32) visit(t, bx0 + i % bnx, by0 + i / bnx, true, lay, pl);
+    }
+}
+
+// slot of the first lane's work item by binary search, the other lanes walk forward from it (they are
+// almost always in the same or the next instance)
+__device__ __forceinline__ uint32_t find_slot_warp(const VisParams& p, uint32_t base, uint32_t w, uint32_t n_visible) {
+    uint32_t slot = 0;
+    if ((threadIdx.x & 31) == 0) slot = find_slot(p, base, n_visible);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    while (slot + 1 < n_visible && __ldg(p.work_prefix + slot + 1) <= w) slot++;
+    return slot;
 }
 
 // ---- pass A1: set up every triangle of the visible instances once, keep the survivors (front-facing,
@@ -211,9 +296,10 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ 
         const uint32_t w = base + lane;
         bool keep = false;
         uint32_t slot = 0, tri = 0, range = 0, layer = 0;
-        TriSetup s;
+        TriSetup s{};
+        const uint32_t wslot = find_slot_warp(p, base, min(w, total - 1), n_visible);
         if (w < total) {
-            slot = find_slot(p, w, n_visible);
+            slot = wslot;
             tri = w - __ldg(p.work_prefix + slot);
             const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
             const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
@@ -223,9 +309,9 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ 
                 keep = true;
                 range = (uint32_t)(s.x_lo / TS) | ((uint32_t)(s.x_hi / TS) << 8) |
                         ((uint32_t)(s.y_lo / TS - (int)p.tile_row0) << 16) | ((uint32_t)(s.y_hi / TS - (int)p.tile_row0) << 24);
-                for_each_bin(p, &s, range, (int)layer, [&](uint32_t list) { atomicAdd(p.bin_count + list, 1u); });
             }
         }
+        bin_triangle(p, keep, s, range, layer, make_uint2(0, 0), [&](uint32_t list, uint2) { atomicAdd(p.bin_count + list, 1u); });
         const uint32_t mask = __ballot_sync(0xffffffffu, keep);
         if (mask) {
             uint32_t first = 0;
@@ -280,54 +366,62 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 // ---- pass A3: scatter the surviving triangles into their bin lists
 __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ VisParams p) {
     const uint32_t n = min(*p.rec_count, p.rec_capacity);
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-        const uint4 rec = p.records[r];
-        const int tx0 = rec.z & 0xff, tx1 = (rec.z >> 8) & 0xff, ty0 = (rec.z >> 16) & 0xff, ty1 = rec.z >> 24;
-        TriSetup s;
-        if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4) {  // the edge test needs the set-up again (rare: large triangles only)
-            const tr_instance* inst = p.instances + __ldg(p.visible_ids + rec.x);
-            const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
-            setup_triangle(p, inst, prim, rec.y, s);
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t r = base + lane;
+        const bool keep = r < n;
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        TriSetup s{};
+        if (keep) {
+            rec = p.records[r];
+            const int tx0 = rec.z & 0xff, tx1 = (rec.z >> 8) & 0xff, ty0 = (rec.z >> 16) & 0xff, ty1 = rec.z >> 24;
+            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4) {  // the edge test needs the set-up again (large triangles only)
+                const tr_instance* inst = p.instances + __ldg(p.visible_ids + rec.x);
+                const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+                setup_triangle(p, inst, prim, rec.y, s);
+            }
         }
-        for_each_bin(p, &s, rec.z, (int)rec.w, [&](uint32_t list) {
+        bin_triangle(p, keep, s, rec.z, rec.w, make_uint2(rec.x, rec.y), [&](uint32_t list, uint2 slot_tri) {
             const uint32_t pos = atomicAdd(p.bin_cursor + list, 1u);
-            if (pos < p.bin_capacity) p.bin_entries[pos] = make_uint2(rec.x, rec.y);
+            if (pos < p.bin_capacity) p.bin_entries[pos] = slot_tri;
         });
     }
 }
 
 // ---- pass B: one CTA per (layer, 64x64 tile): the tile's depth/id words live in shared memory.
-// Each warp takes 32 triangles of the bin list at a time: lane i sets triangle i up and parks an fp32
-// "coarse" form and the exact double form in shared memory; then the warp walks the pixels of all 32
-// bounding boxes together (perfect balance whatever the box sizes).  A pixel is dropped by fp32 edge
-// functions with a rigorous error bound or by a conservative fp32 depth plane against the tile's current
-// depth; the survivors are queued and evaluated 32 at a time with the exact double rule (eval_pixel).
-struct WarpRecs {
-    double A[3][32], B[3][32], C[3][32];
-    float ea[3][32], eb[3][32], ec[3][32], ebound[3][32];
-    float d0[32], gx[32], gy[32], margin[32];
-    float Z[3][32], W[3][32];
-    uint32_t gtid[32];
-    uint32_t box[32];   // x_lo | y_lo << 6 | (bw - 1) << 12
-    uint32_t off[33];
-    uint32_t queue[64];
+// The CTA takes 256 triangles of the bin list per round: thread i sets triangle i up and parks an fp32
+// "coarse" form and the exact double form in shared memory; a CTA-wide scan of the clipped box sizes
+// then lets all 256 threads walk the pixels of all 256 boxes together (perfect balance whatever the box
+// sizes).  A pixel is dropped by fp32 edge functions with a rigorous error bound or by a conservative
+// fp32 depth plane against the tile's current depth; the survivors are queued per warp and evaluated 32
+// at a time with the exact double rule (eval_pixel), so the expensive path runs with full warps.
+constexpr int ROUND = TILE_THREADS;  // triangles per round
+struct TileRecs {
+    double A[3][ROUND], B[3][ROUND], C[3][ROUND];
+    float ea[3][ROUND], eb[3][ROUND], ec[3][ROUND], ebound[3][ROUND];
+    float d0[ROUND], gx[ROUND], gy[ROUND], margin[ROUND];
+    float Z[3][ROUND], W[3][ROUND];
+    uint32_t gtid[ROUND];
+    uint32_t box[ROUND];   // x_lo | y_lo << 6 | (bw - 1) << 12
+    uint32_t off[ROUND + 1];
+    uint32_t queue[TILE_THREADS / 32][64];
+    uint32_t warp_tot[TILE_THREADS / 32];
 };
 
-__device__ __forceinline__ void exact_sample(const VisParams& p, const WarpRecs& wr, unsigned long long* keys, uint32_t q,
-                                             int tile_x0, int tile_y0) {
-    const uint32_t j = q & 31u, lx = (q >> 5) & 63u, ly = (q >> 11) & 63u;
+__device__ __forceinline__ void exact_sample(const TileRecs& tr_, unsigned long long* keys, uint32_t q, int tile_x0, int tile_y0) {
+    const uint32_t j = q & 255u, lx = (q >> 8) & 63u, ly = (q >> 14) & 63u;
     TriSetup s;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        s.A[i] = wr.A[i][j];
-        s.B[i] = wr.B[i][j];
-        s.C[i] = wr.C[i][j];
-        s.Z[i] = wr.Z[i][j];
-        s.W[i] = wr.W[i][j];
+        s.A[i] = tr_.A[i][j];
+        s.B[i] = tr_.B[i][j];
+        s.C[i] = tr_.C[i][j];
+        s.Z[i] = tr_.Z[i][j];
+        s.W[i] = tr_.W[i][j];
     }
     float l[3], d;
     if (!eval_pixel(s, tile_x0 + (int)lx, tile_y0 + (int)ly, l, d)) return;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xffffffffu - wr.gtid[j]);
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xffffffffu - tr_.gtid[j]);
     unsigned long long* k = keys + ly * TS + lx;
     if (*reinterpret_cast<volatile unsigned long long*>(k) < key) atomicMax(k, key);
 }
@@ -335,18 +429,15 @@ __device__ __forceinline__ void exact_sample(const VisParams& p, const WarpRecs&
 __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __grid_constant__ VisParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-    WarpRecs* recs = reinterpret_cast<WarpRecs*>(smem_raw + TS * TS * 8);
-    __shared__ uint32_t s_item, s_cursor;
+    TileRecs& R = *reinterpret_cast<TileRecs*>(smem_raw + TS * TS * 8);
+    __shared__ uint32_t s_item;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpRecs& wr = recs[warp];
     const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* queue = R.queue[warp];
 
     while (true) {
         __syncthreads();
-        if (tid == 0) {
-            s_item = atomicAdd(p.tile_ticket, 1u);
-            s_cursor = 0;
-        }
+        if (tid == 0) s_item = atomicAdd(p.tile_ticket, 1u);
         for (uint32_t i = tid; i < TS * TS; i += TILE_THREADS) keys[i] = 0ull;
         __syncthreads();
         const uint32_t item = s_item;
@@ -357,16 +448,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __g
         const uint32_t begin = min(p.bin_start[item], p.bin_capacity), end = min(p.bin_start[item + 1], p.bin_capacity);
         const uint32_t count = end - begin;
 
-        while (true) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&s_cursor, 32u);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= count) break;
-
-            // ---- lane i: set triangle i up, park both forms in shared memory
+        for (uint32_t round = 0; round < count; round += ROUND) {
+            // ---- thread i: set triangle i up, park both forms in shared memory
             uint32_t n_samples = 0;
-            if (base + lane < count) {
-                const uint2 e = p.bin_entries[begin + base + lane];
+            if (round + tid < count) {
+                const uint2 e = p.bin_entries[begin + round + tid];
                 const tr_instance* inst = p.instances + __ldg(p.visible_ids + e.x);
                 const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
                 TriSetup s;
@@ -376,28 +462,27 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __g
                     if (x_lo <= x_hi && y_lo <= y_hi) {
                         const int bw = x_hi - x_lo + 1;
                         n_samples = (uint32_t)(bw * (y_hi - y_lo + 1));
-                        wr.box[lane] = (uint32_t)x_lo | ((uint32_t)y_lo << 6) | ((uint32_t)(bw - 1) << 12);
-                        wr.gtid[lane] = __ldg(p.work_prefix + e.x) + e.y;
+                        R.box[tid] = (uint32_t)x_lo | ((uint32_t)y_lo << 6) | ((uint32_t)(bw - 1) << 12);
+                        R.gtid[tid] = __ldg(p.work_prefix + e.x) + e.y;
                         const double X0 = (double)tile_x0 + 0.5, Y0 = (double)tile_y0 + 0.5;
                         double cl[3], n_a = 0.0, n_b = 0.0, n_c = 0.0, det = 0.0, absdet = 0.0;
                         float max_z = 0.0f, min_w = s.W[0];
 #pragma unroll
                         for (int i = 0; i < 3; i++) {
-                            wr.A[i][lane] = s.A[i];
-                            wr.B[i][lane] = s.B[i];
-                            wr.C[i][lane] = s.C[i];
-                            wr.Z[i][lane] = s.Z[i];
-                            wr.W[i][lane] = s.W[i];
+                            R.A[i][tid] = s.A[i];
+                            R.B[i][tid] = s.B[i];
+                            R.C[i][tid] = s.C[i];
+                            R.Z[i][tid] = s.Z[i];
+                            R.W[i][tid] = s.W[i];
                             cl[i] = s.A[i] * X0 + s.B[i] * Y0 + s.C[i];  // edge value at the tile's first pixel centre
-                            const float fa = (float)s.A[i], fb = (float)s.B[i], fc = (float)cl[i];
-                            wr.ea[i][lane] = fa;
-                            wr.eb[i][lane] = fb;
-                            wr.ec[i][lane] = fc;
+                            R.ea[i][tid] = (float)s.A[i];
+                            R.eb[i][tid] = (float)s.B[i];
+                            R.ec[i][tid] = (float)cl[i];
                             // |fp32 edge value - double edge value| <= 2^-21 (64(|A|+|B|) + |c|) with a 2x reserve, plus the
                             // rounding of the double evaluation itself (absolute coordinates)
                             const double m = 64.0 * (fabs(s.A[i]) + fabs(s.B[i])) + fabs(cl[i]);
                             const double m_abs = 16384.0 * (fabs(s.A[i]) + fabs(s.B[i])) + fabs(s.C[i]);
-                            wr.ebound[i][lane] = (float)(m * 4.76837158203125e-7 + m_abs * 1e-15) * 1.0001f;
+                            R.ebound[i][tid] = (float)(m * 4.76837158203125e-7 + m_abs * 1e-15) * 1.0001f;
                             n_a += s.A[i] * (double)s.Z[i];
                             n_b += s.B[i] * (double)s.Z[i];
                             n_c += cl[i] * (double)s.Z[i];
@@ -416,46 +501,64 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __g
                             mg = (fabsf(d0) + 64.0f * (fabsf(gx) + fabsf(gy))) * 1.9073486e-6f + (max_z / min_w) * 9.536743e-7f;
                             if (!(mg == mg)) mg = __int_as_float(0x7f800000);
                         }
-                        wr.d0[lane] = d0;
-                        wr.gx[lane] = gx;
-                        wr.gy[lane] = gy;
-                        wr.margin[lane] = mg;
+                        R.d0[tid] = d0;
+                        R.gx[tid] = gx;
+                        R.gy[tid] = gy;
+                        R.margin[tid] = mg;
                     }
                 }
             }
+            // ---- CTA-wide inclusive scan of the box sizes
             uint32_t incl = n_samples;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= (uint32_t)d) incl += o;
             }
-            wr.off[lane + 1] = incl;
-            if (lane == 0) wr.off[0] = 0;
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
+            if (lane == 31) R.warp_tot[warp] = incl;
+            __syncthreads();
+            uint32_t warp_off = 0, total = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < TILE_THREADS / 32; k++) {
+                const uint32_t t = R.warp_tot[k];
+                if (k < warp) warp_off += t;
+                total += t;
+            }
+            R.off[tid + 1] = warp_off + incl;
+            if (tid == 0) R.off[0] = 0;
+            __syncthreads();
 
-            // ---- coarse walk over the pixels of all 32 boxes
-            uint32_t j = 0xffffffffu, j_end = 0, j_off = 0, qn = 0;
+            // ---- coarse walk over the pixels of all boxes: warp w takes samples [32 (8 i + w), +32)
+            uint32_t j = 0, j_end = 0, j_off = 0, qn = 0;
             float a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0, t0 = 0, t1 = 0, t2 = 0;
             float pd0 = 0, pgx = 0, pgy = 0, pmg = 0;
             uint32_t bx = 0, by = 0, bw = 1, magic = 0;
-            for (uint32_t sbase = 0; sbase < total; sbase += 32) {
+            bool first = true;
+            for (uint32_t sbase = warp * 32u; sbase < total; sbase += TILE_THREADS) {
                 const uint32_t sidx = sbase + lane;
                 bool survive = false;
                 uint32_t q = 0;
                 if (sidx < total) {
-                    if (sidx >= j_end) {
-                        do {
-                            j++;
-                            j_end = wr.off[j + 1];
-                        } while (sidx >= j_end);
-                        j_off = wr.off[j];
-                        a0 = wr.ea[0][j]; a1 = wr.ea[1][j]; a2 = wr.ea[2][j];
-                        b0 = wr.eb[0][j]; b1 = wr.eb[1][j]; b2 = wr.eb[2][j];
-                        c0 = wr.ec[0][j]; c1 = wr.ec[1][j]; c2 = wr.ec[2][j];
-                        t0 = wr.ebound[0][j]; t1 = wr.ebound[1][j]; t2 = wr.ebound[2][j];
-                        pd0 = wr.d0[j]; pgx = wr.gx[j]; pgy = wr.gy[j]; pmg = wr.margin[j];
-                        const uint32_t box = wr.box[j];
+                    if (first || sidx >= j_end) {
+                        if (first || sidx >= R.off[min(j + 9u, (uint32_t)ROUND)]) {  // far jump: binary search for the owner of sidx
+                            uint32_t lo = first ? 0u : j, hi = ROUND;
+                            while (hi - lo > 1) {
+                                const uint32_t mid = (lo + hi) >> 1;
+                                if (R.off[mid] <= sidx) lo = mid; else hi = mid;
+                            }
+                            j = lo;
+                        } else {
+                            do { j++; } while (sidx >= R.off[j + 1]);
+                        }
+                        first = false;
+                        j_end = R.off[j + 1];
+                        j_off = R.off[j];
+                        a0 = R.ea[0][j]; a1 = R.ea[1][j]; a2 = R.ea[2][j];
+                        b0 = R.eb[0][j]; b1 = R.eb[1][j]; b2 = R.eb[2][j];
+                        c0 = R.ec[0][j]; c1 = R.ec[1][j]; c2 = R.ec[2][j];
+                        t0 = R.ebound[0][j]; t1 = R.ebound[1][j]; t2 = R.ebound[2][j];
+                        pd0 = R.d0[j]; pgx = R.gx[j]; pgy = R.gy[j]; pmg = R.margin[j];
+                        const uint32_t box = R.box[j];
                         bx = box & 63u;
                         by = (box >> 6) & 63u;
                         bw = (box >> 12) + 1u;
@@ -472,25 +575,25 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __g
                         const float cur = __uint_as_float(reinterpret_cast<volatile uint32_t*>(keys)[(ly * TS + lx) * 2 + 1]);
                         const float dz = fmaf(pgx, fx, fmaf(pgy, fy, pd0));
                         survive = !(dz + pmg < cur);
-                        q = j | (lx << 5) | (ly << 11);
+                        q = j | (lx << 8) | (ly << 14);
                     }
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, survive);
-                if (survive) wr.queue[qn + __popc(m & lt_mask)] = q;
+                if (survive) queue[qn + __popc(m & lt_mask)] = q;
                 qn += __popc(m);
                 __syncwarp();
                 if (qn >= 32u) {
-                    const uint32_t mine = wr.queue[lane];
-                    const uint32_t spill = lane + 32u < qn ? wr.queue[lane + 32u] : 0u;
+                    const uint32_t mine = queue[lane];
+                    const uint32_t spill = lane + 32u < qn ? queue[lane + 32u] : 0u;
                     __syncwarp();
-                    wr.queue[lane] = spill;
+                    queue[lane] = spill;
                     qn -= 32u;
-                    exact_sample(p, wr, keys, mine, tile_x0, tile_y0);
+                    exact_sample(R, keys, mine, tile_x0, tile_y0);
                     __syncwarp();
                 }
             }
-            if (lane < qn) exact_sample(p, wr, keys, wr.queue[lane], tile_x0, tile_y0);
-            __syncwarp();
+            if (lane < qn) exact_sample(R, keys, queue[lane], tile_x0, tile_y0);
+            __syncthreads();  // the records are rewritten by the next round
         }
 
         __syncthreads();
@@ -628,7 +731,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     }
     p.scale1 = c->layer[1].scale.as<float>();
 
-    const size_t tile_smem = (size_t)TS * TS * 8 + (size_t)(TILE_THREADS / 32) * sizeof(WarpRecs);
+    const size_t tile_smem = (size_t)TS * TS * 8 + sizeof(TileRecs);
     static bool attr_set = false;
     if (!attr_set) {
         TR_CUDA(cudaFuncSetAttribute(raster_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
