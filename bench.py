@@ -290,16 +290,9 @@ def run_b200(args, wl):
     m = scene["mesh"]
     r.set_mesh(m["positions"], m["normals"], m["uvs"], m["indices"])
     r.build_clusters(cam.write_cluster_data())
-    exchange = "none"
-    if world > 1:
-        uid = [Renderer.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0, group=cpu_group)
-        r.comm_init(uid[0], rank, world)
-        exchange = args.exchange
-        if exchange == "peer":
-            handles = [None] * world
-            dist.all_gather_object(handles, r.peer_export(), group=cpu_group)
-            r.peer_attach(rank, world, b"".join(handles))
+    exchange = args.exchange if world > 1 else "none"
+    from transmission_renderer_b200 import parallel
+    parallel.init_bands(r, rank, world, group=cpu_group, exchange=args.exchange)
     y0, y1 = host.band_rows(H, rank, world)
     fp = cam.frame_params(host.default_tonemap_params())
 

@@ -244,6 +244,7 @@ int32_t check_device_status(tr_ctx* c, const char* who) {
 }
 
 int32_t comm_allgather_opaque(tr_ctx* c);  // tr_comm.cu
+int32_t comm_barrier(tr_ctx* c);
 void comm_release(tr_ctx* c);
 
 }  // namespace tr
@@ -579,9 +580,11 @@ int32_t tr_frame(tr_ctx* c, const tr_frame_params* f) {
     }
     if (c->n_lights) TR_TRY(tr_assign_lights(c, &f->assign_lights));
     if (!(f->flags & TR_FRAME_SKIP_VISIBILITY)) TR_TRY(tr_visibility(c, &f->push_constants));
+    // peer-store path: a peer's opaque pass writes into THIS rank's mip 0, which the previous frame's transmissive
+    // pass may still be sampling -> cross-GPU barrier before anybody starts shading
+    if (c->n_ranks > 1 && c->peers_attached) TR_TRY(comm_barrier(c));
     TR_TRY(tr_shade_opaque(c, &f->push_constants));
-    if (c->n_ranks > 1 && !c->peers_attached) TR_TRY(tr_allgather_opaque(c));
-    if (c->n_ranks > 1 && c->peers_attached) TR_TRY(tr_allgather_opaque(c));  // peer path: barrier only
+    if (c->n_ranks > 1) TR_TRY(tr_allgather_opaque(c));  // NCCL all-gather, or (peer path) the barrier that ends the exchange
     TR_TRY(tr_generate_mips(c));
     if (c->layer[TR_LAYER_TRANSMISSIVE].valid) TR_TRY(tr_shade_transmission(c, &f->push_constants));
     if (!(f->flags & TR_FRAME_SKIP_TONEMAP)) TR_TRY(tr_tonemap(c, &f->tonemap));

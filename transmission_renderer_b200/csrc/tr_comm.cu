@@ -74,17 +74,21 @@ static void band_of(const tr_ctx* c, int r, uint32_t* y0, uint32_t* y1) {
     *y1 = (uint32_t)(((uint64_t)(r + 1) * c->height) / c->n_ranks);
 }
 
+// cross-GPU barrier on the context's stream: a 4-byte all-reduce
+int32_t comm_barrier(tr_ctx* c) {
+    if (c->n_ranks <= 1) return TR_OK;
+    if (!c->nccl_comm) return fail(TR_ERR_STATE, "communicator not initialised (tr_comm_init)");
+    uint32_t* scratch = c->mip_counter.as<uint32_t>() + 2;
+    int rc = g_nccl.all_reduce(scratch, scratch, 1, kNcclInt32, kNcclSum, c->nccl_comm, c->stream);
+    if (rc) return nccl_fail("ncclAllReduce", rc);
+    return TR_OK;
+}
+
 int32_t comm_allgather_opaque(tr_ctx* c) {
     if (c->n_ranks <= 1) return TR_OK;
     if (!c->nccl_comm) return fail(TR_ERR_STATE, "tr_allgather_opaque: communicator not initialised (tr_comm_init)");
-    if (c->peers_attached) {
-        // peer-store path: bands are already in place everywhere once every rank's K4 has retired;
-        // a 4-byte all-reduce on the same stream is the cross-GPU barrier.
-        uint32_t* scratch = c->mip_counter.as<uint32_t>() + 2;
-        int rc = g_nccl.all_reduce(scratch, scratch, 1, kNcclInt32, kNcclSum, c->nccl_comm, c->stream);
-        if (rc) return nccl_fail("ncclAllReduce", rc);
-        return TR_OK;
-    }
+    // peer-store path: bands are already in place everywhere once every rank's K4 has retired
+    if (c->peers_attached) return comm_barrier(c);
     uint8_t* mip0 = reinterpret_cast<uint8_t*>(c->pyramid.as<uint2>() + c->level_off[0]);
     const size_t row = (size_t)c->width * 8;
     if (c->height % c->n_ranks == 0) {
