@@ -240,17 +240,19 @@ __global__ void __launch_bounds__(TILE) shade_kernel(const __grid_constant__ tr:
             if (lights_in_smem) l = s_lights[m];
             else l = make_light_s(p.lights, m);
             if (next == m) {
-                f3 dir;
-                float att;
-                light_direction_and_attenuation(pos, mk3(l.px, l.py, l.pz), dir, att);
-                float factor = att;
+                // light_direction_and_attenuation (glam-pbr lib.rs:12-23), fast regime; the exact chain is re-derived
+                // from `vec` inside the BRDF only where it matters (tr_device_pbr.cuh "adaptive exactness")
+                const f3 vec = sub3(mk3(l.px, l.py, l.pz), pos);
+                const float inv_d = frsqrt(dot3(vec, vec));
+                const f3 dir = scale3(vec, inv_d);
+                float factor = inv_d * inv_d;
                 if (!TRANS && l.is_spot) {  // lighting.rs:201-203; the transmissive loop has no spotlight factor (:58-92)
                     float theta = -dot3(dir, mk3(l.sx, l.sy, l.sz));
                     factor *= fmaxf((theta - l.cos_outer) * l.inv_eps, 0.0f);
                 }
                 f3 li = scale3(mk3(l.er, l.eg, l.eb), factor);
-                brdf_light(ps, dir, li, diff, spec);
-                if (TRANS) trans = add3(trans, mul3(li, btdf_light(ps, dir)));
+                brdf_point_light(ps, vec, dir, li, diff, spec);
+                if (TRANS) trans = add3(trans, mul3(li, btdf_point_light(ps, vec, dir)));
                 my_i++;
                 next = my_i < my_count ? __ldg(p.cluster_indices + my_base + my_i) : 0xffffffffu;
             }
