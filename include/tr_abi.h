@@ -427,6 +427,11 @@ TR_API int32_t tr_read_hdr(tr_ctx* ctx, uint16_t* rgba16f);              /* hdr_
 TR_API int32_t tr_read_hdr_f32(tr_ctx* ctx, float* rgba32f);             /* needs TR_FLAG_HDR_F32_DEBUG */
 TR_API int32_t tr_read_pyramid_level(tr_ctx* ctx, uint32_t level, uint16_t* rgba16f, uint32_t* w, uint32_t* h);
 TR_API int32_t tr_read_srgb8(tr_ctx* ctx, uint8_t* rgba8);
+/* Same band copy, enqueued on a copy stream behind the frame just recorded, so it overlaps the next tr_frame (the
+ * reference presents frame n while recording frame n+1, src/main.rs:1389-1403).  `rgba8` should be pinned and must stay
+ * valid until tr_wait_readback / tr_sync returns. */
+TR_API int32_t tr_read_srgb8_async(tr_ctx* ctx, uint8_t* rgba8);
+TR_API int32_t tr_wait_readback(tr_ctx* ctx);
 TR_API int32_t tr_mip_levels(tr_ctx* ctx, uint32_t* levels);
 /* per-pass device time of the last tr_frame (profiling.rs zone taxonomy). */
 typedef struct {
@@ -470,6 +475,9 @@ TR_API int32_t tr_device_buffer(tr_ctx* ctx, int32_t what, void** device_ptr, si
 /* ------------------------------------------------------------------ */
 /* kernels launched by this library in this process so far */
 TR_API int32_t tr_launch_count(uint64_t* out);
+/* rasteriser work since the last reset: [0] box pixels binned to tiles, [1] box pixels left after hierarchical Z,
+ * [2] exact (double) coverage evaluations, [3] reserved */
+TR_API int32_t tr_raster_stats(tr_ctx* ctx, uint64_t out[4], int32_t reset);
 /* measured roofline denominators on the context's GPU: dependent-FFMA chains / STREAM-style copy */
 TR_API int32_t tr_measure_fp32_peak(tr_ctx* ctx, float* tflops);
 TR_API int32_t tr_measure_hbm_copy(tr_ctx* ctx, float* gbs);

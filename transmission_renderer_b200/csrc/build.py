@@ -30,17 +30,21 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS + ["build.py"])
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, extra=()):
+    """out / extra: build an experimental variant next to the product library (select it with TR_LIB=path)."""
+    global OUT
+    if out:
+        OUT, force = out, True
     if not force and not needs_build():
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not out else "build_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc()] + NVCC_FLAGS + ["-c", os.path.join(HERE, src), "-o", obj]
+        cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-c", os.path.join(HERE, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False
@@ -61,4 +65,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out, extra=extra))

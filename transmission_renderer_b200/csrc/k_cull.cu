@@ -29,11 +29,12 @@ struct CullParams {
     uint32_t* instance_counts;  // [n_prims]
     uint32_t* visible_ids;      // [n_inst]
     uint32_t* work_prefix;      // [n_inst + 1] exclusive triangle prefix per visible slot
-    uint32_t* scalars;          // [0] n_visible, [1] total triangles (low 32), [2..5] draw_counts
+    uint32_t* scalars;          // [0] n_visible, [1] total triangles (low 32), [2..5] draw_counts, [6] ~min / [7] max bits of slot_z
+    float* slot_z;              // [n_inst] nearest view-space depth of each visible instance (front-to-back binning in K3)
 };
 
 // shader/src/lib.rs:442-469, exact regime
-__device__ __forceinline__ bool cull(float4 sphere, float4 ts, float4 rot, const tr_culling_push_constants& pc) {
+__device__ __forceinline__ bool cull(float4 sphere, float4 ts, float4 rot, const tr_culling_push_constants& pc, float& nearest_z) {
     f3 center = mk3(sphere.x, sphere.y, sphere.z);
     // Similarity * Vec3, shared-structs lib.rs:235-241
     center = xadd3(mk3(ts.x, ts.y, ts.z), xscale3(xquat_mul3(rot.x, rot.y, rot.z, rot.w, center), ts.w));
@@ -41,6 +42,7 @@ __device__ __forceinline__ bool cull(float4 sphere, float4 ts, float4 rot, const
     f4 c = xmat4_mul(view, center.x, center.y, center.z, 1.0f);
     const float cz = -c.z;  // lib.rs:452
     const float radius = xmul(sphere.w, ts.w);
+    nearest_z = fmaxf(cz - radius, pc.z_near);
     bool visible = xadd(cz, radius) > pc.z_near;
     visible &= xsub(xmul(cz, pc.frustum_x_xz.y), xmul(fabsf(c.x), pc.frustum_x_xz.x)) < radius;
     visible &= xsub(xmul(cz, pc.frustum_y_yz.y), xmul(fabsf(c.y), pc.frustum_y_yz.x)) < radius;
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(CULL_THREADS) cull_kernel(const __grid_constan
 
     bool visible = false;
     uint32_t tris = 0;
+    float nearest_z = 0.0f;
     if (i < p.n_inst) {
         const float4* q = reinterpret_cast<const float4*>(p.inst + i);
         const float4 ts = __ldg(q), rot = __ldg(q + 1);
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(CULL_THREADS) cull_kernel(const __grid_constan
         const float4* pq = reinterpret_cast<const float4*>(p.prims + prim);
         const float4 sphere = __ldg(pq);
         const uint4 pinfo = __ldg(reinterpret_cast<const uint4*>(pq + 1));
-        visible = !cull(sphere, ts, rot, p.pc);
+        visible = !cull(sphere, ts, rot, p.pc, nearest_z);
         if (visible) {
             tris = pinfo.y / 3u;
             atomicAdd(p.instance_counts + prim, 1u);  // lib.rs:437-439
@@ -127,6 +130,14 @@ __global__ void __launch_bounds__(CULL_THREADS) cull_kernel(const __grid_constan
         const uint32_t slot = (uint32_t)(base & ((1ull << VIS_BITS) - 1));
         p.visible_ids[slot] = i;
         p.work_prefix[slot] = (uint32_t)(base >> VIS_BITS);
+        p.slot_z[slot] = nearest_z;
+    }
+    // depth range of the visible set (positive floats order like their bit patterns)
+    const uint32_t zb = visible ? __float_as_uint(nearest_z) : 0u;
+    const uint32_t zmax = __reduce_max_sync(0xffffffffu, zb), zmin_c = __reduce_max_sync(0xffffffffu, visible ? ~zb : 0u);
+    if (lane == 0 && zmax) {
+        atomicMax(p.scalars + 7, zmax);
+        atomicMax(p.scalars + 6, zmin_c);
     }
     if (bid == gridDim.x - 1 && tid == 0) {
         const unsigned long long total = s_excl + block_total;
@@ -203,6 +214,7 @@ int32_t launch_cull(tr_ctx* c, const tr_culling_push_constants& pc) {
     TR_TRY(c->cull_scalars.ensure(state_bytes));
     TR_TRY(c->visible_ids.ensure((size_t)c->n_instances * 4));
     TR_TRY(c->work_prefix.ensure(((size_t)c->n_instances + 1) * 4));
+    TR_TRY(c->slot_z.ensure((size_t)c->n_instances * 4));
     for (int b = 0; b < 4; b++) TR_TRY(c->draws[b].ensure((size_t)c->n_primitives * sizeof(tr_draw_indexed_indirect_command)));
     unsigned char* st = c->cull_scalars.as<unsigned char>();
     // zeroing the instance count / draw count buffers, main.rs:1669-1700
@@ -220,6 +232,7 @@ int32_t launch_cull(tr_ctx* c, const tr_culling_push_constants& pc) {
     p.instance_counts = reinterpret_cast<uint32_t*>(st + counts_off);
     p.visible_ids = c->visible_ids.as<uint32_t>();
     p.work_prefix = c->work_prefix.as<uint32_t>();
+    p.slot_z = c->slot_z.as<float>();
     p.scalars = reinterpret_cast<uint32_t*>(st + scalars_off);
     cull_kernel<<<n_blocks, CULL_THREADS, 0, c->stream>>>(p);
     count_launches(2);

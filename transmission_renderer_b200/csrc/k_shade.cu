@@ -104,8 +104,14 @@ __device__ __forceinline__ uint32_t cluster_index(float fx, float fy, float dept
     return cz * u.num_clusters.x * u.num_clusters.y + cy * u.num_clusters.x + cx;
 }
 
+#ifndef TR_SHADE_CTAS_OPAQUE
+#define TR_SHADE_CTAS_OPAQUE 4
+#endif
+#ifndef TR_SHADE_CTAS_TRANS
+#define TR_SHADE_CTAS_TRANS 3
+#endif
 template <bool TRANS, bool HAS_POS, bool F32OUT>
-__global__ void __launch_bounds__(TILE) shade_kernel(const __grid_constant__ tr::ShadeLaunch p) {
+__global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_CTAS_OPAQUE) shade_kernel(const __grid_constant__ tr::ShadeLaunch p) {
     using L = StageLayout<TRANS, HAS_POS>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // STAGES barriers

@@ -26,6 +26,7 @@ namespace {
 constexpr int TS = 64;               // tile edge in pixels
 constexpr int TILE_THREADS = 256;    // 8 warps per tile CTA
 constexpr uint32_t BIN_CAPACITY = 1u << 24;  // (triangle, tile) pairs per frame
+constexpr int DEPTH_BUCKETS = 16;    // bin lists per (layer, tile), nearest instances first
 
 struct VisParams {
     const float* positions;
@@ -36,15 +37,17 @@ struct VisParams {
     const tr_primitive_info* prims;
     const uint32_t* visible_ids;
     const uint32_t* work_prefix;  // [n_visible + 1]
-    const uint32_t* scalars;      // [0] n_visible, [1] total triangles
+    const uint32_t* scalars;      // [0] n_visible, [1] total triangles, [6] ~min / [7] max bits of slot_z
+    const float* slot_z;          // [n_visible] nearest view depth of the instance in each slot
     mat4 proj_view;
     uint32_t width, height, y0, y1;
     unsigned long long* vis[2];
     // sort-middle binning state
-    uint32_t tiles_x, tiles_y, tile_row0, n_tiles;  // tile grid of the band; lists = 2 layers x n_tiles
-    uint32_t* bin_count;          // [2 * n_tiles]
-    uint32_t* bin_start;          // [2 * n_tiles + 1]
-    uint32_t* bin_cursor;         // [2 * n_tiles]
+    uint32_t tiles_x, tiles_y, tile_row0, n_tiles;  // tile grid of the band; lists = 2 layers x n_tiles x DEPTH_BUCKETS
+    uint32_t n_lists;
+    uint32_t* bin_count;          // [n_lists], list = (layer * n_tiles + tile) * DEPTH_BUCKETS + bucket
+    uint32_t* bin_start;          // [n_lists + 1]
+    uint32_t* bin_cursor;         // [n_lists]
     uint2* bin_entries;           // (slot, tri), grouped by list
     uint32_t bin_capacity;
     uint4* records;               // surviving triangles: (slot, tri, tile range, layer)
@@ -52,6 +55,7 @@ struct VisParams {
     uint32_t* rec_count;
     uint32_t* tile_ticket;
     uint32_t* status;             // bit 0: record overflow, bit 1: bin overflow
+    unsigned long long* stats;    // diagnostics: [0] box pixels binned, [1] box pixels after hierarchical Z, [2] exact evaluations
     // resolve outputs
     float* depth[2];
     float* normal[2];
@@ -72,6 +76,7 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 
 // oracle/raster.c setup_triangle
+template <bool WITH_BOX = true>
 __device__ __forceinline__ bool setup_triangle(const VisParams& p, const tr_instance* inst, const tr_primitive_info* prim,
                                                uint32_t tri, TriSetup& s) {
     const float4* iq = reinterpret_cast<const float4*>(inst);
@@ -116,6 +121,7 @@ __device__ __forceinline__ bool setup_triangle(const VisParams& p, const tr_inst
         s.B[i] = dsub(dmul(s.W[a], rx[b]), dmul(rx[a], s.W[b]));
         s.C[i] = dsub(dmul(rx[a], ry[b]), dmul(ry[a], rx[b]));
     }
+    if (!WITH_BOX) return true;  // resolve: the triangle is known to cover the pixel, only the edge functions are needed
     // Vulkan clip volume: w > 0 and z <= w.  Every vertex at/behind the camera plane => no fragment.
     if (!(s.W[0] > 0.0f) && !(s.W[1] > 0.0f) && !(s.W[2] > 0.0f)) return false;
     int x_lo = 0, x_hi = (int)p.width - 1, y_lo = (int)p.y0, y_hi = (int)p.y1 - 1;
@@ -249,7 +255,7 @@ __device__ __forceinline__ void bin_triangle(const VisParams& p, bool keep, cons
             const int y0 = max((ty + (int)p.tile_row0) * TS, t.y_lo), y1 = min((ty + (int)p.tile_row0) * TS + TS - 1, t.y_hi);
             if (!tile_may_overlap(t, x0, y0, x1, y1)) return;
         }
-        f(lay * p.n_tiles + (uint32_t)ty * p.tiles_x + (uint32_t)tx, pl);
+        f((((lay & 1u) * p.n_tiles + (uint32_t)ty * p.tiles_x + (uint32_t)tx) * DEPTH_BUCKETS) + (lay >> 1), pl);
     };
     if (keep && n_tiles <= 16)
         for (int ty = ty0; ty <= ty1; ty++)
@@ -275,6 +281,15 @@ __device__ __forceinline__ void bin_triangle(const VisParams& p, bool keep, cons
         const int bnx = bx1 - bx0 + 1, bn = bnx * (by1 - by0 + 1);
         for (int i = (int)lane; i < bn; i += 32) visit(t, bx0 + i % bnx, by0 + i / bnx, true, lay, pl);
     }
+}
+
+// front-to-back bucket of an instance: log-spaced in its nearest view depth over the visible set's range
+__device__ __forceinline__ uint32_t depth_bucket(const VisParams& p, uint32_t slot) {
+    const float z_hi = __uint_as_float(p.scalars[7]);
+    const float z_lo = fmaxf(__uint_as_float(~p.scalars[6]), z_hi * (1.0f / 64.0f));  // at most 6 octaves: instances that
+    if (!(z_hi > z_lo)) return 0u;                                                     // straddle the camera share bucket 0
+    const float t = __log2f(__ldg(p.slot_z + slot) / z_lo) / __log2f(z_hi / z_lo) * (float)DEPTH_BUCKETS;
+    return (uint32_t)min(max((int)t, 0), DEPTH_BUCKETS - 1);
 }
 
 // slot of the first lane's work item by binary search, the other lanes walk forward from it (they are
@@ -307,6 +322,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ 
             layer = bucket == 0u ? 0u : 1u;
             if ((bucket == 0u || bucket == 2u) && setup_triangle(p, inst, prim, tri, s)) {
                 keep = true;
+                layer |= depth_bucket(p, slot) << 1;  // layer | depth bucket << 1 travels with the record
                 range = (uint32_t)(s.x_lo / TS) | ((uint32_t)(s.x_hi / TS) << 8) |
                         ((uint32_t)(s.y_lo / TS - (int)p.tile_row0) << 16) | ((uint32_t)(s.y_hi / TS - (int)p.tile_row0) << 24);
             }
@@ -326,17 +342,18 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ 
     }
 }
 
-// ---- pass A2: exclusive scan of the bin counts (one CTA; <= 2 * 255 * 255 lists)
+// ---- pass A2: exclusive scan of the bin counts (one CTA; 4 lists per thread per step, 128-bit accesses)
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ VisParams p) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
-    const uint32_t n = 2u * p.n_tiles, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = p.n_lists, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // n is a multiple of 4
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (uint32_t chunk = 0; chunk < n; chunk += 1024) {
-        const uint32_t i = chunk + tid;
-        const uint32_t v = i < n ? p.bin_count[i] : 0u;
-        uint32_t incl = v;
+    for (uint32_t chunk = 0; chunk < n; chunk += 4096) {
+        const uint32_t i0 = chunk + tid * 4;
+        const uint4 q = i0 < n ? *reinterpret_cast<const uint4*>(p.bin_count + i0) : make_uint4(0, 0, 0, 0);
+        const uint32_t sum = q.x + q.y + q.z + q.w;
+        uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -345,13 +362,20 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
         uint32_t off = s_carry, tot = 0;
+#pragma unroll
         for (uint32_t k = 0; k < 32; k++) {
-            if (k < warp) off += s_warp[k];
-            tot += s_warp[k];
+            const uint32_t t = s_warp[k];
+            if (k < warp) off += t;
+            tot += t;
         }
-        if (i < n) {
-            p.bin_start[i] = off + incl - v;
-            p.bin_cursor[i] = off + incl - v;
+        if (i0 < n) {
+            uint4 o;
+            o.x = off + incl - sum;
+            o.y = o.x + q.x;
+            o.z = o.y + q.y;
+            o.w = o.z + q.z;
+            *reinterpret_cast<uint4*>(p.bin_start + i0) = o;
+            *reinterpret_cast<uint4*>(p.bin_cursor + i0) = o;
         }
         __syncthreads();
         if (tid == 0) s_carry += tot;
@@ -395,7 +419,10 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ V
 // sizes).  A pixel is dropped by fp32 edge functions with a rigorous error bound or by a conservative
 // fp32 depth plane against the tile's current depth; the survivors are queued per warp and evaluated 32
 // at a time with the exact double rule (eval_pixel), so the expensive path runs with full warps.
-constexpr int ROUND = TILE_THREADS;  // triangles per round
+#ifndef TR_ROUND
+#define TR_ROUND 64
+#endif
+constexpr int ROUND = TR_ROUND;  // triangles per round (<= TILE_THREADS); smaller rounds refresh the hierarchical Z more often
 struct TileRecs {
     double A[3][ROUND], B[3][ROUND], C[3][ROUND];
     float ea[3][ROUND], eb[3][ROUND], ec[3][ROUND], ebound[3][ROUND];
@@ -406,6 +433,7 @@ struct TileRecs {
     uint32_t off[ROUND + 1];
     uint32_t queue[TILE_THREADS / 32][64];
     uint32_t warp_tot[TILE_THREADS / 32];
+    float zmin_blk[64];    // hierarchical Z: min depth of each 8x8 pixel block, refreshed after every round
 };
 
 __device__ __forceinline__ void exact_sample(const TileRecs& tr_, unsigned long long* keys, uint32_t q, int tile_x0, int tile_y0) {
@@ -426,7 +454,10 @@ __device__ __forceinline__ void exact_sample(const TileRecs& tr_, unsigned long 
     if (*reinterpret_cast<volatile unsigned long long*>(k) < key) atomicMax(k, key);
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __grid_constant__ VisParams p) {
+#ifndef TR_TILE_CTAS
+#define TR_TILE_CTAS 4
+#endif
+__global__ void __launch_bounds__(TILE_THREADS, TR_TILE_CTAS) raster_tiles_kernel(const __grid_constant__ VisParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     TileRecs& R = *reinterpret_cast<TileRecs*>(smem_raw + TS * TS * 8);
@@ -439,19 +470,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __g
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(p.tile_ticket, 1u);
         for (uint32_t i = tid; i < TS * TS; i += TILE_THREADS) keys[i] = 0ull;
+        if (tid < 64) R.zmin_blk[tid] = 0.0f;
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= 2u * p.n_tiles) break;
         const uint32_t layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
         const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         const int tile_x0 = (int)tx * TS, tile_y0 = (int)(ty + p.tile_row0) * TS;
-        const uint32_t begin = min(p.bin_start[item], p.bin_capacity), end = min(p.bin_start[item + 1], p.bin_capacity);
+        // the tile's DEPTH_BUCKETS lists are consecutive: one sequence, nearest instances first
+        const uint32_t begin = min(p.bin_start[item * DEPTH_BUCKETS], p.bin_capacity), end = min(p.bin_start[(item + 1) * DEPTH_BUCKETS], p.bin_capacity);
         const uint32_t count = end - begin;
 
         for (uint32_t round = 0; round < count; round += ROUND) {
             // ---- thread i: set triangle i up, park both forms in shared memory
-            uint32_t n_samples = 0;
-            if (round + tid < count) {
+            uint32_t n_samples = 0, n_box = 0;
+            if (tid < ROUND && round + tid < count) {
                 const uint2 e = p.bin_entries[begin + round + tid];
                 const tr_instance* inst = p.instances + __ldg(p.visible_ids + e.x);
                 const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
@@ -505,7 +538,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __g
                         R.gx[tid] = gx;
                         R.gy[tid] = gy;
                         R.margin[tid] = mg;
+                        // hierarchical Z: the whole clipped box is behind what the tile already holds
+                        const float dmax = d0 + fmaxf(gx * (float)x_lo, gx * (float)x_hi) + fmaxf(gy * (float)y_lo, gy * (float)y_hi) + mg;
+                        float zm = __int_as_float(0x7f800000);
+                        for (int by = y_lo >> 3; by <= (y_hi >> 3); by++)
+                            for (int bx = x_lo >> 3; bx <= (x_hi >> 3); bx++) zm = fminf(zm, R.zmin_blk[by * 8 + bx]);
+                        n_box = n_samples;
+                        if (dmax < zm) n_samples = 0;
                     }
+                }
+            }
+            {   // diagnostics
+                const uint32_t a = __reduce_add_sync(0xffffffffu, n_box), b = __reduce_add_sync(0xffffffffu, n_samples);
+                if (lane == 0 && a) {
+                    atomicAdd(p.stats, (unsigned long long)a);
+                    atomicAdd(p.stats + 1, (unsigned long long)b);
                 }
             }
             // ---- CTA-wide inclusive scan of the box sizes
@@ -524,12 +571,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __g
                 if (k < warp) warp_off += t;
                 total += t;
             }
-            R.off[tid + 1] = warp_off + incl;
+            if (tid < ROUND) R.off[tid + 1] = warp_off + incl;
             if (tid == 0) R.off[0] = 0;
             __syncthreads();
 
             // ---- coarse walk over the pixels of all boxes: warp w takes samples [32 (8 i + w), +32)
-            uint32_t j = 0, j_end = 0, j_off = 0, qn = 0;
+            uint32_t j = 0, j_end = 0, j_off = 0, qn = 0, n_exact = 0;
             float a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0, t0 = 0, t1 = 0, t2 = 0;
             float pd0 = 0, pgx = 0, pgy = 0, pmg = 0;
             uint32_t bx = 0, by = 0, bw = 1, magic = 0;
@@ -581,6 +628,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __g
                 const uint32_t m = __ballot_sync(0xffffffffu, survive);
                 if (survive) queue[qn + __popc(m & lt_mask)] = q;
                 qn += __popc(m);
+                n_exact += __popc(m);
                 __syncwarp();
                 if (qn >= 32u) {
                     const uint32_t mine = queue[lane];
@@ -593,7 +641,20 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) raster_tiles_kernel(const __g
                 }
             }
             if (lane < qn) exact_sample(R, keys, queue[lane], tile_x0, tile_y0);
+            if (lane == 0 && n_exact) atomicAdd(p.stats + 2, (unsigned long long)n_exact);
             __syncthreads();  // the records are rewritten by the next round
+            if (round + ROUND < count) {  // refresh the block minima: 4 threads per 8x8 block, 16 pixels each
+                const uint32_t blk = tid >> 2, part = tid & 3u;
+                const uint32_t ox = (blk & 7u) * 8u, oy = (blk >> 3) * 8u + part * 2u;
+                float m = __int_as_float(0x7f800000);
+#pragma unroll
+                for (uint32_t k = 0; k < 16; k++)
+                    m = fminf(m, __uint_as_float(reinterpret_cast<const uint32_t*>(keys)[((oy + (k >> 3)) * TS + ox + (k & 7u)) * 2 + 1]));
+                m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                if (part == 0) R.zmin_blk[blk] = m;
+                __syncthreads();
+            }
         }
 
         __syncthreads();
@@ -635,7 +696,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Vi
             const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
             TriSetup s;
             float l[3] = {0.f, 0.f, 0.f}, d = 0.0f;
-            const bool ok = setup_triangle(p, inst, prim, tri, s) && eval_pixel(s, (int)px, (int)py, l, d);
+            const bool ok = setup_triangle<false>(p, inst, prim, tri, s) && eval_pixel(s, (int)px, (int)py, l, d);
             (void)ok;  // by construction the winning triangle covers this pixel
             const float4 rot = __ldg(reinterpret_cast<const float4*>(inst) + 1);
             f3 n[3];
@@ -689,13 +750,14 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.rec_capacity = (uint32_t)(c->max_triangles ? c->max_triangles : 1);
     TR_TRY(c->bin_entries.ensure((size_t)p.bin_capacity * sizeof(uint2)));
     TR_TRY(c->tri_records.ensure((size_t)p.rec_capacity * sizeof(uint4)));
-    // state block: [bin_count 2T][rec_count, ticket, pad, pad][bin_start 2T+1][bin_cursor 2T]; the first two parts are zeroed per frame
-    const size_t n_lists = (size_t)2 * p.n_tiles;
+    // state block: [bin_count L][rec_count, ticket, pad, pad][bin_start L+1][bin_cursor L]; the first two parts are zeroed per frame
+    const size_t n_lists = (size_t)2 * p.n_tiles * DEPTH_BUCKETS;
+    p.n_lists = (uint32_t)n_lists;
     const size_t zero_bytes = (n_lists + 4) * 4;
-    TR_TRY(c->bin_state.ensure(zero_bytes + (2 * n_lists + 1) * 4));
+    TR_TRY(c->bin_state.ensure(zero_bytes + (2 * n_lists + 4) * 4));
     if (!c->dev_status.p) {
-        TR_TRY(c->dev_status.ensure(16));
-        TR_CUDA(cudaMemsetAsync(c->dev_status.p, 0, 16, c->stream));
+        TR_TRY(c->dev_status.ensure(64));
+        TR_CUDA(cudaMemsetAsync(c->dev_status.p, 0, 64, c->stream));
     }
     TR_CUDA(cudaMemsetAsync(c->bin_state.p, 0, zero_bytes, c->stream));
     uint32_t* st = c->bin_state.as<uint32_t>();
@@ -703,10 +765,11 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.rec_count = st + n_lists;
     p.tile_ticket = st + n_lists + 1;
     p.bin_start = st + n_lists + 4;
-    p.bin_cursor = p.bin_start + n_lists + 1;
+    p.bin_cursor = p.bin_start + n_lists + 4;  // keeps 16-byte alignment (n_lists is a multiple of 16)
     p.bin_entries = c->bin_entries.as<uint2>();
     p.records = c->tri_records.as<uint4>();
     p.status = c->dev_status.as<uint32_t>();
+    p.stats = reinterpret_cast<unsigned long long*>(c->dev_status.as<unsigned char>() + 16);
 
     p.positions = c->mesh_pos.as<float>();
     p.normals = c->mesh_nrm.as<float>();
@@ -717,6 +780,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.visible_ids = c->visible_ids.as<uint32_t>();
     p.work_prefix = c->work_prefix.as<uint32_t>();
     p.scalars = c->d_cull_scalars;
+    p.slot_z = c->slot_z.as<float>();
     memcpy(&p.proj_view, &pc.proj_view, sizeof(mat4));
     p.width = c->width;
     p.height = c->height;

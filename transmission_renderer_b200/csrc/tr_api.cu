@@ -310,7 +310,7 @@ int32_t tr_destroy(tr_ctx* c) {
     comm_release(c);
     DevBuf* bufs[] = {&c->instances, &c->primitives, &c->materials, &c->lights, &c->lut, &c->mesh_pos, &c->mesh_nrm,
                       &c->mesh_uv, &c->mesh_idx, &c->visible_ids, &c->cull_scalars, &c->draws[0], &c->draws[1],
-                      &c->draws[2], &c->draws[3], &c->work_prefix, &c->cluster_aabbs, &c->cluster_counts,
+                      &c->draws[2], &c->draws[3], &c->work_prefix, &c->slot_z, &c->cluster_aabbs, &c->cluster_counts,
                       &c->cluster_indices, &c->vis[0], &c->vis[1], &c->bin_entries, &c->bin_state, &c->tri_records, &c->dev_status, &c->hdr, &c->hdr_f32, &c->pyramid,
                       &c->srgb8, &c->mip_counter};
     for (DevBuf* b : bufs) b->release();
@@ -327,6 +327,12 @@ int32_t tr_destroy(tr_ctx* c) {
         delete[] c->ev_begin;
         delete[] c->ev_end;
         delete[] c->ev_used;
+    }
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+        cudaEventDestroy(c->ev_frame_done);
+        cudaEventDestroy(c->ev_copy_done);
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -362,6 +368,7 @@ int32_t tr_set_stream(tr_ctx* c, void* cuda_stream) {
 int32_t tr_sync(tr_ctx* c) {
     TR_CHECK_CTX(c);
     TR_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) TR_CUDA(cudaStreamSynchronize(c->copy_stream));
     return check_device_status(c, "tr_sync");
 }
 
@@ -563,6 +570,7 @@ int32_t tr_tonemap(tr_ctx* c, const tr_baked_lottes_tonemapper_params* params) {
     TR_CHECK_CTX(c);
     if (!params) return fail(TR_ERR_INVALID_ARG, "tr_tonemap: null");
     if (!c->hdr_valid) return fail(TR_ERR_STATE, "tr_tonemap: nothing rendered");
+    if (c->copy_pending) TR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));  // the previous band is still being read back
     pass_begin(c, P_TONEMAP);
     TR_TRY(launch_tonemap(c->hdr.as<uint2>(), c->srgb8.as<uchar4>(), c->band_y0 * c->width, c->band_y1 * c->width, *params,
                           c->sm_count, c->stream));
@@ -800,6 +808,30 @@ int32_t tr_read_srgb8(tr_ctx* c, uint8_t* rgba8) {
     return TR_OK;
 }
 
+int32_t tr_read_srgb8_async(tr_ctx* c, uint8_t* rgba8) {
+    TR_CHECK_CTX(c);
+    if (!rgba8) return fail(TR_ERR_INVALID_ARG, "tr_read_srgb8_async: null");
+    if (!c->srgb_valid) return fail(TR_ERR_STATE, "tr_read_srgb8_async: tr_tonemap has not run");
+    if (!c->copy_stream) {
+        TR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        TR_CUDA(cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming));
+        TR_CUDA(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
+    }
+    const size_t off = (size_t)c->band_y0 * c->width * 4, bytes = (size_t)(c->band_y1 - c->band_y0) * c->width * 4;
+    TR_CUDA(cudaEventRecord(c->ev_frame_done, c->stream));
+    TR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_frame_done, 0));
+    TR_CUDA(cudaMemcpyAsync(rgba8 + off, c->srgb8.as<uint8_t>() + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    TR_CUDA(cudaEventRecord(c->ev_copy_done, c->copy_stream));
+    c->copy_pending = true;
+    return TR_OK;
+}
+
+int32_t tr_wait_readback(tr_ctx* c) {
+    TR_CHECK_CTX(c);
+    if (c->copy_pending) TR_CUDA(cudaEventSynchronize(c->ev_copy_done));
+    return TR_OK;
+}
+
 int32_t tr_mip_levels(tr_ctx* c, uint32_t* levels) {
     if (!c || !levels) return fail(TR_ERR_INVALID_ARG, "tr_mip_levels: null");
     *levels = c->levels;
@@ -857,6 +889,17 @@ int32_t tr_eval_ibl_volume_refraction(tr_ctx* c, uint32_t n, const tr_mat4* proj
     return eval_batch(c, n, params, out, [&](const tr_ibl_volume_refraction_params* i, tr_vec3* o) {
         return launch_eval_ibl(n, pv, i, o, pyr, lut, c->stream);
     });
+}
+
+int32_t tr_raster_stats(tr_ctx* c, uint64_t out[4], int32_t reset) {
+    TR_CHECK_CTX(c);
+    if (!out) return fail(TR_ERR_INVALID_ARG, "tr_raster_stats: null");
+    memset(out, 0, 32);
+    if (!c->dev_status.p) return TR_OK;
+    TR_CUDA(cudaStreamSynchronize(c->stream));
+    TR_CUDA(cudaMemcpy(out, c->dev_status.as<unsigned char>() + 16, 32, cudaMemcpyDeviceToHost));
+    if (reset) TR_CUDA(cudaMemset(c->dev_status.as<unsigned char>() + 16, 0, 32));
+    return TR_OK;
 }
 
 int32_t tr_launch_count(uint64_t* out) {

@@ -68,9 +68,9 @@ struct tr_ctx {
     uint32_t n_vertices = 0, n_indices = 0;
 
     // cull outputs (frustum_culling + demultiplex_draws)
-    tr::DevBuf visible_ids, cull_scalars, draws[4], work_prefix;
+    tr::DevBuf visible_ids, cull_scalars, draws[4], work_prefix, slot_z;
     uint32_t* d_instance_counts = nullptr;  // views into cull_scalars (state block of K1)
-    uint32_t* d_cull_scalars = nullptr;     // [0] n_visible [1] visible triangles [2..5] draw_counts
+    uint32_t* d_cull_scalars = nullptr;     // [0] n_visible [1] visible triangles [2..5] draw_counts [6,7] ~min/max bits of slot_z
     std::vector<uint32_t> h_prim_tris, h_inst_prim;  // host copies: triangles per primitive, primitive of each instance
     uint64_t max_triangles = 0;                      // upper bound of the visibility work list
     bool tri_bound_valid = false;
@@ -93,6 +93,11 @@ struct tr_ctx {
     cudaEvent_t (*ev_begin)[tr::P_COUNT] = nullptr, (*ev_end)[tr::P_COUNT] = nullptr;  // [kTimingRing][P_COUNT], lazily created
     bool (*ev_used)[tr::P_COUNT] = nullptr;
     uint64_t timing_frame = 0, timing_first = 0;  // current frame number / first frame not yet summed
+
+    // asynchronous read-back of the sRGB8 band (overlaps the next frame)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_frame_done = nullptr, ev_copy_done = nullptr;
+    bool copy_pending = false;
 
     // multi-GPU
     int rank = 0, n_ranks = 1;

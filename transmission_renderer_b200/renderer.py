@@ -256,6 +256,14 @@ class Renderer:
         return a
 
     # -- glam-pbr contracts --------------------------------------------------------------------
+    def read_srgb8_async(self, out):
+        """Enqueue the band read-back behind the frame just recorded; `out` (H, W, 4) uint8, ideally pinned."""
+        assert out.dtype == np.uint8 and out.size == self.width * self.height * 4 and out.flags.c_contiguous
+        _check(_lib().tr_read_srgb8_async(self._ctx, _p(out)))
+
+    def wait_readback(self):
+        _check(_lib().tr_wait_readback(self._ctx))
+
     def eval_basic_brdf(self, params):
         a = _c(params, abi.basic_brdf_params)
         out = np.zeros(len(a), dtype=abi.brdf_result)
@@ -310,6 +318,11 @@ class Renderer:
         n = C.c_uint64(0)
         _check(_lib().tr_launch_count(C.byref(n)))
         return n.value
+
+    def raster_stats(self, reset=True):
+        out = (C.c_uint64 * 4)()
+        _check(_lib().tr_raster_stats(self._ctx, out, C.c_int32(1 if reset else 0)))
+        return dict(box_pixels=out[0], box_pixels_after_hiz=out[1], exact_evaluations=out[2])
 
     def measure_fp32_peak(self):
         v = C.c_float(0)
