@@ -172,6 +172,8 @@ class CpuShadePath:
         from oracle import pyoracle as oracle
         from transmission_renderer_b200 import abi, host
         self.oracle = oracle
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it may run on
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
         cam = scene["camera"]
         self.w, self.h = cam.width, cam.height
         rows = max(4, min(rows, self.h))
@@ -451,11 +453,12 @@ def run_b200(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"], help="N>1: NCCL all-gather or fused peer stores")
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
+                    help="N>1: opaque bands by fused peer stores over NVLink (default) or by an NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

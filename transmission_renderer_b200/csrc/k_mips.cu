@@ -167,14 +167,30 @@ __global__ void __launch_bounds__(256) mip_kernel(const __grid_constant__ MipPar
         const uint32_t sw = p.w[l - 1], sh = p.h[l - 1], dw = p.w[l], dh = p.h[l];
         const uint2* src = p.base + p.off[l - 1];
         uint2* dst = p.base + p.off[l];
-        for (uint32_t i = tid; i < dw * dh; i += blockDim.x) {
-            const uint32_t dy = i / dw, dx = i - dy * dw;
-            uint32_t x0, x1, y0, y1;
-            float fx, fy;
-            axis_setup(dx, sw, dw, x0, x1, fx);
-            axis_setup(dy, sh, dh, y0, y1, fy);
-            dst[i] = filter4(__ldcg(src + (size_t)y0 * sw + x0), __ldcg(src + (size_t)y0 * sw + x1),
-                             __ldcg(src + (size_t)y1 * sw + x0), __ldcg(src + (size_t)y1 * sw + x1), fx, fy);
+        // four texels per thread per step: their 16 source loads are in flight together (the tail runs on one CTA,
+        // so latency, not bandwidth, is what it waits for)
+        for (uint32_t i0 = tid; i0 < dw * dh; i0 += blockDim.x * 4) {
+            uint2 t[4][4];
+            float fxs[4], fys[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + u * blockDim.x;
+                if (i < dw * dh) {
+                    const uint32_t dy = i / dw, dx = i - dy * dw;
+                    uint32_t x0, x1, y0, y1;
+                    axis_setup(dx, sw, dw, x0, x1, fxs[u]);
+                    axis_setup(dy, sh, dh, y0, y1, fys[u]);
+                    t[u][0] = __ldcg(src + (size_t)y0 * sw + x0);
+                    t[u][1] = __ldcg(src + (size_t)y0 * sw + x1);
+                    t[u][2] = __ldcg(src + (size_t)y1 * sw + x0);
+                    t[u][3] = __ldcg(src + (size_t)y1 * sw + x1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + u * blockDim.x;
+                if (i < dw * dh) dst[i] = filter4(t[u][0], t[u][1], t[u][2], t[u][3], fxs[u], fys[u]);
+            }
         }
         __threadfence();
         __syncthreads();

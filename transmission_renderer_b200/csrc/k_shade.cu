@@ -105,7 +105,7 @@ __device__ __forceinline__ uint32_t cluster_index(float fx, float fy, float dept
 }
 
 #ifndef TR_SHADE_CTAS_OPAQUE
-#define TR_SHADE_CTAS_OPAQUE 4
+#define TR_SHADE_CTAS_OPAQUE 3
 #endif
 #ifndef TR_SHADE_CTAS_TRANS
 #define TR_SHADE_CTAS_TRANS 3
@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
     const uint32_t n_px = p.px_end - p.px_begin;
     const uint32_t n_tiles = (n_px + TILE - 1) / TILE;
     const bool lights_in_smem = p.n_lights <= MAX_SMEM_LIGHTS;
+    const uint32_t lights_saddr = smem_u32(s_lights);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
         f3 pos = mk3(0.f, 0.f, 0.f), emission = mk3(0.f, 0.f, 0.f);
         f3 diff = mk3(0.f, 0.f, 0.f), spec = mk3(0.f, 0.f, 0.f), trans = mk3(0.f, 0.f, 0.f);
         const tr_material_info* mat = nullptr;
-        uint32_t my_count = 0, my_base = 0, my_i = 0;
+        uint32_t my_count = 0, my_base = 0;
         float model_scale = 1.0f;
 
         if (covered) {
@@ -238,14 +239,31 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
         }
 
         // ------------------------------------------------------------ clustered lights: warp-wide sorted merge
-        uint32_t next = my_i < my_count ? __ldg(p.cluster_indices + my_base + my_i) : 0xffffffffu;
+        // every lane walks its own cluster's list (ascending light ids) through a private pointer; the warp takes the
+        // smallest pending id each turn, so all lanes stay converged and each pixel still sums in ascending id order
+        const uint32_t* my_ptr = p.cluster_indices + my_base;
+        const uint32_t* const my_end = my_ptr + my_count;
+        uint32_t next = my_ptr < my_end ? __ldg(my_ptr) : 0xffffffffu;
         while (true) {
             const uint32_t m = __reduce_min_sync(0xffffffffu, next);
             if (m == 0xffffffffu) break;
             LightS l;
-            if (lights_in_smem) l = s_lights[m];
-            else l = make_light_s(p.lights, m);
+            if (lights_in_smem) {
+                // explicit shared-window loads: 3 x 128 bit, address formed from a 32-bit base hoisted out of the loop
+                const uint32_t a = lights_saddr + m * (uint32_t)sizeof(LightS);
+                float4 q0, q1, q2;
+                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a));
+                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(a));
+                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a));
+                l.px = q0.x; l.py = q0.y; l.pz = q0.z; l.er = q0.w;
+                l.eg = q1.x; l.eb = q1.y; l.sx = q1.z; l.sy = q1.w;
+                l.sz = q2.x; l.cos_outer = q2.y; l.inv_eps = q2.z; l.is_spot = __float_as_uint(q2.w);
+            } else {
+                l = make_light_s(p.lights, m);
+            }
             if (next == m) {
+                my_ptr++;
+                const uint32_t upcoming = my_ptr < my_end ? __ldg(my_ptr) : 0xffffffffu;  // issued early: hidden behind the BRDF
                 // light_direction_and_attenuation (glam-pbr lib.rs:12-23), fast regime; the exact chain is re-derived
                 // from `vec` inside the BRDF only where it matters (tr_device_pbr.cuh "adaptive exactness")
                 const f3 vec = sub3(mk3(l.px, l.py, l.pz), pos);
@@ -259,8 +277,7 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
                 f3 li = scale3(mk3(l.er, l.eg, l.eb), factor);
                 brdf_point_light(ps, vec, dir, li, diff, spec);
                 if (TRANS) trans = add3(trans, mul3(li, btdf_point_light(ps, vec, dir)));
-                my_i++;
-                next = my_i < my_count ? __ldg(p.cluster_indices + my_base + my_i) : 0xffffffffu;
+                next = upcoming;
             }
         }
 

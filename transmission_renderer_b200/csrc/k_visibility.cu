@@ -40,6 +40,8 @@ struct VisParams {
     const uint32_t* scalars;      // [0] n_visible, [1] total triangles, [6] ~min / [7] max bits of slot_z
     const float* slot_z;          // [n_visible] nearest view depth of the instance in each slot
     mat4 proj_view;
+    float row_y_norm, row_w_norm;  // |rows 1 and 3 of proj_view (xyz)|: how far a unit world offset moves clip y / w
+    uint32_t band_cull;            // the band is a strict part of the frame: skip instances that cannot reach it
     uint32_t width, height, y0, y1;
     unsigned long long* vis[2];
     // sort-middle binning state
@@ -320,7 +322,23 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ 
             const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
             const uint32_t bucket = __ldg(&prim->draw_buffer_index);
             layer = bucket == 0u ? 0u : 1u;
-            if ((bucket == 0u || bucket == 2u) && setup_triangle(p, inst, prim, tri, s)) {
+            bool on_band = true;
+            if (p.band_cull) {
+                // conservative rows of the instance's bounding sphere: clip(C + d) = clip(C) + M d, |d| <= r
+                const float4 sph = __ldg(reinterpret_cast<const float4*>(prim));
+                const float4 ts = __ldg(reinterpret_cast<const float4*>(inst)), rot = __ldg(reinterpret_cast<const float4*>(inst) + 1);
+                const f3 c = xadd3(mk3(ts.x, ts.y, ts.z), xscale3(xquat_mul3(rot.x, rot.y, rot.z, rot.w, mk3(sph.x, sph.y, sph.z)), ts.w));
+                const f4 cc = xmat4_mul(p.proj_view, c.x, c.y, c.z, 1.0f);
+                const float r = fabsf(sph.w * ts.w) * 1.01f + 1e-3f;
+                const float w_lo = cc.w - r * p.row_w_norm, w_hi = cc.w + r * p.row_w_norm;
+                if (w_lo > 0.0f) {
+                    const float y_lo = cc.y - r * p.row_y_norm, y_hi = cc.y + r * p.row_y_norm;
+                    const float n_lo = fminf(y_lo / w_lo, y_lo / w_hi), n_hi = fmaxf(y_hi / w_lo, y_hi / w_hi);
+                    const float half_h = 0.5f * (float)p.height;
+                    on_band = (n_hi + 1.0f) * half_h + 2.0f >= (float)p.y0 && (n_lo + 1.0f) * half_h - 2.0f <= (float)p.y1;
+                }
+            }
+            if (on_band && (bucket == 0u || bucket == 2u) && setup_triangle(p, inst, prim, tri, s)) {
                 keep = true;
                 layer |= depth_bucket(p, slot) << 1;  // layer | depth bucket << 1 travels with the record
                 range = (uint32_t)(s.x_lo / TS) | ((uint32_t)(s.x_hi / TS) << 8) |
@@ -782,6 +800,12 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.scalars = c->d_cull_scalars;
     p.slot_z = c->slot_z.as<float>();
     memcpy(&p.proj_view, &pc.proj_view, sizeof(mat4));
+    {
+        const float* m = reinterpret_cast<const float*>(&pc.proj_view);  // column-major: element (row r, col k) = m[k * 4 + r]
+        p.row_y_norm = sqrtf(m[1] * m[1] + m[5] * m[5] + m[9] * m[9]) * 1.0001f;
+        p.row_w_norm = sqrtf(m[3] * m[3] + m[7] * m[7] + m[11] * m[11]) * 1.0001f;
+        p.band_cull = (c->band_y0 != 0 || c->band_y1 != c->height) ? 1u : 0u;
+    }
     p.width = c->width;
     p.height = c->height;
     p.y0 = c->band_y0;
