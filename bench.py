@@ -296,6 +296,10 @@ def run_b200(args, wl):
     from transmission_renderer_b200 import parallel
     parallel.init_bands(r, rank, world, group=cpu_group, exchange=args.exchange)
     y0, y1 = host.band_rows(H, rank, world)
+    if args.emulate_band and world == 1:
+        eb_r, eb_n = (int(x) for x in args.emulate_band.split("/"))
+        y0, y1 = host.band_rows(H, eb_r, eb_n)
+        r.set_band(y0, y1)
     fp = cam.frame_params(host.default_tonemap_params())
 
     def sync():
@@ -460,6 +464,8 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
                     help="N>1: opaque bands by fused peer stores over NVLink (default) or by an NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-band", default=None, metavar="R/N",
+                    help="profiling aid (1 GPU): render only band R of N without any exchange, e.g. 3/8")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

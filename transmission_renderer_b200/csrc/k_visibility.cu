@@ -17,13 +17,15 @@
 //   pass 3  per pixel: re-evaluate the winning triangle, interpolate perspective-correct varyings,
 //           write the SoA G-buffer planes of both layers, and clear the visibility words for the
 //           next frame.
+#include <stdlib.h>
+
 #include "tr_internal.h"
 
 using namespace trd;
 
 namespace {
 
-constexpr int TS = 64;               // tile edge in pixels
+constexpr int TS_MAX = 64;           // tile edge in pixels: 64, or 32 when a small band would give too few tiles to fill the GPU
 constexpr int TILE_THREADS = 256;    // 8 warps per tile CTA
 constexpr uint32_t BIN_CAPACITY = 1u << 24;  // (triangle, tile) pairs per frame
 constexpr int DEPTH_BUCKETS = 16;    // bin lists per (layer, tile), nearest instances first
@@ -45,6 +47,7 @@ struct VisParams {
     uint32_t width, height, y0, y1;
     unsigned long long* vis[2];
     // sort-middle binning state
+    int ts;                                         // tile edge chosen for this launch (64 or 32)
     uint32_t tiles_x, tiles_y, tile_row0, n_tiles;  // tile grid of the band; lists = 2 layers x n_tiles x DEPTH_BUCKETS
     uint32_t n_lists;
     uint32_t* bin_count;          // [n_lists], list = (layer * n_tiles + tile) * DEPTH_BUCKETS + bucket
@@ -253,8 +256,8 @@ __device__ __forceinline__ void bin_triangle(const VisParams& p, bool keep, cons
     const int ntx = tx1 - tx0 + 1, n_tiles = ntx * (ty1 - ty0 + 1);
     auto visit = [&](const TriSetup& t, int tx, int ty, bool test, uint32_t lay, uint2 pl) {
         if (test) {
-            const int x0 = max(tx * TS, t.x_lo), x1 = min(tx * TS + TS - 1, t.x_hi);
-            const int y0 = max((ty + (int)p.tile_row0) * TS, t.y_lo), y1 = min((ty + (int)p.tile_row0) * TS + TS - 1, t.y_hi);
+            const int x0 = max(tx * p.ts, t.x_lo), x1 = min(tx * p.ts + p.ts - 1, t.x_hi);
+            const int y0 = max((ty + (int)p.tile_row0) * p.ts, t.y_lo), y1 = min((ty + (int)p.tile_row0) * p.ts + p.ts - 1, t.y_hi);
             if (!tile_may_overlap(t, x0, y0, x1, y1)) return;
         }
         f((((lay & 1u) * p.n_tiles + (uint32_t)ty * p.tiles_x + (uint32_t)tx) * DEPTH_BUCKETS) + (lay >> 1), pl);
@@ -341,8 +344,8 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ 
             if (on_band && (bucket == 0u || bucket == 2u) && setup_triangle(p, inst, prim, tri, s)) {
                 keep = true;
                 layer |= depth_bucket(p, slot) << 1;  // layer | depth bucket << 1 travels with the record
-                range = (uint32_t)(s.x_lo / TS) | ((uint32_t)(s.x_hi / TS) << 8) |
-                        ((uint32_t)(s.y_lo / TS - (int)p.tile_row0) << 16) | ((uint32_t)(s.y_hi / TS - (int)p.tile_row0) << 24);
+                range = (uint32_t)(s.x_lo / p.ts) | ((uint32_t)(s.x_hi / p.ts) << 8) |
+                        ((uint32_t)(s.y_lo / p.ts - (int)p.tile_row0) << 16) | ((uint32_t)(s.y_hi / p.ts - (int)p.tile_row0) << 24);
             }
         }
         bin_triangle(p, keep, s, range, layer, make_uint2(0, 0), [&](uint32_t list, uint2) { atomicAdd(p.bin_count + list, 1u); });
@@ -454,6 +457,7 @@ struct TileRecs {
     float zmin_blk[64];    // hierarchical Z: min depth of each 8x8 pixel block, refreshed after every round
 };
 
+template <int TS>
 __device__ __forceinline__ void exact_sample(const TileRecs& tr_, unsigned long long* keys, uint32_t q, int tile_x0, int tile_y0) {
     const uint32_t j = q & 255u, lx = (q >> 8) & 63u, ly = (q >> 14) & 63u;
     TriSetup s;
@@ -475,6 +479,7 @@ __device__ __forceinline__ void exact_sample(const TileRecs& tr_, unsigned long 
 #ifndef TR_TILE_CTAS
 #define TR_TILE_CTAS 4
 #endif
+template <int TS>
 __global__ void __launch_bounds__(TILE_THREADS, TR_TILE_CTAS) raster_tiles_kernel(const __grid_constant__ VisParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -488,7 +493,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TR_TILE_CTAS) raster_tiles_kerne
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(p.tile_ticket, 1u);
         for (uint32_t i = tid; i < TS * TS; i += TILE_THREADS) keys[i] = 0ull;
-        if (tid < 64) R.zmin_blk[tid] = 0.0f;
+        if (tid < (TS / 8) * (TS / 8)) R.zmin_blk[tid] = 0.0f;
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= 2u * p.n_tiles) break;
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TR_TILE_CTAS) raster_tiles_kerne
                         const float dmax = d0 + fmaxf(gx * (float)x_lo, gx * (float)x_hi) + fmaxf(gy * (float)y_lo, gy * (float)y_hi) + mg;
                         float zm = __int_as_float(0x7f800000);
                         for (int by = y_lo >> 3; by <= (y_hi >> 3); by++)
-                            for (int bx = x_lo >> 3; bx <= (x_hi >> 3); bx++) zm = fminf(zm, R.zmin_blk[by * 8 + bx]);
+                            for (int bx = x_lo >> 3; bx <= (x_hi >> 3); bx++) zm = fminf(zm, R.zmin_blk[by * (TS / 8) + bx]);
                         n_box = n_samples;
                         if (dmax < zm) n_samples = 0;
                     }
@@ -654,23 +659,26 @@ __global__ void __launch_bounds__(TILE_THREADS, TR_TILE_CTAS) raster_tiles_kerne
                     __syncwarp();
                     queue[lane] = spill;
                     qn -= 32u;
-                    exact_sample(R, keys, mine, tile_x0, tile_y0);
+                    exact_sample<TS>(R, keys, mine, tile_x0, tile_y0);
                     __syncwarp();
                 }
             }
-            if (lane < qn) exact_sample(R, keys, queue[lane], tile_x0, tile_y0);
+            if (lane < qn) exact_sample<TS>(R, keys, queue[lane], tile_x0, tile_y0);
             if (lane == 0 && n_exact) atomicAdd(p.stats + 2, (unsigned long long)n_exact);
             __syncthreads();  // the records are rewritten by the next round
             if (round + ROUND < count) {  // refresh the block minima: 4 threads per 8x8 block, 16 pixels each
+                constexpr uint32_t BPR = TS / 8;  // blocks per tile row
                 const uint32_t blk = tid >> 2, part = tid & 3u;
-                const uint32_t ox = (blk & 7u) * 8u, oy = (blk >> 3) * 8u + part * 2u;
                 float m = __int_as_float(0x7f800000);
+                if (blk < BPR * BPR) {
+                    const uint32_t ox = (blk % BPR) * 8u, oy = (blk / BPR) * 8u + part * 2u;
 #pragma unroll
-                for (uint32_t k = 0; k < 16; k++)
-                    m = fminf(m, __uint_as_float(reinterpret_cast<const uint32_t*>(keys)[((oy + (k >> 3)) * TS + ox + (k & 7u)) * 2 + 1]));
+                    for (uint32_t k = 0; k < 16; k++)
+                        m = fminf(m, __uint_as_float(reinterpret_cast<const uint32_t*>(keys)[((oy + (k >> 3)) * TS + ox + (k & 7u)) * 2 + 1]));
+                }
                 m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
                 m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-                if (part == 0) R.zmin_blk[blk] = m;
+                if (part == 0 && blk < BPR * BPR) R.zmin_blk[blk] = m;
                 __syncthreads();
             }
         }
@@ -759,11 +767,19 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
         c->tri_bound_valid = true;
     }
     VisParams p{};
-    p.tiles_x = (c->width + TS - 1) / TS;
-    p.tile_row0 = c->band_y0 / TS;
-    p.tiles_y = (c->band_y1 - 1) / TS - p.tile_row0 + 1;
+    // tile edge: 64 pixels, or 32 when the band is so small that 64-pixel tiles would leave SMs idle / unbalanced
+    {
+        const uint32_t t64 = ((c->width + 63) / 64) * ((c->band_y1 - 1) / 64 - c->band_y0 / 64 + 1);
+        // measured on 1/4 and 1/8 bands of a 4K frame: 32-pixel tiles balance better but cost more set-up work per
+        // triangle than they save, so they are only used when 64-pixel tiles cannot even occupy half the CTA slots
+        p.ts = 2 * t64 * 2 < (uint32_t)c->sm_count * TR_TILE_CTAS ? 32 : 64;
+        if (const char* e = getenv("TR_TILE_EDGE")) p.ts = atoi(e) == 32 ? 32 : 64;   // experiments
+    }
+    p.tiles_x = (c->width + p.ts - 1) / p.ts;
+    p.tile_row0 = c->band_y0 / p.ts;
+    p.tiles_y = (c->band_y1 - 1) / p.ts - p.tile_row0 + 1;
     p.n_tiles = p.tiles_x * p.tiles_y;
-    if (p.tiles_x > 256 || p.tiles_y > 256) return fail(TR_ERR_UNSUPPORTED, "tr_visibility: frame larger than 16384 pixels on a side");
+    if (p.tiles_x > 256 || p.tiles_y > 256) return fail(TR_ERR_UNSUPPORTED, "tr_visibility: frame or band larger than 256 tiles on a side");
     p.bin_capacity = BIN_CAPACITY;
     p.rec_capacity = (uint32_t)(c->max_triangles ? c->max_triangles : 1);
     TR_TRY(c->bin_entries.ensure((size_t)p.bin_capacity * sizeof(uint2)));
@@ -819,14 +835,11 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     }
     p.scale1 = c->layer[1].scale.as<float>();
 
-    const size_t tile_smem = (size_t)TS * TS * 8 + sizeof(TileRecs);
-    static bool attr_set = false;
-    if (!attr_set) {
-        TR_CUDA(cudaFuncSetAttribute(raster_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-        attr_set = true;
-    }
+    const size_t tile_smem = (size_t)p.ts * p.ts * 8 + sizeof(TileRecs);
+    auto tile_kernel = p.ts == 64 ? raster_tiles_kernel<64> : raster_tiles_kernel<32>;
+    TR_CUDA(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
     int per_sm = 0;
-    TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_tiles_kernel, TILE_THREADS, tile_smem));
+    TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel, TILE_THREADS, tile_smem));
     if (per_sm < 1) return fail(TR_ERR_CUDA, "raster_tiles_kernel does not fit on an SM (smem %zu)", tile_smem);
     uint32_t tile_grid = (uint32_t)(c->sm_count * per_sm);
     if (tile_grid > 2 * p.n_tiles) tile_grid = 2 * p.n_tiles;
@@ -834,7 +847,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     bin_count_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
     bin_scan_kernel<<<1, 1024, 0, c->stream>>>(p);
     bin_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
-    raster_tiles_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
+    tile_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
     resolve_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
     count_launches(5);
     TR_CUDA(cudaGetLastError());
