@@ -54,6 +54,19 @@ def make_scene(wl):
     return scenes.instanced_scene(wl["width"], wl["height"], n_instances=wl["n_instances"], n_lights=wl["n_lights"])
 
 
+def ncu_traffic(kernel, workload, world):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (None if there is no capture of
+    this workload / GPU count)."""
+    p = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("workload") == workload and d.get("n_gpus") == world:
+            return d["bytes_per_launch"].get(kernel)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -404,13 +417,14 @@ def run_b200(args, wl):
             kernels[k] = {"ms": ms, "GB/s": gbs, "hbm_frac": gbs / hbm_peak, "TFLOP/s": tfl, "fp32_frac": tfl / fp32_peak}
         dom = max(shade, key=lambda k: shade[k])
         kd = kernels[dom]
+        traffic = ncu_traffic(dom, args.workload, world)
         if kd["fp32_frac"] >= kd["hbm_frac"]:
             roofline = {"kernel": dom, "bound": "fp32", "achieved": kd["TFLOP/s"], "peak": fp32_peak, "unit": "TFLOP/s",
-                        "frac": kd["fp32_frac"], "traffic": None,
+                        "frac": kd["fp32_frac"], "traffic": traffic,
                         "peak_source": "FFMA-chain microbenchmark in this run (MEASURED_PEAKS.json has no FP32 figure; nominal 74.4)"}
         else:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kd["GB/s"], "peak": hbm_peak, "unit": "GB/s",
-                        "frac": kd["hbm_frac"], "traffic": None, "peak_source": hbm_src}
+                        "frac": kd["hbm_frac"], "traffic": traffic, "peak_source": hbm_src}
         line = {
             "metric": "shaded_mpixels_per_s", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
