@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
         PixelShading ps;
         f3 pos = mk3(0.f, 0.f, 0.f), emission = mk3(0.f, 0.f, 0.f);
         f3 diff = mk3(0.f, 0.f, 0.f), spec = mk3(0.f, 0.f, 0.f), trans = mk3(0.f, 0.f, 0.f);
+        f3 sum_d = mk3(0.f, 0.f, 0.f), sum_t = mk3(0.f, 0.f, 0.f);  // clustered lights: sums before the per-pixel colour factors
         const tr_material_info* mat = nullptr;
         uint32_t my_count = 0, my_base = 0;
         float model_scale = 1.0f;
@@ -269,14 +270,15 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
                 const f3 vec = sub3(mk3(l.px, l.py, l.pz), pos);
                 const float inv_d = frsqrt(dot3(vec, vec));
                 const f3 dir = scale3(vec, inv_d);
+                const float nol_raw = dot3(ps.n, dir), vol = dot3(ps.v, dir);
                 float factor = inv_d * inv_d;
                 if (!TRANS && l.is_spot) {  // lighting.rs:201-203; the transmissive loop has no spotlight factor (:58-92)
                     float theta = -dot3(dir, mk3(l.sx, l.sy, l.sz));
                     factor *= fmaxf((theta - l.cos_outer) * l.inv_eps, 0.0f);
                 }
-                f3 li = scale3(mk3(l.er, l.eg, l.eb), factor);
-                brdf_point_light(ps, vec, dir, li, diff, spec);
-                if (TRANS) trans = add3(trans, mul3(li, btdf_point_light(ps, vec, dir)));
+                const f3 li = scale3(mk3(l.er, l.eg, l.eb), factor);
+                brdf_point_light(ps, vec, nol_raw, vol, li, sum_d, spec);
+                if (TRANS) btdf_point_light(ps, vec, nol_raw, vol, li, sum_t);
                 next = upcoming;
             }
         }
@@ -284,6 +286,8 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
         // ------------------------------------------------------------ epilogue
         float4 out = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // clear colour, main.rs:1592-1602
         if (covered) {
+            diff = add3(diff, mul3(sum_d, ps.c_diff_pi));   // diffuse_brdf's c_diff / pi, once for all clustered lights
+            if (TRANS) trans = add3(trans, mul3(sum_t, ps.base));
             if (TRANS) {
                 const float4 acol = __ldg(reinterpret_cast<const float4*>(&mat->attenuation_colour));
                 IblVolumeRefractionParams ip;

@@ -44,6 +44,7 @@ TRD float to_dielectric_f0(float ior) {
 struct PixelShading {
     f3 n, v;            // unit normal / view (exact regime)
     float nov;          // Dot::new(normal, view), clamped (lib.rs:92-99)
+    float nov_raw;      // n.v before the clamp (the fast light loop derives n.h and v.l' from raw dot products)
     f3 f0, df;          // combined f0 and (f90 - f0)           (lib.rs:425-435)
     f3 c_diff_pi;       // lerp(base, 0, metallic) / pi         (lib.rs:404, 359)
     f3 base;            // diffuse_colour
@@ -52,13 +53,16 @@ struct PixelShading {
     float nov2_term;    // nov^2 (1 - a2) + a2
     // transmission lobe: alpha_t = alpha * clamp(2 ior - 2, 0, 1)       (lib.rs:144-148, 209)
     float at2, at2m1, one_m_at2, nov2_term_t;
+    // hoisted for the fast light loop: sqrt(nov2_term[_t]) and alpha^2 / (2 pi)
+    float s_nov, s_nov_t, a2_2pi, at2_2pi;
 };
 
 TRD PixelShading make_pixel_shading(const MaterialParams& m, f3 n, f3 v, bool with_transmission) {
     PixelShading s;
     s.n = n;
     s.v = v;
-    s.nov = fmaxf(xdot3(n, v), TR_F32_EPSILON);
+    s.nov_raw = xdot3(n, v);
+    s.nov = fmaxf(s.nov_raw, TR_F32_EPSILON);
     float d0 = to_dielectric_f0(m.index_of_refraction);
     f3 dielectric = scale3(scale3(m.specular_colour, d0), m.specular_factor);
     s.f0 = lerp3(dielectric, m.diffuse_colour, m.metallic);
@@ -71,6 +75,9 @@ TRD PixelShading make_pixel_shading(const MaterialParams& m, f3 n, f3 v, bool wi
     s.a2m1 = xsub(s.a2, 1.0f);
     s.one_m_a2 = 1.0f - s.a2;
     s.nov2_term = fmaf(s.nov * s.nov, s.one_m_a2, s.a2);
+    s.s_nov = fsqrt(s.nov2_term);
+    s.a2_2pi = s.a2 * (0.5f * TR_FRAC_1_PI);
+    s.s_nov_t = s.at2_2pi = 0.0f;
     if (with_transmission) {
         float c = xsub(xmul(m.index_of_refraction, 2.0f), 2.0f);
         c = fminf(fmaxf(c, 0.0f), 1.0f);
@@ -79,6 +86,8 @@ TRD PixelShading make_pixel_shading(const MaterialParams& m, f3 n, f3 v, bool wi
         s.at2m1 = xsub(s.at2, 1.0f);
         s.one_m_at2 = 1.0f - s.at2;
         s.nov2_term_t = fmaf(s.nov * s.nov, s.one_m_at2, s.at2);
+        s.s_nov_t = fsqrt(s.nov2_term_t);
+        s.at2_2pi = s.at2 * (0.5f * TR_FRAC_1_PI);
     } else {
         s.at2 = s.at2m1 = s.one_m_at2 = s.nov2_term_t = 0.0f;
     }
@@ -161,55 +170,54 @@ TRD float exact_noh(const PixelShading& s, f3 l) {
     return fmaxf(xdot3(s.n, h), TR_F32_EPSILON);
 }
 
-// d_ggx * v_smith_ggx_correlated given f = noh^2 (a^2 - 1) + 1
-TRD float ggx_d_times_v_f(float f, float nol, float nov, float a2, float one_m_a2, float nov2_term) {
-    float d = a2 * frcp(TR_PI * f * f);
-    float ggx = fmaf(nol, fsqrt(nov2_term), nov * fsqrt(fmaf(nol * nol, one_m_a2, a2)));
-    float vis = ggx > 0.0f ? 0.5f * frcp(ggx) : 0.0f;
-    return d * vis;
+// One GGX lobe of the fast light loop.  For unit v and l': |v + l'|^2 = 2 (1 + v.l'), so with opv = 1 + v.l'
+//   n.h = (n.v + n.l') / sqrt(2 opv),   v.h = opv / sqrt(2 opv)
+// and the halfway vector is never formed.  Returns d_ggx * v_smith_ggx_correlated = (a^2 / 2 pi) / (f^2 ggx)
+// (lib.rs:101-133 merged into one reciprocal; ggx > 0 always because n.v and n.l' are clamped to EPSILON).
+template <typename ExactNoh>
+TRD float ggx_lobe(float noh_num, float opv, float nol, float nov, float a2, float a2m1, float one_m_a2, float s_nov,
+                   float a2_2pi, ExactNoh exact, float& voh) {
+    float inv_h = frsqrt(opv + opv);
+    float noh = fmaxf(noh_num * inv_h, TR_F32_EPSILON);
+    voh = fmaxf(opv * inv_h, TR_F32_EPSILON);
+    float f = fmaf(noh * noh, a2m1, 1.0f);
+    if (f < TR_EXACT_F) {
+        noh = exact();
+        f = xadd(xmul(xmul(noh, noh), a2m1), 1.0f);
+    }
+    float ggx = fmaf(nol, s_nov, nov * fsqrt(fmaf(nol * nol, one_m_a2, a2)));
+    return a2_2pi * frcp(f * f * ggx);
 }
 
-// basic_brdf (lib.rs:377-423) for a point light at offset `vec` from the fragment; `l` = vec / |vec| (fast regime)
-TRD void brdf_point_light(const PixelShading& s, f3 vec, f3 l, f3 light_intensity, f3& diffuse_acc, f3& specular_acc) {
-    f3 hv = add3(s.v, l);
-    float inv = frsqrt(dot3(hv, hv));
-    float noh = fmaxf(dot3(s.n, hv) * inv, TR_F32_EPSILON);
-    float voh = fmaxf(dot3(s.v, hv) * inv, TR_F32_EPSILON);
-    float nol = fmaxf(dot3(s.n, l), TR_F32_EPSILON);
-    float f = fmaf(noh * noh, s.a2m1, 1.0f);
-    if (f < TR_EXACT_F) {
-        noh = exact_noh(s, exact_light_dir(vec));
-        f = xadd(xmul(xmul(noh, noh), s.a2m1), 1.0f);
-    }
+// basic_brdf (lib.rs:377-423) for a point light at offset `vec`; `l` = vec / |vec| (fast), nol_raw = n.l, vol = v.l.
+// Accumulates sum(li * kd) (to be multiplied by c_diff / pi once, after the loop) and sum(li * F * D * V).
+TRD void brdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vol, f3 light, f3& diffuse_sum, f3& specular_acc) {
+    float voh;
+    float nol = fmaxf(nol_raw, TR_F32_EPSILON);
+    float dv = ggx_lobe(s.nov_raw + nol_raw, 1.0f + vol, nol, s.nov, s.a2, s.a2m1, s.one_m_a2, s.s_nov, s.a2_2pi,
+                        [&]() { return exact_noh(s, exact_light_dir(vec)); }, voh);
     f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
-    f3 li = scale3(light_intensity, nol);
+    f3 li = scale3(light, nol);
     float kd = 1.0f - max_element3(fresnel);
-    float dv = ggx_d_times_v_f(f, nol, s.nov, s.a2, s.one_m_a2, s.nov2_term);
-    diffuse_acc = fma3(mul3(li, s.c_diff_pi), kd, diffuse_acc);
+    diffuse_sum = fma3(li, kd, diffuse_sum);
     specular_acc = fma3(mul3(li, fresnel), dv, specular_acc);
 }
 
-// transmission_btdf (lib.rs:200-233) for the same light, unweighted
-TRD f3 btdf_point_light(const PixelShading& s, f3 vec, f3 l) {
-    float ldn = dot3(l, s.n);
-    f3 lr = fma3(s.n, -2.0f * ldn, l);                      // light + 2 n dot(-light, n), lib.rs:211
-    f3 lm = scale3(lr, frsqrt(dot3(lr, lr)));
-    f3 hv = add3(s.v, lm);
-    float inv = frsqrt(dot3(hv, hv));
-    float noh = fmaxf(dot3(s.n, hv) * inv, TR_F32_EPSILON);
-    float voh = fmaxf(dot3(s.v, hv) * inv, TR_F32_EPSILON);
-    float nolm = fmaxf(dot3(s.n, lm), TR_F32_EPSILON);
-    float f = fmaf(noh * noh, s.at2m1, 1.0f);
-    if (f < TR_EXACT_F) {
-        f3 lx = exact_light_dir(vec);
-        f3 lmx = xnormalize3(xadd3(lx, xscale3(xscale3(s.n, 2.0f), -xdot3(lx, s.n))));
-        noh = exact_noh(s, lmx);
-        f = xadd(xmul(xmul(noh, noh), s.at2m1), 1.0f);
-    }
-    float dv = ggx_d_times_v_f(f, nolm, s.nov, s.at2, s.one_m_at2, s.nov2_term_t);
+// transmission_btdf (lib.rs:200-233) for the same light: l' = l - 2 (n.l) n is a reflection, so it is unit,
+// n.l' = -n.l and v.l' = v.l - 2 (n.l)(n.v).  Accumulates sum(light * (1 - F) * D * V) (times base colour after the loop).
+TRD void btdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vol, f3 light, f3& transmission_sum) {
+    float voh;
+    float nolm = fmaxf(-nol_raw, TR_F32_EPSILON);
+    float vlm = fmaf(-2.0f * nol_raw, s.nov_raw, vol);
+    float dv = ggx_lobe(s.nov_raw - nol_raw, 1.0f + vlm, nolm, s.nov, s.at2, s.at2m1, s.one_m_at2, s.s_nov_t, s.at2_2pi,
+                        [&]() {
+                            f3 lx = exact_light_dir(vec);
+                            f3 lmx = xnormalize3(xadd3(lx, xscale3(xscale3(s.n, 2.0f), -xdot3(lx, s.n))));
+                            return exact_noh(s, lmx);
+                        }, voh);
     f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
     f3 t = mk3((1.0f - fresnel.x) * dv, (1.0f - fresnel.y) * dv, (1.0f - fresnel.z) * dv);
-    return mul3(t, s.base);
+    transmission_sum = add3(transmission_sum, mul3(light, t));
 }
 
 // ---- contract-shaped wrappers (used by the tr_eval_* batch evaluators) ----
