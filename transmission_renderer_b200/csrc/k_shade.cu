@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
     const uint32_t n_px = p.px_end - p.px_begin;
     const uint32_t n_tiles = (n_px + TILE - 1) / TILE;
     const bool lights_in_smem = p.n_lights <= MAX_SMEM_LIGHTS;
-    const uint32_t lights_saddr = smem_u32(s_lights);
+    uint32_t lights_saddr = smem_u32(s_lights);
+    asm volatile("mov.u32 %0, %0;" : "+r"(lights_saddr));  // opaque to the optimiser: keep it in a register instead of re-deriving it per light
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
@@ -242,9 +243,9 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
         // ------------------------------------------------------------ clustered lights: warp-wide sorted merge
         // every lane walks its own cluster's list (ascending light ids) through a private pointer; the warp takes the
         // smallest pending id each turn, so all lanes stay converged and each pixel still sums in ascending id order
-        const uint32_t* my_ptr = p.cluster_indices + my_base;
-        const uint32_t* const my_end = my_ptr + my_count;
-        uint32_t next = my_ptr < my_end ? __ldg(my_ptr) : 0xffffffffu;
+        const uint32_t* const my_list = p.cluster_indices + my_base;
+        uint32_t my_i = 0;
+        uint32_t next = my_count ? __ldg(my_list) : 0xffffffffu;
         while (true) {
             const uint32_t m = __reduce_min_sync(0xffffffffu, next);
             if (m == 0xffffffffu) break;
@@ -263,8 +264,8 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
                 l = make_light_s(p.lights, m);
             }
             if (next == m) {
-                my_ptr++;
-                const uint32_t upcoming = my_ptr < my_end ? __ldg(my_ptr) : 0xffffffffu;  // issued early: hidden behind the BRDF
+                my_i++;
+                const uint32_t upcoming = my_i < my_count ? __ldg(my_list + my_i) : 0xffffffffu;  // issued early: hidden behind the BRDF
                 // light_direction_and_attenuation (glam-pbr lib.rs:12-23), fast regime; the exact chain is re-derived
                 // from `vec` inside the BRDF only where it matters (tr_device_pbr.cuh "adaptive exactness")
                 const f3 vec = sub3(mk3(l.px, l.py, l.pz), pos);
