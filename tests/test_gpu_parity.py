@@ -450,3 +450,92 @@ def test_full_frame(oracle, ggx_lut, kind, size):
     d = np.abs(srgb.astype(int) - ref_srgb.astype(int))
     assert d.max() <= SRGB_TOL, f"{(d > SRGB_TOL).sum()} channels off by more than {SRGB_TOL}/255"
     assert times["total_ms"] > 0
+
+
+# ------------------------------------------------------------------------------ edge cases and error behaviour
+def test_light_list_overflow_is_clamped(oracle):
+    """More than MAX_LIGHTS_PER_CLUSTER (128) lights reach one cluster: the reference's append would run into the next
+    cluster's slice (shader/src/lib.rs:640-644); both sides keep the 128 lowest ids instead."""
+    w, h = 128, 72
+    cam = scenes.Camera(w, h, (0.0, 2.0, 5.0), 0.0, -5.0)
+    uniforms = host.make_uniforms(w, h)
+    lights = scenes.hashed_point_lights(200, 77, box=((-1, 1, 0), (1, 3, 2)), intensity=(40.0, 50.0))
+    aabbs, counts, indices = oracle_cluster_lights(oracle, cam, uniforms, lights)
+    assert counts.max() == abi.TR_MAX_LIGHTS_PER_CLUSTER
+    with Renderer(w, h) as r:
+        gpu_setup(r, None, uniforms, abi.default_material(1), lights)
+        r.build_clusters(cam.write_cluster_data())
+        r.assign_lights(cam.assign_lights())
+        gc, gi = r.read_cluster_lights(len(aabbs))
+    np.testing.assert_array_equal(gc, counts)
+    used = np.arange(abi.TR_MAX_LIGHTS_PER_CLUSTER)[None, :] < counts[:, None]
+    np.testing.assert_array_equal(gi.reshape(-1, abi.TR_MAX_LIGHTS_PER_CLUSTER)[used], indices.reshape(-1, abi.TR_MAX_LIGHTS_PER_CLUSTER)[used])
+
+
+def test_empty_view_and_resize(oracle, ggx_lut):
+    """Camera looking away from everything: nothing visible, the frame is the clear colour; then the swapchain-resize
+    path (src/main.rs:996-1166) and a normal frame at the new size."""
+    s = scenes.sphere_grid_scene(320, 180, transmissive_knot=True)
+    away = scenes.Camera(320, 180, (0.0, 3.0, 6.0), 180.0, 60.0)
+    with Renderer(320, 180) as r:
+        _upload_scene(r, ggx_lut, s)
+        r.build_clusters(away.write_cluster_data())
+        r.frame(away.frame_params(host.default_tonemap_params()))
+        assert len(r.read_visible_instances()) <= 1   # only the ground quad's huge bounding sphere survives the cull
+        hdr = oracle.f16_to_f32(r.read_hdr())
+        assert (hdr[..., :3] == 0).all() and (hdr[..., 3] == 1).all()
+        assert (r.read_gbuffer(0)["depth"] == 0).all() and (r.read_gbuffer(1)["depth"] == 0).all()
+        w, h = 200, 120
+        r.resize(w, h)
+        s2 = scenes.sphere_grid_scene(w, h, transmissive_knot=True)
+        cam = s2["camera"]
+        r.set_uniforms(s2["uniforms"])
+        r.build_clusters(cam.write_cluster_data())
+        r.frame(cam.frame_params(host.default_tonemap_params()))
+        got = r.read_hdr()
+        assert got.shape == (h, w, 4)
+        ref = _oracle_frame(oracle, ggx_lut, s2)
+        levels = oracle.build_pyramid(ref["o16"])
+        _, t16 = oracle.shade_transmission_frame(ref["g1"], ref["scene"], levels, ggx_lut, ref["o32"], ref["o16"])
+        assert rel_l2(oracle.f16_to_f32(got)[..., :3], oracle.f16_to_f32(t16)[..., :3]) < REL_L2_TOL
+
+
+def test_error_behaviour():
+    """The boundary never ignores what it does not implement and enforces call order (include/tr_abi.h)."""
+    from transmission_renderer_b200 import TrError
+    cam = scenes.Camera(64, 64)
+    with Renderer(64, 64) as r:
+        m = abi.default_material(1)
+        m["textures"][0, 0] = 3
+        with pytest.raises(TrError) as e:
+            r.set_materials(m)
+        assert e.value.status == -2                                   # TR_ERR_UNSUPPORTED: texture-mapped material
+        p = np.zeros(1, dtype=abi.primitive_info)
+        p["draw_buffer_index"] = 1
+        with pytest.raises(TrError) as e:
+            r.set_primitives(p)
+        assert e.value.status == -2                                   # alpha-clip bucket
+        u = host.make_uniforms(64, 64)
+        u["debug_clusters"] = 1
+        with pytest.raises(TrError) as e:
+            r.set_uniforms(u)
+        assert e.value.status == -2
+        with pytest.raises(TrError) as e:
+            r.shade_opaque(cam.push_constants())
+        assert e.value.status == -6                                   # TR_ERR_STATE: uniforms / G-buffer missing
+        r.set_uniforms(host.make_uniforms(64, 64))
+        r.set_materials(abi.default_material(1))
+        pc = cam.push_constants()
+        pc["acceleration_structure_address"] = 1
+        with pytest.raises(TrError) as e:
+            r.shade_opaque(pc)
+        assert e.value.status == -2                                   # ray-query shadows
+        bad = scenes.Camera(32, 32).push_constants()
+        with pytest.raises(TrError) as e:
+            r.shade_opaque(bad)
+        assert e.value.status == -1                                   # TR_ERR_INVALID_ARG: framebuffer size mismatch
+        with pytest.raises(TrError) as e:
+            r.generate_mips()
+        assert e.value.status == -6
+    with pytest.raises(TrError):
+        Renderer(0, 10)
