@@ -283,7 +283,7 @@ TR_STATIC_ASSERT(sizeof(tr_ibl_volume_refraction_params) == 104, "IblVolumeRefra
 typedef enum {
     TR_OK = 0,
     TR_ERR_INVALID_ARG = -1,
-    TR_ERR_UNSUPPORTED = -2, /* e.g. Textures.* != -1, debug_clusters != 0, RT address != 0 */
+    TR_ERR_UNSUPPORTED = -2, /* e.g. alpha-clip draw buffers, debug_clusters != 0, RT address != 0 */
     TR_ERR_CUDA = -3,
     TR_ERR_NCCL = -4,
     TR_ERR_OOM = -5,
@@ -319,6 +319,10 @@ typedef struct {
     const uint32_t* material_id; /* [h*w]   */
     const float* scale;          /* [h*w] or NULL (layer 0) */
     const float* position;       /* [h*w*3] or NULL */
+    /* forward differences to the right / lower neighbour on the pixel's own triangle: what the 2x2 quad gives the
+     * reference's fragment stage implicitly (texture level of detail; ddx/ddy in lighting.rs:246-249).  NULL => 0. */
+    const float* duv;            /* [h*w*4] du/dx, dv/dx, du/dy, dv/dy */
+    const float* ddepth;         /* [h*w*2] d(frag_coord.z)/dx, /dy */
 } tr_gbuffer_planes;
 
 typedef struct {
@@ -328,6 +332,8 @@ typedef struct {
     uint32_t* material_id;
     float* scale;
     float* position; /* filled only if the layer carries explicit positions */
+    float* duv;      /* filled only once textures are bound (tr_set_texture) */
+    float* ddepth;
 } tr_gbuffer_planes_out;
 
 enum { TR_LAYER_OPAQUE = 0, TR_LAYER_TRANSMISSIVE = 1 };
@@ -359,6 +365,13 @@ TR_API int32_t tr_set_lights(tr_ctx* ctx, const tr_light* lights, uint32_t n);  
 TR_API int32_t tr_set_uniforms(tr_ctx* ctx, const tr_uniforms* uniforms);                    /* set0/b3, main.rs:1231 */
 /* set0/b0[ggx_lut_texture_index]: RGBA8 UNORM, one mip (main.rs:295-330). */
 TR_API int32_t tr_set_ggx_lut(tr_ctx* ctx, const uint8_t* rgba8, uint32_t width, uint32_t height);
+/* set0/b0[index]: one bindless sampled image of the material system (src/descriptor_sets.rs, MAX_IMAGES = 193,
+ * src/main.rs:59), as the loader creates it (src/model_loading.rs:340-379): RGBA8, `srgb` != 0 for R8G8B8A8_SRGB, with
+ * its mip chain.  levels[k] points to mip k, which is max(1, width >> k) x max(1, height >> k) texels, tightly packed.
+ * Sampled with the repeat sampler (linear min/mag/mip, src/main.rs:683-692). */
+#define TR_MAX_IMAGES 193u
+TR_API int32_t tr_set_texture(tr_ctx* ctx, uint32_t index, const uint8_t* const* levels, uint32_t n_levels,
+                              uint32_t width, uint32_t height, int32_t srgb);
 /* vertex bindings 0..2 + index buffer (pipelines.rs:291-307, main.rs:2516-2557). */
 TR_API int32_t tr_set_mesh(tr_ctx* ctx, const float* positions, const float* normals, const float* uvs,
                            uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices);

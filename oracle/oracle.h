@@ -117,7 +117,20 @@ typedef struct {
     const uint32_t* material_id;
     const float* scale;    /* may be NULL */
     const float* position; /* may be NULL => reconstruct from depth */
+    const float* duv;      /* [h*w*4] uv(x+1,y)-uv(x,y), uv(x,y+1)-uv(x,y) on the pixel's own triangle; may be NULL (=> 0) */
+    const float* ddepth;   /* [h*w*2] the same forward differences of frag_coord.z; may be NULL (=> 0) */
 } orc_gbuffer;
+
+/* Bindless sampled images of the material system (descriptor set 0 binding 0, src/descriptor_sets.rs; loader
+ * src/model_loading.rs:340-379): RGBA8, sRGB or UNORM, with the full mip chain the loader creates. */
+typedef struct {
+    uint32_t width, height, levels, srgb;
+    const uint8_t* data[16]; /* RGBA8 per level, level k is max(1, w >> k) x max(1, h >> k) */
+} orc_texture;
+/* texture.sample(sampler, uv) with the repeat sampler (linear min/mag/mip, src/main.rs:683-692) and the level of detail
+ * from the uv differences to the right and lower neighbour (Vulkan: lambda = log2(max(|d(uv*size)/dx|, |d(uv*size)/dy|))) */
+v4 orc_sample_texture(const orc_texture* t, v2 uv, v2 duv_dx, v2 duv_dy);
+float orc_srgb8_to_linear(uint8_t c);
 
 typedef struct {
     const tr_push_constants* pc;
@@ -129,13 +142,22 @@ typedef struct {
     const uint32_t* cluster_light_counts;
     const uint32_t* cluster_light_indices;
     uint32_t n_clusters;
+    const orc_texture* textures; /* may be NULL when no material binds one */
+    uint32_t n_textures;
 } orc_scene;
 
+/* what the 2x2 quad gave the reference's fragment stage implicitly: differences to the right / lower neighbour */
+typedef struct {
+    v2 duv_dx, duv_dy;
+    v3 dpos_dx, dpos_dy; /* world position differences (ddx / ddy of -view_vector, lighting.rs:246-249) */
+} orc_frag_derivatives;
+
 /* `fragment`, shader/src/lib.rs:164-249, for one pixel; returns rgba */
-v4 orc_fragment(v3 position, v3 normal, v2 uv, uint32_t material_id, v4 frag_coord, const orc_scene* s);
+v4 orc_fragment(v3 position, v3 normal, v2 uv, uint32_t material_id, v4 frag_coord, const orc_scene* s,
+                const orc_frag_derivatives* d /* NULL => zero */);
 /* `fragment_transmission`, shader/src/lib.rs:37-162 */
 v4 orc_fragment_transmission(v3 position, v3 normal, v2 uv, uint32_t material_id, float model_scale, v4 frag_coord,
-                             const orc_scene* s, const orc_pyramid* fb, const orc_lut* lut);
+                             const orc_scene* s, const orc_pyramid* fb, const orc_lut* lut, const orc_frag_derivatives* d);
 
 /* Frame drivers: rows [y0,y1), OpenMP over rows.  Outputs are full-frame
  * buffers; any may be NULL.  Opaque: clears to (0,0,0,1) then shades covered
@@ -170,7 +192,8 @@ typedef struct {
 void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_inst, const tr_primitive_info* prims,
                     uint32_t n_prims, const uint32_t* visible_ids, uint32_t n_visible, const tr_push_constants* pc,
                     uint32_t y0, uint32_t y1, float* depth0, float* normal0, float* uv0, uint32_t* mat0, float* depth1,
-                    float* normal1, float* uv1, uint32_t* mat1, float* scale1);
+                    float* normal1, float* uv1, uint32_t* mat1, float* scale1,
+                    float* duv0, float* ddepth0, float* duv1, float* ddepth1 /* derivative planes, any may be NULL */);
 
 int orc_num_threads(void);
 void orc_set_num_threads(int n);

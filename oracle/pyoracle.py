@@ -36,13 +36,20 @@ class Lut(C.Structure):
 
 class GBuffer(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depth", C.c_void_p), ("normal", C.c_void_p),
-                ("uv", C.c_void_p), ("material_id", C.c_void_p), ("scale", C.c_void_p), ("position", C.c_void_p)]
+                ("uv", C.c_void_p), ("material_id", C.c_void_p), ("scale", C.c_void_p), ("position", C.c_void_p),
+                ("duv", C.c_void_p), ("ddepth", C.c_void_p)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("levels", C.c_uint32), ("srgb", C.c_uint32),
+                ("data", C.c_void_p * 16)]
 
 
 class Scene(C.Structure):
     _fields_ = [("pc", C.c_void_p), ("uniforms", C.c_void_p), ("materials", C.c_void_p), ("n_materials", C.c_uint32),
                 ("lights", C.c_void_p), ("n_lights", C.c_uint32), ("cluster_light_counts", C.c_void_p),
-                ("cluster_light_indices", C.c_void_p), ("n_clusters", C.c_uint32)]
+                ("cluster_light_indices", C.c_void_p), ("n_clusters", C.c_uint32), ("textures", C.c_void_p),
+                ("n_textures", C.c_uint32)]
 
 
 class Mesh(C.Structure):
@@ -259,10 +266,48 @@ def _gbuffer_struct(g, w, h):
     k.mat = _c(g["material_id"], np.uint32)
     k.scale = _c(g["scale"], np.float32) if g.get("scale") is not None else None
     k.pos = _c(g["position"], np.float32) if g.get("position") is not None else None
+    k.duv = _c(g["duv"], np.float32) if g.get("duv") is not None else None
+    k.ddepth = _c(g["ddepth"], np.float32) if g.get("ddepth") is not None else None
     s = GBuffer(w, h, k.depth.ctypes.data, k.normal.ctypes.data, k.uv.ctypes.data if k.uv is not None else None,
                 k.mat.ctypes.data, k.scale.ctypes.data if k.scale is not None else None,
-                k.pos.ctypes.data if k.pos is not None else None)
+                k.pos.ctypes.data if k.pos is not None else None, k.duv.ctypes.data if k.duv is not None else None,
+                k.ddepth.ctypes.data if k.ddepth is not None else None)
     return s, k
+
+
+def make_texture_array(textures):
+    """textures: list of dict(levels=[(h, w, 4) uint8 ...], srgb=bool).  Returns (ctypes array, keep-alive)."""
+    arr = (Texture * max(len(textures), 1))()
+    keep = []
+    for i, t in enumerate(textures):
+        lv = [_c(l, np.uint8) for l in t["levels"]]
+        keep.append(lv)
+        arr[i].height, arr[i].width = lv[0].shape[0], lv[0].shape[1]
+        arr[i].levels = len(lv)
+        arr[i].srgb = 1 if t["srgb"] else 0
+        for k, l in enumerate(lv):
+            arr[i].data[k] = l.ctypes.data
+    return arr, keep
+
+
+def sample_texture(texture, uv, duv_dx, duv_dy):
+    """uv, duv_dx, duv_dy: (n, 2).  Returns (n, 4) float32."""
+    arr, keep = make_texture_array([texture])
+    uv, dx, dy = (_c(a, np.float32).reshape(-1, 2) for a in (uv, duv_dx, duv_dy))
+    L = lib()
+    out = np.zeros((len(uv), 4), np.float32)
+
+    class V2(C.Structure):
+        _fields_ = [("x", C.c_float), ("y", C.c_float)]
+
+    class V4(C.Structure):
+        _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("w", C.c_float)]
+    L.orc_sample_texture.restype = V4
+    L.orc_sample_texture.argtypes = [C.c_void_p, V2, V2, V2]
+    for i in range(len(uv)):
+        r = L.orc_sample_texture(C.addressof(arr[0]), V2(*uv[i]), V2(*dx[i]), V2(*dy[i]))
+        out[i] = (r.x, r.y, r.z, r.w)
+    return out
 
 
 def _scene_struct(sc):
@@ -273,8 +318,10 @@ def _scene_struct(sc):
     k.l = _c(sc["lights"], abi.light) if len(sc["lights"]) else np.zeros(1, dtype=abi.light)
     k.cc = _c(sc["cluster_light_counts"], np.uint32)
     k.ci = _c(sc["cluster_light_indices"], np.uint32)
+    k.tex, k.tex_keep = make_texture_array(sc.get("textures") or [])
+    n_tex = len(sc.get("textures") or [])
     s = Scene(k.pc.ctypes.data, k.u.ctypes.data, k.m.ctypes.data, len(k.m), k.l.ctypes.data, len(sc["lights"]),
-              k.cc.ctypes.data, k.ci.ctypes.data, len(k.cc))
+              k.cc.ctypes.data, k.ci.ctypes.data, len(k.cc), C.addressof(k.tex) if n_tex else None, n_tex)
     return s, k
 
 
@@ -317,8 +364,9 @@ def tonemap_frame(hdr16, params, y0=0, y1=None):
     return out
 
 
-def visibility(mesh, instances, primitives, visible_ids, push_constants, y0=0, y1=None):
-    """mesh: dict(positions (n,3), normals (n,3), uvs (n,2), indices (m,)).  Returns two G-buffer dicts."""
+def visibility(mesh, instances, primitives, visible_ids, push_constants, y0=0, y1=None, derivatives=False):
+    """mesh: dict(positions (n,3), normals (n,3), uvs (n,2), indices (m,)).  Returns two G-buffer dicts; with
+    derivatives=True each also carries the duv (h,w,4) / ddepth (h,w,2) forward-difference planes."""
     pos = _c(mesh["positions"], np.float32)
     nrm = _c(mesh["normals"], np.float32)
     uvs = _c(mesh["uvs"], np.float32)
@@ -334,13 +382,15 @@ def visibility(mesh, instances, primitives, visible_ids, push_constants, y0=0, y
     for _ in range(2):
         layers.append(dict(depth=np.zeros((h, w), np.float32), normal=np.zeros((h, w, 3), np.float32),
                            uv=np.zeros((h, w, 2), np.float32), material_id=np.full((h, w), 0xFFFFFFFF, np.uint32),
-                           scale=np.zeros((h, w), np.float32), position=None))
+                           scale=np.zeros((h, w), np.float32), position=None,
+                           duv=np.zeros((h, w, 4), np.float32) if derivatives else None,
+                           ddepth=np.zeros((h, w, 2), np.float32) if derivatives else None))
     a, b = layers
     lib().orc_visibility(C.byref(m), _p(instances), C.c_uint32(len(instances)), _p(primitives),
                          C.c_uint32(len(primitives)), _p(visible_ids), C.c_uint32(len(visible_ids)), _p(pc),
                          C.c_uint32(y0), C.c_uint32(y1), _p(a["depth"]), _p(a["normal"]), _p(a["uv"]),
                          _p(a["material_id"]), _p(b["depth"]), _p(b["normal"]), _p(b["uv"]), _p(b["material_id"]),
-                         _p(b["scale"]))
+                         _p(b["scale"]), _p(a["duv"]), _p(a["ddepth"]), _p(b["duv"]), _p(b["ddepth"]))
     a["scale"] = None
     return a, b
 

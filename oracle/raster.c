@@ -161,6 +161,25 @@ static int eval_pixel(const tri_setup* s, int px, int py, float l[3], float* dep
     return 1;
 }
 
+/* barycentrics / depth of the triangle's plane at a pixel centre WITHOUT the coverage test: what a helper invocation of
+ * the 2x2 quad evaluates for the derivatives.  Returns 0 where the plane has no valid perspective division. */
+static int eval_plane(const tri_setup* s, int px, int py, float l[3], float* depth) {
+    double qx = (double)px + 0.5, qy = (double)py + 0.5;
+    double E[3];
+    for (int i = 0; i < 3; i++) E[i] = (s->A[i] * qx + s->B[i] * qy) + s->C[i];
+    double S = (E[0] + E[1]) + E[2];
+    if (!(S > 0.0)) return 0;
+    double r = 1.0 / S;
+    l[0] = (float)(E[0] * r);
+    l[1] = (float)(E[1] * r);
+    l[2] = (float)(E[2] * r);
+    float zq = (l[0] * s->Z[0] + l[1] * s->Z[1]) + l[2] * s->Z[2];
+    float wq = (l[0] * s->W[0] + l[1] * s->W[1]) + l[2] * s->W[2];
+    if (!(wq > 0.0f)) return 0;
+    *depth = zq / wq;
+    return 1;
+}
+
 static void atomic_max_u64(uint64_t* addr, uint64_t v) {
     uint64_t cur = __atomic_load_n(addr, __ATOMIC_RELAXED);
     while (cur < v && !__atomic_compare_exchange_n(addr, &cur, v, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
@@ -172,7 +191,8 @@ static uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_inst, const tr_primitive_info* prims,
                     uint32_t n_prims, const uint32_t* visible_ids, uint32_t n_visible, const tr_push_constants* pc,
                     uint32_t y0, uint32_t y1, float* depth0, float* normal0, float* uv0, uint32_t* mat0, float* depth1,
-                    float* normal1, float* uv1, uint32_t* mat1, float* scale1) {
+                    float* normal1, float* uv1, uint32_t* mat1, float* scale1, float* duv0, float* ddepth0, float* duv1,
+                    float* ddepth1) {
     (void)n_prims;
     uint32_t width = pc->framebuffer_size.x, height = pc->framebuffer_size.y;
     m4 pv;
@@ -222,6 +242,8 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
         float* normal = layer == 0 ? normal0 : normal1;
         float* uv = layer == 0 ? uv0 : uv1;
         uint32_t* mat = layer == 0 ? mat0 : mat1;
+        float* duv = layer == 0 ? duv0 : duv1;
+        float* ddepth = layer == 0 ? ddepth0 : ddepth1;
 #pragma omp parallel for schedule(dynamic, 4)
         for (int64_t yy = (int64_t)y0; yy < (int64_t)y1; yy++) {
             for (uint32_t x = 0; x < width; x++) {
@@ -233,6 +255,8 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
                     uv[i * 2] = uv[i * 2 + 1] = 0.0f;
                     mat[i] = 0xffffffffu;
                     if (layer == 1 && scale1) scale1[i] = 0.0f;
+                    if (duv) duv[i * 4] = duv[i * 4 + 1] = duv[i * 4 + 2] = duv[i * 4 + 3] = 0.0f;
+                    if (ddepth) ddepth[i * 2] = ddepth[i * 2 + 1] = 0.0f;
                     continue;
                 }
                 uint32_t gtid = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
@@ -265,6 +289,21 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
                 uv[i * 2 + 1] = (l[0] * u0[1] + l[1] * u1[1]) + l[2] * u2[1];
                 mat[i] = inst[ii].material_id;
                 if (layer == 1 && scale1) scale1[i] = inst[ii].transform.translation_and_scale.w;
+                if (duv || ddepth) { /* forward differences to (x+1, y) and (x, y+1) on this triangle's plane */
+                    for (int k = 0; k < 2; k++) {
+                        float ln[3], dn;
+                        float du = 0.0f, dv = 0.0f, dd = 0.0f;
+                        if (eval_plane(&s, (int)x + (k == 0), (int)yy + (k == 1), ln, &dn)) {
+                            float un = (ln[0] * u0[0] + ln[1] * u1[0]) + ln[2] * u2[0];
+                            float vn = (ln[0] * u0[1] + ln[1] * u1[1]) + ln[2] * u2[1];
+                            du = un - uv[i * 2 + 0];
+                            dv = vn - uv[i * 2 + 1];
+                            dd = dn - d;
+                        }
+                        if (duv) { duv[i * 4 + k * 2] = du; duv[i * 4 + k * 2 + 1] = dv; }
+                        if (ddepth) ddepth[i * 2 + k] = dd;
+                    }
+                }
             }
         }
     }

@@ -7,8 +7,9 @@
  *   shared-structs/src/lib.rs:43-67, 90-138
  * plus the sampling rules the Vulkan implementation supplied in the reference
  *  and the G-buffer decode that stands in for the
- * rasteriser's varying interpolation.  Texture-mapped branches
- * (`textures.* != -1`) are out of scope and rejected upstream.
+ * rasteriser's varying interpolation, including the texture-mapped branches
+ * (`textures.* != -1`: lighting.rs:222-313, lib.rs:66-77,120-124,190-194) with a
+ * software restatement of the repeat sampler and implicit level of detail.
  * PARITY UNPINNED (oracle.h).
  */
 #include "oracle.h"
@@ -182,21 +183,138 @@ v2 orc_sample_lut(const orc_lut* lut, float n_dot_v, float roughness) {
 }
 
 /* ------------------------------------------------------------------ */
+/* material textures: texture.sample(sampler, uv), shader/src/lib.rs:251-267 */
+/* sampler = linear min/mag, linear mip, REPEAT (default address mode),  */
+/* min_lod 0, max_lod NONE, no anisotropy (src/main.rs:683-692)          */
+/* ------------------------------------------------------------------ */
+float orc_srgb8_to_linear(uint8_t c) { /* R8G8B8A8_SRGB decode, evaluated in double and rounded once */
+    double x = (double)c / 255.0;
+    return (float)(x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4));
+}
+
+static void repeat_setup(float u, uint32_t size, uint32_t* i0, uint32_t* i1, float* frac) {
+    float p = u * (float)size - 0.5f;
+    if (!(p == p) || !(fabsf(p) < 1.0e9f)) p = 0.0f; /* NaN / absurd coordinate -> texel 0 */
+    float fl = floorf(p);
+    int64_t i = (int64_t)fl, n = (int64_t)size;
+    int64_t a = i % n, b = (i + 1) % n;
+    *i0 = (uint32_t)(a < 0 ? a + n : a);
+    *i1 = (uint32_t)(b < 0 ? b + n : b);
+    *frac = p - fl;
+}
+
+static v4 sample_texture_level(const orc_texture* t, uint32_t level, v2 uv) {
+    uint32_t w = t->width >> level, h = t->height >> level;
+    if (w == 0) w = 1;
+    if (h == 0) h = 1;
+    const uint8_t* d = t->data[level];
+    uint32_t x0, x1, y0, y1;
+    float fx, fy;
+    repeat_setup(uv.x, w, &x0, &x1, &fx);
+    repeat_setup(uv.y, h, &y0, &y1, &fy);
+    float out[4];
+    for (int c = 0; c < 4; c++) {
+        uint8_t b00 = d[((size_t)y0 * w + x0) * 4 + c], b10 = d[((size_t)y0 * w + x1) * 4 + c];
+        uint8_t b01 = d[((size_t)y1 * w + x0) * 4 + c], b11 = d[((size_t)y1 * w + x1) * 4 + c];
+        int decode = t->srgb && c < 3; /* alpha is linear in the sRGB formats */
+        float t00 = decode ? orc_srgb8_to_linear(b00) : (float)b00 / 255.0f;
+        float t10 = decode ? orc_srgb8_to_linear(b10) : (float)b10 / 255.0f;
+        float t01 = decode ? orc_srgb8_to_linear(b01) : (float)b01 / 255.0f;
+        float t11 = decode ? orc_srgb8_to_linear(b11) : (float)b11 / 255.0f;
+        out[c] = lerpf(lerpf(t00, t10, fx), lerpf(t01, t11, fx), fy);
+    }
+    return v4_new(out[0], out[1], out[2], out[3]);
+}
+
+v4 orc_sample_texture(const orc_texture* t, v2 uv, v2 duv_dx, v2 duv_dy) {
+    /* scale factor rho of the Vulkan level-of-detail operation, in level-0 texels per pixel */
+    float ux = duv_dx.x * (float)t->width, vx = duv_dx.y * (float)t->height;
+    float uy = duv_dy.x * (float)t->width, vy = duv_dy.y * (float)t->height;
+    float rho2 = f_max(ux * ux + vx * vx, uy * uy + vy * vy);
+    float lod = 0.5f * orc_log2_spec(rho2); /* log2(rho); -inf for rho == 0 */
+    float max_lod = (float)(t->levels - 1);
+    if (!(lod > 0.0f)) lod = 0.0f;
+    if (lod > max_lod) lod = max_lod;
+    float l0f = floorf(lod);
+    uint32_t l0 = (uint32_t)l0f;
+    uint32_t l1 = l0 + 1 < t->levels ? l0 + 1 : t->levels - 1;
+    float f = lod - l0f;
+    v4 a = sample_texture_level(t, l0, uv), b = sample_texture_level(t, l1, uv);
+    return v4_new(lerpf(a.x, b.x, f), lerpf(a.y, b.y, f), lerpf(a.z, b.z, f), lerpf(a.w, b.w, f));
+}
+
+/* ------------------------------------------------------------------ */
 /* fragment stage                                                       */
 /* ------------------------------------------------------------------ */
 static v3 from_a(tr_vec3a a) { return v3_new(a.x, a.y, a.z); }
 
-/* lighting.rs:261-301 with every texture index == -1 */
-static orc_material_params get_material_params(tr_vec4 diffuse, const tr_material_info* m) {
+typedef struct { /* TextureSampler, shader/src/lib.rs:251-267 */
+    const orc_scene* s;
+    v2 uv, duv_dx, duv_dy;
+} texture_sampler;
+
+static v4 tex_sample(const texture_sampler* ts, int32_t id) {
+    if (!ts->s->textures || (uint32_t)id >= ts->s->n_textures) return v4_new(0.0f, 0.0f, 0.0f, 0.0f); /* robust access */
+    return orc_sample_texture(&ts->s->textures[id], ts->uv, ts->duv_dx, ts->duv_dy);
+}
+
+/* lighting.rs:261-301 */
+static orc_material_params get_material_params(tr_vec4 diffuse, const tr_material_info* m, const texture_sampler* ts) {
     orc_material_params r;
+    float metallic = m->metallic_factor, roughness = m->roughness_factor;
+    if (m->textures.metallic_roughness != -1) {
+        v4 sample = tex_sample(ts, m->textures.metallic_roughness);
+        metallic *= sample.z; /* "These two are switched!" lighting.rs:272-276 */
+        roughness *= sample.y;
+    }
+    v3 specular_colour = from_a(m->specular_colour_factor);
+    if (m->textures.specular_colour != -1) {
+        v4 sample = tex_sample(ts, m->textures.specular_colour);
+        specular_colour = v3_mul(specular_colour, v3_new(sample.x, sample.y, sample.z));
+    }
+    float specular_factor = m->specular_factor;
+    if (m->textures.specular != -1) specular_factor *= tex_sample(ts, m->textures.specular).w;
     r.diffuse_colour = v3_new(diffuse.x, diffuse.y, diffuse.z);
-    r.metallic = m->metallic_factor;
-    r.perceptual_roughness = m->roughness_factor;
+    r.metallic = metallic;
+    r.perceptual_roughness = roughness;
     r.index_of_refraction = m->index_of_refraction;
-    r.specular_colour = from_a(m->specular_colour_factor);
-    r.specular_factor = m->specular_factor;
+    r.specular_colour = specular_colour;
+    r.specular_factor = specular_factor;
     return r;
 }
+
+/* lighting.rs:303-313 */
+static v3 get_emission(const tr_material_info* m, const texture_sampler* ts) {
+    v3 e = from_a(m->emissive_factor);
+    if (m->textures.emissive != -1) {
+        v4 sample = tex_sample(ts, m->textures.emissive);
+        e = v3_mul(e, v3_new(sample.x, sample.y, sample.z));
+    }
+    return e;
+}
+
+/* lighting.rs:222-259: calculate_normal + compute_cotangent_frame; `position` there is -view_vector, whose ddx / ddy are
+ * the world-position differences */
+static v3 calculate_normal(v3 interpolated_normal, const texture_sampler* ts, const tr_material_info* m,
+                           const orc_frag_derivatives* d) {
+    v3 normal = v3_normalize(interpolated_normal);
+    if (m->textures.normal_map != -1) {
+        v4 smp = tex_sample(ts, m->textures.normal_map);
+        float k = 128.0f / 127.0f;
+        v3 map_normal = v3_new(smp.x * 255.0f / 127.0f - k, smp.y * 255.0f / 127.0f - k, smp.z * 255.0f / 127.0f - k);
+        v3 dp1 = d->dpos_dx, dp2 = d->dpos_dy;
+        v3 dp2perp = v3_cross(dp2, normal), dp1perp = v3_cross(normal, dp1);
+        v3 t = v3_add(v3_scale(dp2perp, d->duv_dx.x), v3_scale(dp1perp, d->duv_dy.x));
+        v3 b = v3_add(v3_scale(dp2perp, d->duv_dx.y), v3_scale(dp1perp, d->duv_dy.y));
+        float invmax = 1.0f / sqrtf(f_max(v3_dot(t, t), v3_dot(b, b)));
+        v3 c0 = v3_scale(t, invmax), c1 = v3_scale(b, invmax);
+        v3 r = v3_add(v3_add(v3_scale(c0, map_normal.x), v3_scale(c1, map_normal.y)), v3_scale(normal, map_normal.z));
+        normal = v3_normalize(r);
+    }
+    return normal;
+}
+
+static const orc_frag_derivatives k_zero_derivatives = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
 
 /* shader/src/lib.rs:88-98 / 205-215; robust-buffer-access semantics for an out-of-range cluster */
 static uint32_t cluster_index(v4 frag_coord, const tr_uniforms* u) {
@@ -216,16 +334,22 @@ static v3 light_emission(const tr_light* l) {
 }
 
 /* shader/src/lib.rs:164-249 + lighting.rs:145-220 */
-v4 orc_fragment(v3 position, v3 normal_in, v2 uv, uint32_t material_id, v4 frag_coord, const orc_scene* s) {
-    (void)uv;
+v4 orc_fragment(v3 position, v3 normal_in, v2 uv, uint32_t material_id, v4 frag_coord, const orc_scene* s,
+                const orc_frag_derivatives* d) {
+    if (!d) d = &k_zero_derivatives;
     const tr_material_info* material = &s->materials[material_id];
+    texture_sampler ts = {s, uv, d->duv_dx, d->duv_dy};
     tr_vec4 diffuse = material->diffuse_factor;
+    if (material->textures.diffuse != -1) { /* lib.rs:190-194 */
+        v4 smp = tex_sample(&ts, material->textures.diffuse);
+        diffuse.x *= smp.x; diffuse.y *= smp.y; diffuse.z *= smp.z; diffuse.w *= smp.w;
+    }
 
     v3 view_vector = v3_sub(from_a(s->pc->view_position), position);
     v3 view = v3_normalize(view_vector);
-    v3 normal = v3_normalize(normal_in); /* lighting.rs:229 */
-    orc_material_params mp = get_material_params(diffuse, material);
-    v3 emission = from_a(material->emissive_factor); /* lighting.rs:303-313 */
+    v3 normal = calculate_normal(normal_in, &ts, material, d); /* lighting.rs:222-241 */
+    orc_material_params mp = get_material_params(diffuse, material, &ts);
+    v3 emission = get_emission(material, &ts); /* lighting.rs:303-313 */
 
     uint32_t cluster = cluster_index(frag_coord, s->uniforms);
     uint32_t num_lights = cluster < s->n_clusters ? s->cluster_light_counts[cluster] : 0u;
@@ -254,17 +378,23 @@ v4 orc_fragment(v3 position, v3 normal_in, v2 uv, uint32_t material_id, v4 frag_
 
 /* shader/src/lib.rs:37-162 + lighting.rs:13-95 */
 v4 orc_fragment_transmission(v3 position, v3 normal_in, v2 uv, uint32_t material_id, float model_scale, v4 frag_coord,
-                             const orc_scene* s, const orc_pyramid* fb, const orc_lut* lut) {
-    (void)uv;
+                             const orc_scene* s, const orc_pyramid* fb, const orc_lut* lut, const orc_frag_derivatives* d) {
+    if (!d) d = &k_zero_derivatives;
     const tr_material_info* material = &s->materials[material_id];
+    texture_sampler ts = {s, uv, d->duv_dx, d->duv_dy};
     tr_vec4 diffuse = material->diffuse_factor;
+    if (material->textures.diffuse != -1) { /* lib.rs:66-69 */
+        v4 smp = tex_sample(&ts, material->textures.diffuse);
+        diffuse.x *= smp.x; diffuse.y *= smp.y; diffuse.z *= smp.z; diffuse.w *= smp.w;
+    }
     float transmission_factor = material->transmission_factor;
+    if (material->textures.transmission != -1) transmission_factor *= tex_sample(&ts, material->textures.transmission).x; /* :71-77 */
 
     v3 view_vector = v3_sub(from_a(s->pc->view_position), position);
     v3 view = v3_normalize(view_vector);
-    v3 normal = v3_normalize(normal_in);
-    orc_material_params mp = get_material_params(diffuse, material);
-    v3 emission = from_a(material->emissive_factor);
+    v3 normal = calculate_normal(normal_in, &ts, material, d);
+    orc_material_params mp = get_material_params(diffuse, material, &ts);
+    v3 emission = get_emission(material, &ts);
 
     uint32_t cluster = cluster_index(frag_coord, s->uniforms);
     uint32_t num_lights = cluster < s->n_clusters ? s->cluster_light_counts[cluster] : 0u;
@@ -290,7 +420,8 @@ v4 orc_fragment_transmission(v3 position, v3 normal_in, v2 uv, uint32_t material
                                                    orc_transmission_btdf(mp, normal, view, direction)));
     }
 
-    float thickness = material->thickness_factor; /* lib.rs:120 */
+    float thickness = material->thickness_factor; /* lib.rs:120-124 */
+    if (material->textures.thickness != -1) thickness *= tex_sample(&ts, material->textures.thickness).y;
 
     orc_ibl_params ip;
     ip.material_params = mp;
@@ -324,6 +455,23 @@ static v3 decode_position(const orc_gbuffer* g, const m4* inv_pv, uint32_t x, ui
     return v3_new(h.x / h.w, h.y / h.w, h.z / h.w);
 }
 
+/* differences to the right / lower neighbour on the pixel's own triangle, from the derivative planes of the G-buffer */
+static orc_frag_derivatives decode_derivatives(const orc_gbuffer* g, const m4* inv_pv, uint32_t x, uint32_t y, float depth, v3 pos) {
+    orc_frag_derivatives d = k_zero_derivatives;
+    size_t i = (size_t)y * g->width + x;
+    if (g->duv) {
+        d.duv_dx.x = g->duv[i * 4]; d.duv_dx.y = g->duv[i * 4 + 1];
+        d.duv_dy.x = g->duv[i * 4 + 2]; d.duv_dy.y = g->duv[i * 4 + 3];
+    }
+    if (g->ddepth && !g->position) {
+        v3 px = decode_position(g, inv_pv, x + 1, y, depth + g->ddepth[i * 2]);
+        v3 py = decode_position(g, inv_pv, x, y + 1, depth + g->ddepth[i * 2 + 1]);
+        d.dpos_dx = v3_sub(px, pos);
+        d.dpos_dy = v3_sub(py, pos);
+    }
+    return d;
+}
+
 static void store_px(float* f32buf, uint16_t* a, uint16_t* b, size_t i, v4 c) {
     if (f32buf) {
         f32buf[i * 4] = c.x; f32buf[i * 4 + 1] = c.y; f32buf[i * 4 + 2] = c.z; f32buf[i * 4 + 3] = c.w;
@@ -351,7 +499,8 @@ void orc_shade_opaque_frame(const orc_gbuffer* g, const orc_scene* s, uint32_t y
                 v3 n = v3_new(g->normal[i * 3], g->normal[i * 3 + 1], g->normal[i * 3 + 2]);
                 v2 uv = {g->uv ? g->uv[i * 2] : 0.0f, g->uv ? g->uv[i * 2 + 1] : 0.0f};
                 v4 fc = v4_new((float)x + 0.5f, (float)y + 0.5f, depth, 1.0f);
-                c = orc_fragment(pos, n, uv, g->material_id[i], fc, s);
+                orc_frag_derivatives d = decode_derivatives(g, &inv_pv, x, y, depth, pos);
+                c = orc_fragment(pos, n, uv, g->material_id[i], fc, s, &d);
             }
             store_px(hdr_f32, hdr_f16, opaque_f16, i, c);
         }
@@ -376,7 +525,8 @@ void orc_shade_transmission_frame(const orc_gbuffer* g, const orc_scene* s, cons
             v2 uv = {g->uv ? g->uv[i * 2] : 0.0f, g->uv ? g->uv[i * 2 + 1] : 0.0f};
             v4 fc = v4_new((float)x + 0.5f, (float)y + 0.5f, depth, 1.0f);
             float scale = g->scale ? g->scale[i] : 1.0f;
-            v4 c = orc_fragment_transmission(pos, n, uv, g->material_id[i], scale, fc, s, fb, lut);
+            orc_frag_derivatives d = decode_derivatives(g, &inv_pv, x, y, depth, pos);
+            v4 c = orc_fragment_transmission(pos, n, uv, g->material_id[i], scale, fc, s, fb, lut, &d);
             store_px(hdr_f32, hdr_f16, NULL, i, c);
         }
     }

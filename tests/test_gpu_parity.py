@@ -506,10 +506,10 @@ def test_error_behaviour():
     cam = scenes.Camera(64, 64)
     with Renderer(64, 64) as r:
         m = abi.default_material(1)
-        m["textures"][0, 0] = 3
+        m["textures"][0, 0] = 500
         with pytest.raises(TrError) as e:
             r.set_materials(m)
-        assert e.value.status == -2                                   # TR_ERR_UNSUPPORTED: texture-mapped material
+        assert e.value.status == -1                                   # TR_ERR_INVALID_ARG: image index beyond MAX_IMAGES
         p = np.zeros(1, dtype=abi.primitive_info)
         p["draw_buffer_index"] = 1
         with pytest.raises(TrError) as e:
@@ -539,3 +539,53 @@ def test_error_behaviour():
         assert e.value.status == -6
     with pytest.raises(TrError):
         Renderer(0, 10)
+
+
+# ------------------------------------------------------------------------------ row N2: texture-mapped materials, normal mapping
+def _textured_reference(oracle, lut, s):
+    cam = s["camera"]
+    pc = cam.push_constants()
+    _, visible = oracle.frustum_culling(s["instances"], s["primitives"], cam.culling())
+    g0, g1 = oracle.visibility(s["mesh"], s["instances"], s["primitives"], visible, pc, derivatives=True)
+    _, cc, ci = oracle_cluster_lights(oracle, cam, s["uniforms"], s["lights"])
+    sc = oracle_scene(pc, s["uniforms"], s["materials"], s["lights"], cc, ci)
+    sc["textures"] = s["textures"]
+    o32, o16 = oracle.shade_opaque_frame(g0, sc)
+    levels = oracle.build_pyramid(o16)
+    t32, t16 = oracle.shade_transmission_frame(g1, sc, levels, lut, o32, o16)
+    return dict(g0=g0, g1=g1, o32=o32, o16=o16, t32=t32, t16=t16)
+
+
+@pytest.mark.parametrize("size", [(640, 360), (333, 187)])
+def test_textured_frame(oracle, ggx_lut, size):
+    """Every texture slot the shaders read (diffuse, metallic-roughness, normal map, emissive, transmission, thickness,
+    specular, specular colour), implicit level of detail from the uv differences, repeat addressing, normal mapping
+    through the cotangent frame — whole frames against the oracle; the derivative planes of the G-buffer bit for bit."""
+    w, h = size
+    s = scenes.textured_sphere_scene(w, h)
+    ref = _textured_reference(oracle, ggx_lut, s)
+    cam = s["camera"]
+    with Renderer(w, h, f32_debug=True) as r:
+        r.set_textures(s["textures"])
+        _upload_scene(r, ggx_lut, s)
+        r.frame(cam.frame_params(host.default_tonemap_params()))
+        for layer, g in ((0, ref["g0"]), (1, ref["g1"])):
+            got = r.read_gbuffer(layer, derivatives=True)
+            for k in ("depth", "uv", "duv", "ddepth"):
+                assert got[k].tobytes() == np.asarray(g[k]).tobytes(), f"layer {layer} plane {k}: {(got[k] != g[k]).sum()} values differ"
+        got32 = r.read_hdr_f32()
+        got_o16 = r.read_pyramid_level(0)
+    duv = ref["g0"]["duv"][ref["g0"]["depth"] > 0]
+    assert np.abs(duv).max() > 1e-3                                           # the level of detail is really exercised
+    e_o = rel_l2(oracle.f16_to_f32(got_o16)[..., :3], oracle.f16_to_f32(ref["o16"])[..., :3])
+    e_t = rel_l2(got32[..., :3], ref["t32"][..., :3])
+    print(f"textured {w}x{h}: opaque fp16 rel-L2 {e_o:.2e}, final fp32 rel-L2 {e_t:.2e}")
+    assert e_o < REL_L2_TOL and e_t < REL_L2_TOL
+    # the textures matter: the same frame with the bindings removed is far away
+    plain = dict(s, materials=s["materials"].copy())
+    plain["materials"]["textures"] = -1
+    with Renderer(w, h, f32_debug=True) as r:
+        _upload_scene(r, ggx_lut, plain)
+        r.frame(cam.frame_params(host.default_tonemap_params()))
+        untextured = r.read_hdr_f32()
+    assert rel_l2(untextured[..., :3], ref["t32"][..., :3]) > 0.05

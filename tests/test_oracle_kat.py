@@ -463,3 +463,79 @@ def test_ibl_volume_refraction_vs_f64(oracle, ggx_lut):
     # the fetch is discontinuous in uv at texel boundaries only through fp32 rounding of uv*size: compare in L2
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-4
     assert np.median(np.abs(got - ref) / (np.abs(ref) + 1e-3)) < 1e-5
+
+
+# ------------------------------------------------------------------------------ row N2: texture sampler known answers
+def _tex(levels, srgb=False):
+    return dict(levels=[np.ascontiguousarray(l, np.uint8) for l in levels], srgb=srgb)
+
+
+def test_srgb_decode_known_values(oracle):
+    L = oracle.lib()
+    L.orc_srgb8_to_linear.restype = C.c_float
+    L.orc_srgb8_to_linear.argtypes = [C.c_uint8]
+    assert L.orc_srgb8_to_linear(0) == 0.0 and L.orc_srgb8_to_linear(255) == 1.0
+    assert abs(L.orc_srgb8_to_linear(128) - 0.21586050) < 1e-7        # ((128/255 + 0.055) / 1.055)^2.4
+    assert abs(L.orc_srgb8_to_linear(10) - 10 / 255 / 12.92) < 1e-9   # linear toe
+
+
+def test_texture_bilinear_and_repeat(oracle):
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (8, 8, 4), dtype=np.uint8)
+    t = _tex([img])
+    z = np.zeros((1, 2), f32)
+    # texel centres return the texel, also one period away (REPEAT, src/main.rs:683-692 default address mode)
+    for (x, y) in ((0, 0), (3, 5), (7, 7)):
+        uv = np.array([[(x + 0.5) / 8, (y + 0.5) / 8]], f32)
+        for shift in ((0, 0), (3, -2), (-1, 1)):
+            got = oracle.sample_texture(t, uv + np.array(shift, f32), z, z)[0]
+            np.testing.assert_allclose(got, img[y, x] / 255.0, atol=2e-6)
+    # half way between two texel centres: their mean; across the border it wraps
+    got = oracle.sample_texture(t, np.array([[4.0 / 8, 2.5 / 8]], f32), z, z)[0]
+    np.testing.assert_allclose(got, (img[2, 3].astype(float) + img[2, 4]) / 2 / 255, atol=2e-6)
+    got = oracle.sample_texture(t, np.array([[0.0, 0.5 / 8]], f32), z, z)[0]
+    np.testing.assert_allclose(got, (img[0, 7].astype(float) + img[0, 0]) / 2 / 255, atol=2e-6)
+
+
+def test_texture_level_of_detail(oracle):
+    # every level a different constant: the sample reveals the level of detail the derivatives select
+    size = 16
+    levels = [np.full((size >> k, size >> k, 4), 40 * k, np.uint8) for k in range(5)]
+    t = _tex(levels)
+    uv = np.array([[0.3, 0.6]], f32)
+    for texels_per_pixel, lod in ((0.5, 0.0), (1.0, 0.0), (2.0, 1.0), (4.0, 2.0), (3.0, math.log2(3.0)), (1000.0, 4.0)):
+        d = np.array([[texels_per_pixel / size, 0.0]], f32)
+        for dx, dy in ((d, 0 * d), (0 * d, d[:, ::-1].copy())):
+            got = oracle.sample_texture(t, uv, dx, dy)[0, 0] * 255.0
+            assert abs(got - 40 * lod) < 1e-2, (texels_per_pixel, got)
+
+
+def test_flat_normal_map_and_unit_textures_change_nothing(oracle, ggx_lut):
+    """A normal map of (128, 128, 255) decodes to (0, 0, 1) exactly (lighting.rs:236) and all-255 textures multiply by
+    one: the fragment must equal the untextured one up to the re-normalisation rounding."""
+    from pipeline import oracle_cluster_lights, oracle_scene
+    from transmission_renderer_b200 import scenes
+    w, h = 96, 54
+    s = scenes.sphere_grid_scene(w, h, grid=3, transmissive_knot=True)
+    cam = s["camera"]
+    pc = cam.push_constants()
+    _, visible = oracle.frustum_culling(s["instances"], s["primitives"], cam.culling())
+    g0, g1 = oracle.visibility(s["mesh"], s["instances"], s["primitives"], visible, pc, derivatives=True)
+    _, cc, ci = oracle_cluster_lights(oracle, cam, s["uniforms"], s["lights"])
+    base = oracle_scene(pc, s["uniforms"], s["materials"], s["lights"], cc, ci)
+    ref32, _ = oracle.shade_opaque_frame(g0, base)
+    white = np.full((4, 4, 4), 255, np.uint8)
+    flat = np.tile(np.array([128, 128, 255, 255], np.uint8), (4, 4, 1))
+    textures = [_tex(scenes.make_mips(white, True), True), _tex(scenes.make_mips(flat, False)), _tex(scenes.make_mips(white, False))]
+    mats = s["materials"].copy()
+    mats["textures"][:, scenes.TEX_SLOTS["diffuse"]] = 0
+    mats["textures"][:, scenes.TEX_SLOTS["normal_map"]] = 1
+    mats["textures"][:, scenes.TEX_SLOTS["metallic_roughness"]] = 2
+    mats["textures"][:, scenes.TEX_SLOTS["specular"]] = 2
+    mats["textures"][:, scenes.TEX_SLOTS["specular_colour"]] = 0
+    tex = dict(base, materials=mats, textures=textures)
+    got32, _ = oracle.shade_opaque_frame(g0, tex)
+    covered = g0["depth"] > 0
+    assert covered.mean() > 0.3
+    a, b = got32[covered][:, :3].astype(np.float64), ref32[covered][:, :3].astype(np.float64)
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 2e-5

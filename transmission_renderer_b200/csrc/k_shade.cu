@@ -110,8 +110,8 @@ __device__ __forceinline__ uint32_t cluster_index(float fx, float fy, float dept
 #ifndef TR_SHADE_CTAS_TRANS
 #define TR_SHADE_CTAS_TRANS 3
 #endif
-template <bool TRANS, bool HAS_POS, bool F32OUT>
-__global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_CTAS_OPAQUE) shade_kernel(const __grid_constant__ tr::ShadeLaunch p) {
+template <bool TRANS, bool HAS_POS, bool F32OUT, bool TEX>
+__global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_CTAS_OPAQUE)) shade_kernel(const __grid_constant__ tr::ShadeLaunch p) {
     using L = StageLayout<TRANS, HAS_POS>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // STAGES barriers
@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
         const tr_material_info* mat = nullptr;
         uint32_t my_count = 0, my_base = 0;
         float model_scale = 1.0f;
+        float roughness_px = 0.0f, transmission_px = 0.0f, thickness_px = 0.0f;  // after their textures (lib.rs:71-77, 120-124)
 
         if (covered) {
             const uint32_t py = g / p.width, px = g - py * p.width;
@@ -209,21 +210,77 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
                 pos = mk3(xdiv(h.x, h.w), xdiv(h.y, h.w), xdiv(h.z, h.w));
             }
             mat = p.materials + s_mat[tid];
-            const float4 dfac = __ldg(reinterpret_cast<const float4*>(&mat->diffuse_factor));
+            float4 dfac = __ldg(reinterpret_cast<const float4*>(&mat->diffuse_factor));
             const float4 emis = __ldg(reinterpret_cast<const float4*>(&mat->emissive_factor));
             const float4 scol = __ldg(reinterpret_cast<const float4*>(&mat->specular_colour_factor));
-            MaterialParams mp;  // get_material_params, lighting.rs:261-301 (no textures)
-            mp.diffuse_colour = mk3(dfac.x, dfac.y, dfac.z);
+            MaterialParams mp;  // get_material_params, lighting.rs:261-301
             mp.metallic = __ldg(&mat->metallic_factor);
             mp.perceptual_roughness = __ldg(&mat->roughness_factor);
             mp.index_of_refraction = __ldg(&mat->index_of_refraction);
             mp.specular_colour = mk3(scol.x, scol.y, scol.z);
             mp.specular_factor = __ldg(&mat->specular_factor);
             emission = mk3(emis.x, emis.y, emis.z);
+            if (TRANS) {
+                transmission_px = __ldg(&mat->transmission_factor);
+                thickness_px = __ldg(&mat->thickness_factor);
+            }
 
             f3 view_pos = mk3(p.view_position[0], p.view_position[1], p.view_position[2]);
             f3 v = xnormalize3(xsub3(view_pos, pos));                                    // lib.rs:196-197
-            f3 nrm = xnormalize3(mk3(s_normal[tid * 3], s_normal[tid * 3 + 1], s_normal[tid * 3 + 2]));  // lighting.rs:229
+            const f3 n_in = mk3(s_normal[tid * 3], s_normal[tid * 3 + 1], s_normal[tid * 3 + 2]);
+            f3 nrm;
+            if (TEX) {
+                // texture-mapped material (exact regime, oracle/shade.c): lib.rs:66-77,120-124,190-194; lighting.rs:222-313
+                const int32_t* tx = &mat->textures.diffuse;
+                TextureSampler ts;
+                ts.textures = p.textures;
+                ts.n_textures = p.n_textures;
+                ts.u = __ldg(p.uv + (size_t)g * 2);
+                ts.v = __ldg(p.uv + (size_t)g * 2 + 1);
+                ts.duv = __ldg(p.duv + g);
+                const int32_t t_diffuse = __ldg(tx + 0), t_mr = __ldg(tx + 1), t_normal = __ldg(tx + 2), t_emissive = __ldg(tx + 3);
+                const int32_t t_specular = __ldg(tx + 7), t_spec_colour = __ldg(tx + 8);
+                if (t_diffuse != -1) {
+                    const f4 smp = ts.sample(t_diffuse);
+                    dfac.x = xmul(dfac.x, smp.x); dfac.y = xmul(dfac.y, smp.y); dfac.z = xmul(dfac.z, smp.z); dfac.w = xmul(dfac.w, smp.w);
+                }
+                f3 dpos_dx = mk3(0.f, 0.f, 0.f), dpos_dy = mk3(0.f, 0.f, 0.f);
+                if (!HAS_POS && t_normal != -1) {  // world positions of the right / lower neighbour on this pixel's triangle
+                    const float2 dd = __ldg(p.ddepth + g);
+                    const float nx1 = xsub(xmul(xdiv((float)(px + 1) + 0.5f, (float)p.width), 2.0f), 1.0f);
+                    const float ny0 = xsub(xmul(xdiv(fy, (float)p.height), 2.0f), 1.0f);
+                    const float nx0 = xsub(xmul(xdiv(fx, (float)p.width), 2.0f), 1.0f);
+                    const float ny1 = xsub(xmul(xdiv((float)(py + 1) + 0.5f, (float)p.height), 2.0f), 1.0f);
+                    const f4 hx = xmat4_mul(p.inv_proj_view, nx1, ny0, xadd(depth, dd.x), 1.0f);
+                    const f4 hy = xmat4_mul(p.inv_proj_view, nx0, ny1, xadd(depth, dd.y), 1.0f);
+                    dpos_dx = xsub3(mk3(xdiv(hx.x, hx.w), xdiv(hx.y, hx.w), xdiv(hx.z, hx.w)), pos);
+                    dpos_dy = xsub3(mk3(xdiv(hy.x, hy.w), xdiv(hy.y, hy.w), xdiv(hy.z, hy.w)), pos);
+                }
+                if (TRANS) {
+                    const int32_t t_transmission = __ldg(tx + 5), t_thickness = __ldg(tx + 6);
+                    if (t_transmission != -1) transmission_px = xmul(transmission_px, ts.sample(t_transmission).x);
+                    if (t_thickness != -1) thickness_px = xmul(thickness_px, ts.sample(t_thickness).y);
+                }
+                nrm = calculate_normal(n_in, t_normal, ts, dpos_dx, dpos_dy);
+                if (t_mr != -1) {
+                    const f4 smp = ts.sample(t_mr);
+                    mp.metallic = xmul(mp.metallic, smp.z);  // "These two are switched!", lighting.rs:272-276
+                    mp.perceptual_roughness = xmul(mp.perceptual_roughness, smp.y);
+                }
+                if (t_spec_colour != -1) {
+                    const f4 smp = ts.sample(t_spec_colour);
+                    mp.specular_colour = mk3(xmul(mp.specular_colour.x, smp.x), xmul(mp.specular_colour.y, smp.y), xmul(mp.specular_colour.z, smp.z));
+                }
+                if (t_specular != -1) mp.specular_factor = xmul(mp.specular_factor, ts.sample(t_specular).w);
+                if (t_emissive != -1) {
+                    const f4 smp = ts.sample(t_emissive);
+                    emission = mk3(xmul(emission.x, smp.x), xmul(emission.y, smp.y), xmul(emission.z, smp.z));
+                }
+            } else {
+                nrm = xnormalize3(n_in);  // lighting.rs:229
+            }
+            mp.diffuse_colour = mk3(dfac.x, dfac.y, dfac.z);
+            roughness_px = mp.perceptual_roughness;
             ps = make_pixel_shading(mp, nrm, v, TRANS);
             if (TRANS) model_scale = s_scale[tid];
 
@@ -294,19 +351,19 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
                 IblVolumeRefractionParams ip;
                 ip.material_params.diffuse_colour = ps.base;
                 ip.material_params.metallic = 0.0f;
-                ip.material_params.perceptual_roughness = __ldg(&mat->roughness_factor);
+                ip.material_params.perceptual_roughness = roughness_px;
                 ip.material_params.index_of_refraction = __ldg(&mat->index_of_refraction);
                 ip.material_params.specular_colour = mk3(0.f, 0.f, 0.f);
                 ip.material_params.specular_factor = 0.0f;
                 ip.normal = ps.n;
                 ip.view = ps.v;
                 ip.position = pos;
-                ip.thickness = __ldg(&mat->thickness_factor);            // lib.rs:120
+                ip.thickness = thickness_px;                                // lib.rs:120-124
                 ip.model_scale = model_scale;
                 ip.attenuation_distance = __ldg(&mat->attenuation_distance);
                 ip.attenuation_colour = mk3(acol.x, acol.y, acol.z);
                 trans = add3(trans, ibl_volume_refraction(ip, p.proj_view, p.log2_size_x, p.pyramid, p.lut, ps.f0, ps.df));
-                const float tf = __ldg(&mat->transmission_factor);
+                const float tf = transmission_px;
                 f3 real_t = scale3(trans, tf);                              // lib.rs:157
                 diff = lerp3(diff, real_t, tf);                             // lib.rs:159
             }
@@ -351,7 +408,7 @@ __global__ void __launch_bounds__(TILE, TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_C
     }
 }
 
-template <bool TRANS, bool HAS_POS, bool F32OUT>
+template <bool TRANS, bool HAS_POS, bool F32OUT, bool TEX>
 int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
     using L = StageLayout<TRANS, HAS_POS>;
     const uint32_t n_px = p.px_end - p.px_begin;
@@ -359,7 +416,7 @@ int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
     const uint32_t n_tiles = (n_px + TILE - 1) / TILE;
     const uint32_t n_smem_lights = p.n_lights <= (uint32_t)MAX_SMEM_LIGHTS ? p.n_lights : 0u;
     const size_t smem = 128 + (size_t)STAGES * L::kBytes + (size_t)n_smem_lights * sizeof(LightS);
-    auto kern = shade_kernel<TRANS, HAS_POS, F32OUT>;
+    auto kern = shade_kernel<TRANS, HAS_POS, F32OUT, TEX>;
     TR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE, smem));
@@ -375,10 +432,16 @@ int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
 template <bool TRANS>
 int32_t launch_any(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
     const bool pos = p.position != nullptr, f32 = p.hdr_f32 != nullptr;
-    if (pos && f32) return launch_variant<TRANS, true, true>(p, sm_count, s);
-    if (pos) return launch_variant<TRANS, true, false>(p, sm_count, s);
-    if (f32) return launch_variant<TRANS, false, true>(p, sm_count, s);
-    return launch_variant<TRANS, false, false>(p, sm_count, s);
+    if (p.textures != nullptr) {  // some material binds a texture
+        if (pos && f32) return launch_variant<TRANS, true, true, true>(p, sm_count, s);
+        if (pos) return launch_variant<TRANS, true, false, true>(p, sm_count, s);
+        if (f32) return launch_variant<TRANS, false, true, true>(p, sm_count, s);
+        return launch_variant<TRANS, false, false, true>(p, sm_count, s);
+    }
+    if (pos && f32) return launch_variant<TRANS, true, true, false>(p, sm_count, s);
+    if (pos) return launch_variant<TRANS, true, false, false>(p, sm_count, s);
+    if (f32) return launch_variant<TRANS, false, true, false>(p, sm_count, s);
+    return launch_variant<TRANS, false, false, false>(p, sm_count, s);
 }
 
 }  // namespace

@@ -67,6 +67,8 @@ struct VisParams {
     float* uv[2];
     uint32_t* material_id[2];
     float* scale1;
+    float4* duv[2];               // derivative planes (nullptr unless some material binds a texture)
+    float2* ddepth[2];
 };
 
 struct TriSetup {
@@ -218,6 +220,25 @@ __device__ __forceinline__ bool eval_pixel(const TriSetup& s, int px, int py, fl
     const float d = xdiv(zq, wq);
     if (!(d > 0.0f) || d > 1.0f) return false;
     depth = d;
+    return true;
+}
+
+// oracle/raster.c eval_plane: barycentrics / depth of the triangle's plane at a pixel centre without the coverage test
+__device__ __forceinline__ bool eval_plane(const TriSetup& s, int px, int py, float l[3], float& depth) {
+    const double qx = (double)px + 0.5, qy = (double)py + 0.5;
+    double E[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) E[i] = dadd(dadd(dmul(s.A[i], qx), dmul(s.B[i], qy)), s.C[i]);
+    const double S = dadd(dadd(E[0], E[1]), E[2]);
+    if (!(S > 0.0)) return false;
+    const double r = __ddiv_rn(1.0, S);
+    l[0] = __double2float_rn(dmul(E[0], r));
+    l[1] = __double2float_rn(dmul(E[1], r));
+    l[2] = __double2float_rn(dmul(E[2], r));
+    const float zq = xadd(xadd(xmul(l[0], s.Z[0]), xmul(l[1], s.Z[1])), xmul(l[2], s.Z[2]));
+    const float wq = xadd(xadd(xmul(l[0], s.W[0]), xmul(l[1], s.W[1])), xmul(l[2], s.W[2]));
+    if (!(wq > 0.0f)) return false;
+    depth = xdiv(zq, wq);
     return true;
 }
 
@@ -692,6 +713,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TR_TILE_CTAS) raster_tiles_kerne
     }
 }
 
+template <bool DERIV>
 __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ VisParams p) {
     const uint32_t n_visible = p.scalars[0];
     const uint32_t begin = p.y0 * p.width, end = p.y1 * p.width;
@@ -709,6 +731,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Vi
                 p.uv[layer][(size_t)i * 2] = 0.0f; p.uv[layer][(size_t)i * 2 + 1] = 0.0f;
                 p.material_id[layer][i] = 0xffffffffu;
                 if (layer == 1) p.scale1[i] = 0.0f;
+                if (DERIV) {
+                    p.duv[layer][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    p.ddepth[layer][i] = make_float2(0.f, 0.f);
+                }
                 continue;
             }
             const uint32_t w = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
@@ -736,8 +762,27 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Vi
             p.normal[layer][(size_t)i * 3 + 1] = xadd(xadd(xmul(l[0], n[0].y), xmul(l[1], n[1].y)), xmul(l[2], n[2].y));
             p.normal[layer][(size_t)i * 3 + 2] = xadd(xadd(xmul(l[0], n[0].z), xmul(l[1], n[1].z)), xmul(l[2], n[2].z));
             const float *u0 = p.uvs + (size_t)s.vid[0] * 2, *u1 = p.uvs + (size_t)s.vid[1] * 2, *u2 = p.uvs + (size_t)s.vid[2] * 2;
-            p.uv[layer][(size_t)i * 2 + 0] = xadd(xadd(xmul(l[0], __ldg(u0)), xmul(l[1], __ldg(u1))), xmul(l[2], __ldg(u2)));
-            p.uv[layer][(size_t)i * 2 + 1] = xadd(xadd(xmul(l[0], __ldg(u0 + 1)), xmul(l[1], __ldg(u1 + 1))), xmul(l[2], __ldg(u2 + 1)));
+            const float uv_u = xadd(xadd(xmul(l[0], __ldg(u0)), xmul(l[1], __ldg(u1))), xmul(l[2], __ldg(u2)));
+            const float uv_v = xadd(xadd(xmul(l[0], __ldg(u0 + 1)), xmul(l[1], __ldg(u1 + 1))), xmul(l[2], __ldg(u2 + 1)));
+            p.uv[layer][(size_t)i * 2 + 0] = uv_u;
+            p.uv[layer][(size_t)i * 2 + 1] = uv_v;
+            if (DERIV) {  // forward differences to (x+1, y) and (x, y+1) on this triangle's plane
+                float dq[6];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    float ln[3], dn;
+                    dq[k * 2] = dq[k * 2 + 1] = dq[4 + k] = 0.0f;
+                    if (eval_plane(s, (int)px + (k == 0), (int)py + (k == 1), ln, dn)) {
+                        const float un = xadd(xadd(xmul(ln[0], __ldg(u0)), xmul(ln[1], __ldg(u1))), xmul(ln[2], __ldg(u2)));
+                        const float vn = xadd(xadd(xmul(ln[0], __ldg(u0 + 1)), xmul(ln[1], __ldg(u1 + 1))), xmul(ln[2], __ldg(u2 + 1)));
+                        dq[k * 2] = xsub(un, uv_u);
+                        dq[k * 2 + 1] = xsub(vn, uv_v);
+                        dq[4 + k] = xsub(dn, d);
+                    }
+                }
+                p.duv[layer][i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+                p.ddepth[layer][i] = make_float2(dq[4], dq[5]);
+            }
             p.material_id[layer][i] = __ldg(&inst->material_id);
             if (layer == 1) p.scale1[i] = __ldg(&inst->transform.translation_and_scale.w);
         }
@@ -834,6 +879,10 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
         p.material_id[l] = c->layer[l].material_id.as<uint32_t>();
     }
     p.scale1 = c->layer[1].scale.as<float>();
+    for (int l = 0; l < 2; l++) {
+        p.duv[l] = c->materials_textured ? c->layer[l].duv.as<float4>() : nullptr;
+        p.ddepth[l] = c->materials_textured ? c->layer[l].ddepth.as<float2>() : nullptr;
+    }
 
     const size_t tile_smem = (size_t)p.ts * p.ts * 8 + sizeof(TileRecs);
     auto tile_kernel = p.ts == 64 ? raster_tiles_kernel<64> : raster_tiles_kernel<32>;
@@ -848,7 +897,8 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     bin_scan_kernel<<<1, 1024, 0, c->stream>>>(p);
     bin_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
     tile_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
-    resolve_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
+    if (c->materials_textured) resolve_kernel<true><<<c->sm_count * 8, 256, 0, c->stream>>>(p);
+    else resolve_kernel<false><<<c->sm_count * 8, 256, 0, c->stream>>>(p);
     count_launches(5);
     TR_CUDA(cudaGetLastError());
     for (int l = 0; l < 2; l++) {

@@ -113,6 +113,15 @@ int32_t ensure_layer(tr_ctx* c, int layer, bool with_position) {
     TR_TRY(g.material_id.ensure(npx * 4));
     TR_TRY(g.scale.ensure(npx * 4));
     if (with_position) TR_TRY(g.position.ensure(npx * 12));
+    if (c->materials_textured) {  // derivative planes exist only while some material binds a texture
+        const bool fresh = g.duv.bytes < npx * 16;
+        TR_TRY(g.duv.ensure(npx * 16));
+        TR_TRY(g.ddepth.ensure(npx * 8));
+        if (fresh) {
+            TR_CUDA(cudaMemsetAsync(g.duv.p, 0, npx * 16, c->stream));
+            TR_CUDA(cudaMemsetAsync(g.ddepth.p, 0, npx * 8, c->stream));
+        }
+    }
     return TR_OK;
 }
 
@@ -209,6 +218,19 @@ static int32_t fill_shade(tr_ctx* c, const tr_push_constants* pc, int layer, Sha
     s->material_id = g.material_id.as<uint32_t>();
     s->scale = g.scale.as<float>();
     s->position = g.has_position ? g.position.as<float>() : nullptr;
+    if (c->materials_textured) {
+        TR_TRY(ensure_layer(c, layer, g.has_position));
+        if (c->tex_table_dirty || !c->tex_table.p) {
+            TR_TRY(c->tex_table.ensure(sizeof(trd::TexDesc) * TR_MAX_IMAGES));
+            TR_CUDA(cudaMemcpyAsync(c->tex_table.p, c->h_tex, sizeof(trd::TexDesc) * TR_MAX_IMAGES, cudaMemcpyHostToDevice, c->stream));
+            c->tex_table_dirty = false;
+        }
+        s->uv = g.uv.as<float>();
+        s->duv = g.duv.as<float4>();
+        s->ddepth = g.ddepth.as<float2>();
+        s->textures = c->tex_table.as<trd::TexDesc>();
+        s->n_textures = c->n_textures;
+    }
     s->materials = c->materials.as<tr_material_info>();
     s->lights = c->lights.as<tr_light>();
     s->n_lights = c->n_lights;
@@ -314,9 +336,12 @@ int32_t tr_destroy(tr_ctx* c) {
                       &c->cluster_indices, &c->vis[0], &c->vis[1], &c->bin_entries, &c->bin_state, &c->tri_records, &c->dev_status, &c->hdr, &c->hdr_f32, &c->pyramid,
                       &c->srgb8, &c->mip_counter};
     for (DevBuf* b : bufs) b->release();
+    for (DevBuf& b : c->tex_data) b.release();
+    c->tex_table.release();
     for (int l = 0; l < 2; l++) {
         GLayer& g = c->layer[l];
         g.depth.release(); g.normal.release(); g.uv.release(); g.material_id.release(); g.scale.release(); g.position.release();
+        g.duv.release(); g.ddepth.release();
     }
     if (c->ev_begin) {
         for (int f = 0; f < kTimingRing; f++)
@@ -411,12 +436,16 @@ int32_t tr_set_primitives(tr_ctx* c, const tr_primitive_info* prims, uint32_t n)
 int32_t tr_set_materials(tr_ctx* c, const tr_material_info* materials, uint32_t n) {
     TR_CHECK_CTX(c);
     if (n && !materials) return fail(TR_ERR_INVALID_ARG, "tr_set_materials: null");
+    bool textured = false;
     for (uint32_t i = 0; i < n; i++) {
         const int32_t* t = &materials[i].textures.diffuse;
-        for (int k = 0; k < 9; k++)
-            if (t[k] != -1)
-                return fail(TR_ERR_UNSUPPORTED, "tr_set_materials: material %u binds texture slot %d (texture-mapped materials are out of scope)", i, k);
+        for (int k = 0; k < 9; k++) {
+            if (t[k] < -1 || t[k] >= (int32_t)TR_MAX_IMAGES)
+                return fail(TR_ERR_INVALID_ARG, "tr_set_materials: material %u texture slot %d names image %d (0..%u or -1)", i, k, t[k], TR_MAX_IMAGES - 1);
+            if (k != 4 && t[k] != -1) textured = true;  // slot 4 (occlusion) is never sampled by the shaders
+        }
     }
+    c->materials_textured = textured;
     TR_TRY(upload(c, c->materials, materials, (size_t)n * sizeof(tr_material_info)));
     c->n_materials = n;
     return TR_OK;
@@ -456,6 +485,56 @@ int32_t tr_set_ggx_lut(tr_ctx* c, const uint8_t* rgba8, uint32_t width, uint32_t
     TR_CUDA(cudaMemcpy(c->lut.p, rg.data(), rg.size(), cudaMemcpyHostToDevice));
     c->lut_w = width;
     c->lut_h = height;
+    return TR_OK;
+}
+
+// sRGB8 -> linear, evaluated in double and rounded once (R8G8B8A8_SRGB decode of the sampled image)
+static float srgb8_to_linear(uint8_t v) {
+    const double x = (double)v / 255.0;
+    return (float)(x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4));
+}
+
+int32_t tr_set_texture(tr_ctx* c, uint32_t index, const uint8_t* const* levels, uint32_t n_levels, uint32_t width, uint32_t height,
+                       int32_t srgb) {
+    TR_CHECK_CTX(c);
+    if (index >= TR_MAX_IMAGES) return fail(TR_ERR_INVALID_ARG, "tr_set_texture: image %u of at most %u", index, TR_MAX_IMAGES);
+    if (!levels || n_levels == 0 || n_levels > 16 || !width || !height) return fail(TR_ERR_INVALID_ARG, "tr_set_texture: bad arguments");
+    float table[256], unorm[256];
+    for (int v = 0; v < 256; v++) {
+        table[v] = srgb ? srgb8_to_linear((uint8_t)v) : (float)v / 255.0f;
+        unorm[v] = (float)v / 255.0f;  // alpha stays linear in the sRGB formats
+    }
+    trd::TexDesc d{};
+    d.w = width;
+    d.h = height;
+    d.levels = n_levels;
+    d.srgb = srgb ? 1u : 0u;
+    size_t total = 0;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        if (!levels[l]) return fail(TR_ERR_INVALID_ARG, "tr_set_texture: level %u is null", l);
+        d.off[l] = (uint32_t)total;
+        const uint32_t w = width >> l ? width >> l : 1u, h = height >> l ? height >> l : 1u;
+        total += (size_t)w * h;
+    }
+    std::vector<float> texels(total * 4);
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t w = width >> l ? width >> l : 1u, h = height >> l ? height >> l : 1u;
+        const uint8_t* src = levels[l];
+        float* dst = texels.data() + (size_t)d.off[l] * 4;
+        for (size_t i = 0; i < (size_t)w * h; i++) {
+            dst[i * 4 + 0] = table[src[i * 4 + 0]];
+            dst[i * 4 + 1] = table[src[i * 4 + 1]];
+            dst[i * 4 + 2] = table[src[i * 4 + 2]];
+            dst[i * 4 + 3] = unorm[src[i * 4 + 3]];
+        }
+    }
+    TR_CUDA(cudaStreamSynchronize(c->stream));  // a frame in flight may still sample the old image
+    TR_TRY(c->tex_data[index].ensure(total * 16));
+    TR_CUDA(cudaMemcpy(c->tex_data[index].p, texels.data(), total * 16, cudaMemcpyHostToDevice));
+    d.base = c->tex_data[index].as<float4>();
+    c->h_tex[index] = d;
+    if (index + 1 > c->n_textures) c->n_textures = index + 1;
+    c->tex_table_dirty = true;
     return TR_OK;
 }
 
@@ -659,6 +738,12 @@ int32_t tr_set_gbuffer(tr_ctx* c, int32_t layer, const tr_gbuffer_planes* g) {
         TR_CUDA(cudaMemcpy(L.scale.p, ones.data(), npx * 4, cudaMemcpyHostToDevice));
     }
     if (g->position) TR_CUDA(cudaMemcpyAsync(L.position.p, g->position, npx * 12, cudaMemcpyHostToDevice, c->stream));
+    if (c->materials_textured) {
+        if (g->duv) TR_CUDA(cudaMemcpyAsync(L.duv.p, g->duv, npx * 16, cudaMemcpyHostToDevice, c->stream));
+        else TR_CUDA(cudaMemsetAsync(L.duv.p, 0, npx * 16, c->stream));
+        if (g->ddepth) TR_CUDA(cudaMemcpyAsync(L.ddepth.p, g->ddepth, npx * 8, cudaMemcpyHostToDevice, c->stream));
+        else TR_CUDA(cudaMemsetAsync(L.ddepth.p, 0, npx * 8, c->stream));
+    }
     L.has_position = g->position != nullptr;
     L.valid = true;
     return TR_OK;
@@ -678,6 +763,8 @@ int32_t tr_read_gbuffer(tr_ctx* c, int32_t layer, const tr_gbuffer_planes_out* g
     if (g->material_id) TR_CUDA(cudaMemcpy(g->material_id, L.material_id.p, npx * 4, cudaMemcpyDeviceToHost));
     if (g->scale) TR_CUDA(cudaMemcpy(g->scale, L.scale.p, npx * 4, cudaMemcpyDeviceToHost));
     if (g->position && L.has_position) TR_CUDA(cudaMemcpy(g->position, L.position.p, npx * 12, cudaMemcpyDeviceToHost));
+    if (g->duv && L.duv.p) TR_CUDA(cudaMemcpy(g->duv, L.duv.p, npx * 16, cudaMemcpyDeviceToHost));
+    if (g->ddepth && L.ddepth.p) TR_CUDA(cudaMemcpy(g->ddepth, L.ddepth.p, npx * 8, cudaMemcpyDeviceToHost));
     return TR_OK;
 }
 

@@ -321,6 +321,100 @@ TRD float2 sample_lut(const LutDesc& lut, float nov, float roughness) {
     return make_float2(fmaf(bx - ax, fy, ax), fmaf(by - ay, fy, ay));
 }
 
+// ---- material textures (row N2): texture.sample(sampler, uv) with the repeat sampler, shader/src/lib.rs:251-267.
+// Everything here runs in the exact regime and mirrors oracle/shade.c line by line: the sampled values feed the shading
+// normal and the roughness, i.e. the ill-conditioned n.h chain, and the level of detail is a discrete decision.
+struct TexDesc {
+    const float4* base;     // decoded texels (sRGB -> linear / UNORM -> [0,1] done at upload), all levels
+    uint32_t w, h, levels, srgb;
+    uint32_t off[16];       // texel offset of each level
+};
+
+TRD float xlerp1(float a, float b, float t) { return xadd(a, xmul(xsub(b, a), t)); }
+
+TRD void repeat_setup(float u, uint32_t size, uint32_t& i0, uint32_t& i1, float& frac) {
+    float p = xsub(xmul(u, (float)size), 0.5f);
+    if (!(p == p) || !(fabsf(p) < 1.0e9f)) p = 0.0f;
+    const float fl = floorf(p);
+    const int i = (int)fl, n = (int)size;
+    int a = i % n, b = (i + 1) % n;
+    i0 = (uint32_t)(a < 0 ? a + n : a);
+    i1 = (uint32_t)(b < 0 ? b + n : b);
+    frac = xsub(p, fl);
+}
+
+TRD f4 sample_texture_level(const TexDesc& t, uint32_t level, float u, float v) {
+    uint32_t w = t.w >> level, h = t.h >> level;
+    if (w == 0) w = 1;
+    if (h == 0) h = 1;
+    const float4* d = t.base + t.off[level];
+    uint32_t x0, x1, y0, y1;
+    float fx, fy;
+    repeat_setup(u, w, x0, x1, fx);
+    repeat_setup(v, h, y0, y1, fy);
+    const float4 t00 = __ldg(d + (size_t)y0 * w + x0), t10 = __ldg(d + (size_t)y0 * w + x1);
+    const float4 t01 = __ldg(d + (size_t)y1 * w + x0), t11 = __ldg(d + (size_t)y1 * w + x1);
+    f4 r;
+    r.x = xlerp1(xlerp1(t00.x, t10.x, fx), xlerp1(t01.x, t11.x, fx), fy);
+    r.y = xlerp1(xlerp1(t00.y, t10.y, fx), xlerp1(t01.y, t11.y, fx), fy);
+    r.z = xlerp1(xlerp1(t00.z, t10.z, fx), xlerp1(t01.z, t11.z, fx), fy);
+    r.w = xlerp1(xlerp1(t00.w, t10.w, fx), xlerp1(t01.w, t11.w, fx), fy);
+    return r;
+}
+
+// duv = (du/dx, dv/dx, du/dy, dv/dy): differences to the right / lower neighbour (Vulkan level-of-detail operation)
+TRD f4 sample_texture(const TexDesc& t, float u, float v, float4 duv) {
+    const float ux = xmul(duv.x, (float)t.w), vx = xmul(duv.y, (float)t.h);
+    const float uy = xmul(duv.z, (float)t.w), vy = xmul(duv.w, (float)t.h);
+    const float rho2 = rmax(xadd(xmul(ux, ux), xmul(vx, vx)), xadd(xmul(uy, uy), xmul(vy, vy)));
+    float lod = xmul(0.5f, xlog2_spec(rho2));
+    const float max_lod = (float)(t.levels - 1);
+    if (!(lod > 0.0f)) lod = 0.0f;
+    if (lod > max_lod) lod = max_lod;
+    const float l0f = floorf(lod);
+    const uint32_t l0 = (uint32_t)l0f;
+    const uint32_t l1 = l0 + 1 < t.levels ? l0 + 1 : t.levels - 1;
+    const float f = xsub(lod, l0f);
+    const f4 a = sample_texture_level(t, l0, u, v), b = sample_texture_level(t, l1, u, v);
+    f4 r;
+    r.x = xlerp1(a.x, b.x, f);
+    r.y = xlerp1(a.y, b.y, f);
+    r.z = xlerp1(a.z, b.z, f);
+    r.w = xlerp1(a.w, b.w, f);
+    return r;
+}
+
+struct TextureSampler {  // shader/src/lib.rs:251-267
+    const TexDesc* textures;
+    uint32_t n_textures;
+    float u, v;
+    float4 duv;
+    TRD f4 sample(int32_t id) const {
+        f4 z;
+        z.x = z.y = z.z = z.w = 0.0f;
+        if ((uint32_t)id >= n_textures || textures[id].base == nullptr) return z;  // robust access: unbound image reads 0
+        return sample_texture(textures[id], u, v, duv);
+    }
+};
+
+// calculate_normal + compute_cotangent_frame, shader/src/lighting.rs:222-259 (oracle/shade.c calculate_normal)
+TRD f3 calculate_normal(f3 interpolated, int32_t normal_map, const TextureSampler& ts, f3 dpos_dx, f3 dpos_dy) {
+    f3 normal = xnormalize3(interpolated);
+    if (normal_map != -1) {
+        const f4 smp = ts.sample(normal_map);
+        const float k = xdiv(128.0f, 127.0f);
+        const f3 m = mk3(xsub(xdiv(xmul(smp.x, 255.0f), 127.0f), k), xsub(xdiv(xmul(smp.y, 255.0f), 127.0f), k),
+                         xsub(xdiv(xmul(smp.z, 255.0f), 127.0f), k));
+        const f3 dp2perp = xcross3(dpos_dy, normal), dp1perp = xcross3(normal, dpos_dx);
+        const f3 t = xadd3(xscale3(dp2perp, ts.duv.x), xscale3(dp1perp, ts.duv.z));
+        const f3 b = xadd3(xscale3(dp2perp, ts.duv.y), xscale3(dp1perp, ts.duv.w));
+        const float invmax = xdiv(1.0f, xsqrt(rmax(xdot3(t, t), xdot3(b, b))));
+        const f3 c0 = xscale3(t, invmax), c1 = xscale3(b, invmax);
+        normal = xnormalize3(xadd3(xadd3(xscale3(c0, m.x), xscale3(c1, m.y)), xscale3(normal, m.z)));
+    }
+    return normal;
+}
+
 struct IblVolumeRefractionParams {  // lib.rs:235-246; proj_view and log2(size_x) are per-launch constants
     MaterialParams material_params;
     f3 normal, view, position;

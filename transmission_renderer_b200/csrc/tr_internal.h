@@ -39,7 +39,7 @@ struct DevBuf {
 };
 
 struct GLayer {
-    DevBuf depth, normal, uv, material_id, scale, position;
+    DevBuf depth, normal, uv, material_id, scale, position, duv, ddepth;
     bool has_position = false;
     bool valid = false;
 };
@@ -64,6 +64,12 @@ struct tr_ctx {
     bool have_uniforms = false;
     tr::DevBuf lut;
     uint32_t lut_w = 0, lut_h = 0;
+    // material textures (row N2): decoded RGBA32F texels per image, descriptor table on the device
+    tr::DevBuf tex_data[TR_MAX_IMAGES], tex_table;
+    trd::TexDesc h_tex[TR_MAX_IMAGES] = {};
+    uint32_t n_textures = 0;          // highest bound index + 1
+    bool tex_table_dirty = false;
+    bool materials_textured = false;  // some material binds a texture: derivative planes + textured shading variant
     tr::DevBuf mesh_pos, mesh_nrm, mesh_uv, mesh_idx;
     uint32_t n_vertices = 0, n_indices = 0;
 
@@ -116,6 +122,11 @@ struct ShadeLaunch {
     const uint32_t* material_id;
     const float* scale;     // transmissive layer
     const float* position;  // optional
+    const float* uv;        // textured materials only
+    const float4* duv;
+    const float2* ddepth;
+    const trd::TexDesc* textures;  // nullptr: no material binds a texture
+    uint32_t n_textures;
     const tr_material_info* materials;
     const tr_light* lights;
     uint32_t n_lights;

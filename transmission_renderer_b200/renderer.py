@@ -37,7 +37,10 @@ class _Config(C.Structure):
 
 class _Planes(C.Structure):
     _fields_ = [("depth", C.c_void_p), ("normal", C.c_void_p), ("uv", C.c_void_p), ("material_id", C.c_void_p),
-                ("scale", C.c_void_p), ("position", C.c_void_p)]
+                ("scale", C.c_void_p), ("position", C.c_void_p), ("duv", C.c_void_p), ("ddepth", C.c_void_p)]
+
+
+_PLANES = ("depth", "normal", "uv", "material_id", "scale", "position", "duv", "ddepth")
 
 
 class Renderer:
@@ -106,6 +109,17 @@ class Renderer:
         a = _c(rgba8, np.uint8)
         _check(_lib().tr_set_ggx_lut(self._ctx, _p(a), C.c_uint32(a.shape[1]), C.c_uint32(a.shape[0])))
 
+    def set_texture(self, index, levels, srgb):
+        """levels: list of (h, w, 4) uint8 mips, level 0 first (scenes.make_mips)."""
+        lv = [_c(l, np.uint8) for l in levels]
+        ptrs = (C.c_void_p * len(lv))(*[l.ctypes.data for l in lv])
+        _check(_lib().tr_set_texture(self._ctx, C.c_uint32(index), ptrs, C.c_uint32(len(lv)), C.c_uint32(lv[0].shape[1]),
+                                     C.c_uint32(lv[0].shape[0]), C.c_int32(1 if srgb else 0)))
+
+    def set_textures(self, textures):
+        for i, t in enumerate(textures):
+            self.set_texture(i, t["levels"], t["srgb"])
+
     def set_mesh(self, positions, normals, uvs, indices):
         p, n, u, i = _c(positions, np.float32), _c(normals, np.float32), _c(uvs, np.float32), _c(indices, np.uint32)
         _check(_lib().tr_set_mesh(self._ctx, _p(p), _p(n), _p(u), C.c_uint32(len(p)), _p(i), C.c_uint32(i.size)))
@@ -162,22 +176,23 @@ class Renderer:
         keep = dict(depth=_c(gbuffer["depth"], np.float32), normal=_c(gbuffer["normal"], np.float32),
                     material_id=_c(gbuffer["material_id"], np.uint32))
         assert keep["depth"].size == npx and keep["normal"].size == npx * 3 and keep["material_id"].size == npx
-        for k, dt, mult in (("uv", np.float32, 2), ("scale", np.float32, 1), ("position", np.float32, 3)):
+        for k, dt, mult in (("uv", np.float32, 2), ("scale", np.float32, 1), ("position", np.float32, 3),
+                            ("duv", np.float32, 4), ("ddepth", np.float32, 2)):
             v = gbuffer.get(k)
             keep[k] = None if v is None else _c(v, dt)
             assert keep[k] is None or keep[k].size == npx * mult
-        planes = _Planes(*[None if keep[k] is None else keep[k].ctypes.data
-                           for k in ("depth", "normal", "uv", "material_id", "scale", "position")])
+        planes = _Planes(*[None if keep[k] is None else keep[k].ctypes.data for k in _PLANES])
         _check(_lib().tr_set_gbuffer(self._ctx, C.c_int32(layer), C.byref(planes)))
         self.sync()
 
-    def read_gbuffer(self, layer, with_position=False):
+    def read_gbuffer(self, layer, with_position=False, derivatives=False):
         h, w = self.height, self.width
         g = dict(depth=np.zeros((h, w), np.float32), normal=np.zeros((h, w, 3), np.float32),
                  uv=np.zeros((h, w, 2), np.float32), material_id=np.zeros((h, w), np.uint32),
-                 scale=np.zeros((h, w), np.float32), position=np.zeros((h, w, 3), np.float32) if with_position else None)
-        planes = _Planes(*[None if g[k] is None else g[k].ctypes.data
-                           for k in ("depth", "normal", "uv", "material_id", "scale", "position")])
+                 scale=np.zeros((h, w), np.float32), position=np.zeros((h, w, 3), np.float32) if with_position else None,
+                 duv=np.zeros((h, w, 4), np.float32) if derivatives else None,
+                 ddepth=np.zeros((h, w, 2), np.float32) if derivatives else None)
+        planes = _Planes(*[None if g[k] is None else g[k].ctypes.data for k in _PLANES])
         _check(_lib().tr_read_gbuffer(self._ctx, C.c_int32(layer), C.byref(planes)))
         return g
 

@@ -414,3 +414,118 @@ def instanced_scene(width, height, n_instances=10000, n_lights=64, seed=0x5EED00
     lights = hashed_point_lights(n_lights, seed ^ 0x11, box=((-30, 0.5, -30), (30, 12, 30)))
     return dict(camera=cam, mesh=mesh, primitives=prims, instances=inst, materials=mats, lights=lights,
                 uniforms=host.make_uniforms(width, height))
+
+
+# --------------------------------------------------------------------------- procedural material textures (row N2)
+def srgb_decode(c8):
+    x = np.asarray(c8, np.float64) / 255.0
+    return np.where(x <= 0.04045, x / 12.92, ((x + 0.055) / 1.055) ** 2.4)
+
+
+def srgb_encode(lin):
+    lin = np.clip(np.asarray(lin, np.float64), 0.0, 1.0)
+    s = np.where(lin <= 0.0031308, lin * 12.92, 1.055 * lin ** (1 / 2.4) - 0.055)
+    return np.floor(s * 255.0 + 0.5).astype(np.uint8)
+
+
+def make_mips(rgba8, srgb):
+    """Full mip chain (src/model_loading.rs:354: levels = floor(log2(min(w, h))) + 1) by 2x2 box filtering — what the
+    loader's blit chain produces for power-of-two images; colour of sRGB images is filtered in linear light."""
+    levels = [np.ascontiguousarray(rgba8, np.uint8)]
+    n = host.mip_levels_for_size(rgba8.shape[1], rgba8.shape[0])
+    for _ in range(1, n):
+        src = levels[-1]
+        h, w = max(1, src.shape[0] // 2), max(1, src.shape[1] // 2)
+        lin = src.astype(np.float64) / 255.0
+        if srgb:
+            lin[..., :3] = srgb_decode(src[..., :3])
+        lin = lin[: h * 2, : w * 2] if src.shape[0] >= 2 and src.shape[1] >= 2 else lin
+        if src.shape[0] >= 2 and src.shape[1] >= 2:
+            lin = lin.reshape(h, 2, w, 2, 4).mean(axis=(1, 3))
+        else:
+            lin = lin[:h, :w]
+        out = np.floor(np.clip(lin, 0, 1) * 255.0 + 0.5).astype(np.uint8)
+        if srgb:
+            out[..., :3] = srgb_encode(lin[..., :3])
+        levels.append(out)
+    return levels
+
+
+def _value_noise(size, cells, seed):
+    g = hash01(seed, np.arange(cells * cells, dtype=np.uint64)).reshape(cells, cells).astype(np.float64)
+    t = (np.arange(size) + 0.5) / size * cells
+    i0 = np.floor(t).astype(int) % cells
+    i1 = (i0 + 1) % cells
+    f = t - np.floor(t)
+    f = f * f * (3 - 2 * f)
+    top = g[i0][:, i0] * (1 - f)[None, :] + g[i0][:, i1] * f[None, :]
+    bot = g[i1][:, i0] * (1 - f)[None, :] + g[i1][:, i1] * f[None, :]
+    return top * (1 - f)[:, None] + bot * f[:, None]
+
+
+def procedural_textures(size=256, seed=0x5EED00A2):
+    """Tileable RGBA8 textures for every slot of `Textures` the shaders read (shared-structs lib.rs:143-153):
+    0 diffuse (sRGB, checker + noise), 1 metallic-roughness (UNORM: G roughness, B metallic), 2 normal map (UNORM),
+    3 emissive (sRGB, sparse dots), 4 transmission (R), 5 thickness (G), 6 specular (A), 7 specular colour (sRGB)."""
+    y, x = np.mgrid[0:size, 0:size]
+    n1 = _value_noise(size, 8, seed)
+    n2 = _value_noise(size, 16, seed + 1)
+    n3 = _value_noise(size, 4, seed + 2)
+    chk = (((x // (size // 8)) + (y // (size // 8))) & 1).astype(np.float64)
+
+    def pack(r, g, b, a=1.0):
+        img = np.stack(np.broadcast_arrays(r, g, b, a), -1)
+        return np.floor(np.clip(img, 0, 1) * 255.0 + 0.5).astype(np.uint8)
+
+    diffuse = pack(0.25 + 0.6 * chk * n1 + 0.1 * n2, 0.3 + 0.5 * (1 - chk) * n2, 0.35 + 0.4 * n3, 0.4 + 0.6 * n2)
+    metal_rough = pack(0.0 * n1, 0.25 + 0.7 * n1, (n3 > 0.55).astype(np.float64))
+    height = 0.6 * n1 + 0.4 * n2
+    dx = (np.roll(height, -1, axis=1) - np.roll(height, 1, axis=1)) * size / 16.0
+    dy = (np.roll(height, -1, axis=0) - np.roll(height, 1, axis=0)) * size / 16.0
+    nrm = np.stack([-dx, -dy, np.ones_like(dx)], -1)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    normal_map = pack(nrm[..., 0] * 0.5 + 0.5, nrm[..., 1] * 0.5 + 0.5, nrm[..., 2] * 0.5 + 0.5)
+    dots = ((n2 > 0.8) & (chk > 0)).astype(np.float64)
+    emissive = pack(dots, 0.6 * dots, 0.2 * dots)
+    transmission = pack(0.35 + 0.65 * n1, 0 * n1, 0 * n1)
+    thickness = pack(0 * n1, 0.3 + 0.7 * n3, 0 * n1)
+    specular = pack(0 * n1, 0 * n1, 0 * n1, 0.3 + 0.7 * n2)
+    specular_colour = pack(0.6 + 0.4 * n1, 0.6 + 0.4 * n2, 0.6 + 0.4 * n3)
+    flags = [True, False, False, True, False, False, False, True]
+    imgs = [diffuse, metal_rough, normal_map, emissive, transmission, thickness, specular, specular_colour]
+    return [dict(levels=make_mips(im, srgb), srgb=srgb) for im, srgb in zip(imgs, flags)]
+
+
+# indices into abi.material_info["textures"]: diffuse, metallic_roughness, normal_map, emissive, occlusion, transmission,
+# thickness, specular, specular_colour
+TEX_SLOTS = dict(diffuse=0, metallic_roughness=1, normal_map=2, emissive=3, occlusion=4, transmission=5, thickness=6,
+                 specular=7, specular_colour=8)
+
+
+def textured_sphere_scene(width, height, seed=0x5EED00A3, grid=5, uv_repeat=3.0):
+    """Row N2: the config-2/3 layout with texture-mapped materials — every sphere binds a different subset of the
+    texture slots (normal maps on half of them), the ground binds diffuse + normal map with uv repeat, and the
+    transmissive knot binds transmission + thickness + diffuse."""
+    s = sphere_grid_scene(width, height, seed=seed, grid=grid, transmissive_knot=True)
+    textures = procedural_textures()
+    mats = s["materials"]
+    n_s = grid * grid
+    bind = [("diffuse", 0), ("metallic_roughness", 1), ("normal_map", 2), ("emissive", 3), ("specular", 6),
+            ("specular_colour", 7)]
+    for k in range(n_s):
+        for j, (slot, tex) in enumerate(bind):
+            if (k >> j) & 1 or (slot == "diffuse" and k % 3 == 0):
+                mats["textures"][k, TEX_SLOTS[slot]] = tex
+        if mats["textures"][k, TEX_SLOTS["emissive"]] != -1:
+            mats["emissive_factor"][k, :3] = (2.0, 2.0, 2.0)
+    ground, knot = n_s, n_s + 1
+    mats["textures"][ground, TEX_SLOTS["diffuse"]] = 0
+    mats["textures"][ground, TEX_SLOTS["normal_map"]] = 2
+    mats["textures"][ground, TEX_SLOTS["metallic_roughness"]] = 1
+    mats["textures"][knot, TEX_SLOTS["diffuse"]] = 0
+    mats["textures"][knot, TEX_SLOTS["transmission"]] = 4
+    mats["textures"][knot, TEX_SLOTS["thickness"]] = 5
+    mats["textures"][knot, TEX_SLOTS["normal_map"]] = 2
+    s["mesh"]["uvs"] = (s["mesh"]["uvs"] * f32(uv_repeat)).astype(f32)   # exercises the repeat wrap
+    s["textures"] = textures
+    return s
