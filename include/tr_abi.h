@@ -124,7 +124,7 @@ typedef struct TR_ALIGN16 {
 /* shared-structs/src/lib.rs:262-268 */
 typedef struct TR_ALIGN16 {
     tr_vec4 packed_bounding_sphere; /* xyz centre, w radius, model space */
-    uint32_t draw_buffer_index;     /* 0 opaque, 1 alpha clip, 2 transmission, 3 transmission alpha clip */
+    uint32_t draw_buffer_index;     /* 0 opaque, 1 alpha clip, 2 transmission, 3 transmission alpha clip (model_loading.rs:68-78) */
     uint32_t index_count;
     uint32_t first_index;
     uint32_t first_instance;

@@ -193,7 +193,9 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
                     uint32_t n_prims, const uint32_t* visible_ids, uint32_t n_visible, const tr_push_constants* pc,
                     uint32_t y0, uint32_t y1, float* depth0, float* normal0, float* uv0, uint32_t* mat0, float* depth1,
                     float* normal1, float* uv1, uint32_t* mat1, float* scale1,
-                    float* duv0, float* ddepth0, float* duv1, float* ddepth1 /* derivative planes, any may be NULL */);
+                    float* duv0, float* ddepth0, float* duv1, float* ddepth1 /* derivative planes, any may be NULL */,
+                    const tr_material_info* materials /* NULL: no alpha clipping */, const orc_texture* textures,
+                    uint32_t n_textures);
 
 int orc_num_threads(void);
 void orc_set_num_threads(int n);

@@ -364,7 +364,8 @@ def tonemap_frame(hdr16, params, y0=0, y1=None):
     return out
 
 
-def visibility(mesh, instances, primitives, visible_ids, push_constants, y0=0, y1=None, derivatives=False):
+def visibility(mesh, instances, primitives, visible_ids, push_constants, y0=0, y1=None, derivatives=False,
+               materials=None, textures=None):
     """mesh: dict(positions (n,3), normals (n,3), uvs (n,2), indices (m,)).  Returns two G-buffer dicts; with
     derivatives=True each also carries the duv (h,w,4) / ddepth (h,w,2) forward-difference planes."""
     pos = _c(mesh["positions"], np.float32)
@@ -386,11 +387,14 @@ def visibility(mesh, instances, primitives, visible_ids, push_constants, y0=0, y
                            duv=np.zeros((h, w, 4), np.float32) if derivatives else None,
                            ddepth=np.zeros((h, w, 2), np.float32) if derivatives else None))
     a, b = layers
+    mats = None if materials is None else _c(materials, abi.material_info)
+    tex_arr, tex_keep = make_texture_array(textures or [])
     lib().orc_visibility(C.byref(m), _p(instances), C.c_uint32(len(instances)), _p(primitives),
                          C.c_uint32(len(primitives)), _p(visible_ids), C.c_uint32(len(visible_ids)), _p(pc),
                          C.c_uint32(y0), C.c_uint32(y1), _p(a["depth"]), _p(a["normal"]), _p(a["uv"]),
                          _p(a["material_id"]), _p(b["depth"]), _p(b["normal"]), _p(b["uv"]), _p(b["material_id"]),
-                         _p(b["scale"]), _p(a["duv"]), _p(a["ddepth"]), _p(b["duv"]), _p(b["ddepth"]))
+                         _p(b["scale"]), _p(a["duv"]), _p(a["ddepth"]), _p(b["duv"]), _p(b["ddepth"]),
+                         _p(mats), C.addressof(tex_arr) if textures else None, C.c_uint32(len(textures or [])))
     a["scale"] = None
     return a, b
 

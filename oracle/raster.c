@@ -192,7 +192,7 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
                     uint32_t n_prims, const uint32_t* visible_ids, uint32_t n_visible, const tr_push_constants* pc,
                     uint32_t y0, uint32_t y1, float* depth0, float* normal0, float* uv0, uint32_t* mat0, float* depth1,
                     float* normal1, float* uv1, uint32_t* mat1, float* scale1, float* duv0, float* ddepth0, float* duv1,
-                    float* ddepth1) {
+                    float* ddepth1, const tr_material_info* materials, const orc_texture* textures, uint32_t n_textures) {
     (void)n_prims;
     uint32_t width = pc->framebuffer_size.x, height = pc->framebuffer_size.y;
     m4 pv;
@@ -207,12 +207,14 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
     for (uint32_t i = 0; i < n_inst; i++) tri_prefix[i + 1] = tri_prefix[i] + prims[inst[i].primitive_id].index_count / 3;
 
     for (int layer = 0; layer < 2; layer++) {
-        uint32_t bucket = layer == 0 ? 0u : 2u;
+        /* draw buffers 0 (opaque) and 1 (alpha clip) share the opaque layer, 2 and 3 the transmissive one
+         * (src/main.rs:1900-1944, 2005-2042) */
 #pragma omp parallel for schedule(dynamic, 8)
         for (int64_t vv = 0; vv < (int64_t)n_visible; vv++) {
             uint32_t ii = visible_ids[vv];
             const tr_primitive_info* prim = &prims[inst[ii].primitive_id];
-            if (prim->draw_buffer_index != bucket) continue;
+            if (prim->draw_buffer_index > 3u || (int)(prim->draw_buffer_index >> 1) != layer) continue;
+            int alpha_clip = (prim->draw_buffer_index & 1u) != 0;
             uint32_t ntri = prim->index_count / 3;
             for (uint32_t t = 0; t < ntri; t++) {
                 tri_setup s;
@@ -222,6 +224,27 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
                     for (int px = s.x_lo; px <= s.x_hi; px++) {
                         float l[3], d;
                         if (!eval_pixel(&s, px, py, l, &d)) continue;
+                        if (alpha_clip && materials) { /* depth_pre_pass_alpha_clip, shader/src/lib.rs:269-293 */
+                            const tr_material_info* m = &materials[inst[ii].material_id];
+                            float alpha = m->diffuse_factor.w;
+                            if (m->textures.diffuse != -1) {
+                                const float *u0 = &mesh->uvs[s.vid[0] * 2], *u1 = &mesh->uvs[s.vid[1] * 2], *u2 = &mesh->uvs[s.vid[2] * 2];
+                                v2 uv = {(l[0] * u0[0] + l[1] * u1[0]) + l[2] * u2[0], (l[0] * u0[1] + l[1] * u1[1]) + l[2] * u2[1]};
+                                v2 dq[2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
+                                for (int k = 0; k < 2; k++) {
+                                    float ln[3], dn;
+                                    if (eval_plane(&s, px + (k == 0), py + (k == 1), ln, &dn)) {
+                                        dq[k].x = ((ln[0] * u0[0] + ln[1] * u1[0]) + ln[2] * u2[0]) - uv.x;
+                                        dq[k].y = ((ln[0] * u0[1] + ln[1] * u1[1]) + ln[2] * u2[1]) - uv.y;
+                                    }
+                                }
+                                float a = 0.0f;
+                                if (textures && (uint32_t)m->textures.diffuse < n_textures)
+                                    a = orc_sample_texture(&textures[m->textures.diffuse], uv, dq[0], dq[1]).w;
+                                alpha *= a;
+                            }
+                            if (alpha < m->alpha_clipping_cutoff) continue; /* kill */
+                        }
                         size_t i = (size_t)py * width + px;
                         if (layer == 1) { /* GREATER against the opaque depth already in the shared depth buffer */
                             float dop;

@@ -511,10 +511,10 @@ def test_error_behaviour():
             r.set_materials(m)
         assert e.value.status == -1                                   # TR_ERR_INVALID_ARG: image index beyond MAX_IMAGES
         p = np.zeros(1, dtype=abi.primitive_info)
-        p["draw_buffer_index"] = 1
+        p["draw_buffer_index"] = 4
         with pytest.raises(TrError) as e:
             r.set_primitives(p)
-        assert e.value.status == -2                                   # alpha-clip bucket
+        assert e.value.status == -1                                   # there are four draw buffers
         u = host.make_uniforms(64, 64)
         u["debug_clusters"] = 1
         with pytest.raises(TrError) as e:
@@ -546,7 +546,8 @@ def _textured_reference(oracle, lut, s):
     cam = s["camera"]
     pc = cam.push_constants()
     _, visible = oracle.frustum_culling(s["instances"], s["primitives"], cam.culling())
-    g0, g1 = oracle.visibility(s["mesh"], s["instances"], s["primitives"], visible, pc, derivatives=True)
+    g0, g1 = oracle.visibility(s["mesh"], s["instances"], s["primitives"], visible, pc, derivatives=True,
+                               materials=s["materials"], textures=s["textures"])
     _, cc, ci = oracle_cluster_lights(oracle, cam, s["uniforms"], s["lights"])
     sc = oracle_scene(pc, s["uniforms"], s["materials"], s["lights"], cc, ci)
     sc["textures"] = s["textures"]
@@ -589,3 +590,37 @@ def test_textured_frame(oracle, ggx_lut, size):
         r.frame(cam.frame_params(host.default_tonemap_params()))
         untextured = r.read_hdr_f32()
     assert rel_l2(untextured[..., :3], ref["t32"][..., :3]) > 0.05
+
+
+# ------------------------------------------------------------------------------ row N3: alpha-clip draw buffers
+@pytest.mark.parametrize("size", [(640, 360), (301, 170)])
+def test_alpha_clip_frame(oracle, ggx_lut, size):
+    """Draw buffers 1 and 3: fragments whose diffuse alpha (factor x texture) is below the cutoff are killed in the depth
+    pre-pass, so what lies behind shows through.  G-buffer planes bit for bit, whole frame within tolerance."""
+    w, h = size
+    s = scenes.alpha_clip_scene(w, h)
+    ref = _textured_reference(oracle, ggx_lut, s)
+    cam = s["camera"]
+    with Renderer(w, h, f32_debug=True) as r:
+        r.set_textures(s["textures"])
+        _upload_scene(r, ggx_lut, s)
+        counts, visible = oracle.frustum_culling(s["instances"], s["primitives"], cam.culling())
+        draws, dcounts = oracle.demultiplex_draws(s["primitives"], counts)
+        r.frame(cam.frame_params(host.default_tonemap_params()))
+        for b in range(4):
+            assert r.read_draws(b).tobytes() == draws[b].tobytes()
+        assert dcounts[1] > 0 and dcounts[3] > 0
+        for layer, g in ((0, ref["g0"]), (1, ref["g1"])):
+            got = r.read_gbuffer(layer, derivatives=True)
+            for k in ("depth", "normal", "uv", "material_id", "duv", "ddepth"):
+                a, b_ = got[k], np.asarray(g[k]).reshape(got[k].shape)
+                assert a.tobytes() == b_.tobytes(), f"layer {layer} plane {k}: {(a != b_).sum()} values differ"
+        got32 = r.read_hdr_f32()
+    e_t = rel_l2(got32[..., :3], ref["t32"][..., :3])
+    print(f"alpha clip {w}x{h}: final fp32 rel-L2 {e_t:.2e}")
+    assert e_t < REL_L2_TOL
+    # the alpha test really removes fragments: without materials (no clipping) the oracle's opaque layer differs
+    _, vis2 = oracle.frustum_culling(s["instances"], s["primitives"], cam.culling())
+    g0_solid, g1_solid = oracle.visibility(s["mesh"], s["instances"], s["primitives"], vis2, cam.push_constants())
+    assert (g0_solid["material_id"] != ref["g0"]["material_id"]).mean() > 0.01
+    assert (g1_solid["depth"] != ref["g1"]["depth"]).mean() > 0.002

@@ -67,6 +67,9 @@ struct VisParams {
     float* uv[2];
     uint32_t* material_id[2];
     float* scale1;
+    const tr_material_info* materials;  // alpha-clip draw buffers only (nullptr: none in the scene)
+    const TexDesc* textures;
+    uint32_t n_textures;
     float4* duv[2];               // derivative planes (nullptr unless some material binds a texture)
     float2* ddepth[2];
 };
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ 
             const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
             const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
             const uint32_t bucket = __ldg(&prim->draw_buffer_index);
-            layer = bucket == 0u ? 0u : 1u;
+            layer = bucket >> 1;  // draw buffers 0/1 (opaque, alpha clip) -> layer 0, 2/3 -> the transmissive layer
             bool on_band = true;
             if (p.band_cull) {
                 // conservative rows of the instance's bounding sphere: clip(C + d) = clip(C) + M d, |d| <= r
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ 
                     on_band = (n_hi + 1.0f) * half_h + 2.0f >= (float)p.y0 && (n_lo + 1.0f) * half_h - 2.0f <= (float)p.y1;
                 }
             }
-            if (on_band && (bucket == 0u || bucket == 2u) && setup_triangle(p, inst, prim, tri, s)) {
+            if (on_band && bucket < 4u && setup_triangle(p, inst, prim, tri, s)) {
                 keep = true;
                 layer |= depth_bucket(p, slot) << 1;  // layer | depth bucket << 1 travels with the record
                 range = (uint32_t)(s.x_lo / p.ts) | ((uint32_t)(s.x_hi / p.ts) << 8) |
@@ -471,6 +474,8 @@ struct TileRecs {
     float d0[ROUND], gx[ROUND], gy[ROUND], margin[ROUND];
     float Z[3][ROUND], W[3][ROUND];
     uint32_t gtid[ROUND];
+    uint32_t clip_mat[ROUND];  // material id of an alpha-clip triangle, 0xffffffff otherwise
+    uint2 entry[ROUND];        // (slot, tri): the alpha test re-reads the triangle's uvs
     uint32_t box[ROUND];   // x_lo | y_lo << 6 | (bw - 1) << 12
     uint32_t off[ROUND + 1];
     uint32_t queue[TILE_THREADS / 32][64];
@@ -478,8 +483,41 @@ struct TileRecs {
     float zmin_blk[64];    // hierarchical Z: min depth of each 8x8 pixel block, refreshed after every round
 };
 
-template <int TS>
-__device__ __forceinline__ void exact_sample(const TileRecs& tr_, unsigned long long* keys, uint32_t q, int tile_x0, int tile_y0) {
+// depth_pre_pass_alpha_clip (shader/src/lib.rs:269-293): diffuse alpha (factor x texture, implicit level of detail from
+// the uv differences to the right / lower neighbour on the triangle's plane) against the material's cutoff
+__device__ __noinline__ bool alpha_test_kills(const VisParams& p, const TriSetup& s, const float l[3], uint2 entry, uint32_t mat_id,
+                                               int px, int py) {
+    const tr_material_info* m = p.materials + mat_id;
+    float alpha = __ldg(&m->diffuse_factor.w);
+    const int32_t t_diffuse = __ldg(&m->textures.diffuse);
+    if (t_diffuse != -1) {
+        const tr_instance* inst = p.instances + __ldg(p.visible_ids + entry.x);
+        const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+        const uint32_t base = __ldg(&prim->first_index) + entry.y * 3;
+        const uint32_t v0 = __ldg(p.indices + base), v1 = __ldg(p.indices + base + 2), v2 = __ldg(p.indices + base + 1);  // setup order (0, 2, 1)
+        const float *u0 = p.uvs + (size_t)v0 * 2, *u1 = p.uvs + (size_t)v1 * 2, *u2 = p.uvs + (size_t)v2 * 2;
+        const float uu = xadd(xadd(xmul(l[0], __ldg(u0)), xmul(l[1], __ldg(u1))), xmul(l[2], __ldg(u2)));
+        const float vv = xadd(xadd(xmul(l[0], __ldg(u0 + 1)), xmul(l[1], __ldg(u1 + 1))), xmul(l[2], __ldg(u2 + 1)));
+        float dq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            float ln[3], dn;
+            if (eval_plane(s, px + (k == 0), py + (k == 1), ln, dn)) {
+                dq[k * 2] = xsub(xadd(xadd(xmul(ln[0], __ldg(u0)), xmul(ln[1], __ldg(u1))), xmul(ln[2], __ldg(u2))), uu);
+                dq[k * 2 + 1] = xsub(xadd(xadd(xmul(ln[0], __ldg(u0 + 1)), xmul(ln[1], __ldg(u1 + 1))), xmul(ln[2], __ldg(u2 + 1))), vv);
+            }
+        }
+        float a = 0.0f;
+        if (p.textures && (uint32_t)t_diffuse < p.n_textures && p.textures[t_diffuse].base)
+            a = sample_texture(p.textures[t_diffuse], uu, vv, make_float4(dq[0], dq[1], dq[2], dq[3])).w;
+        alpha = xmul(alpha, a);
+    }
+    return alpha < __ldg(&m->alpha_clipping_cutoff);
+}
+
+template <int TS, bool CLIP>
+__device__ __forceinline__ void exact_sample(const VisParams& p, const TileRecs& tr_, unsigned long long* keys, uint32_t q, int tile_x0,
+                                             int tile_y0) {
     const uint32_t j = q & 255u, lx = (q >> 8) & 63u, ly = (q >> 14) & 63u;
     TriSetup s;
 #pragma unroll
@@ -492,6 +530,8 @@ __device__ __forceinline__ void exact_sample(const TileRecs& tr_, unsigned long 
     }
     float l[3], d;
     if (!eval_pixel(s, tile_x0 + (int)lx, tile_y0 + (int)ly, l, d)) return;
+    const uint32_t clip_mat = CLIP ? tr_.clip_mat[j] : 0xffffffffu;
+    if (CLIP && clip_mat != 0xffffffffu && alpha_test_kills(p, s, l, tr_.entry[j], clip_mat, tile_x0 + (int)lx, tile_y0 + (int)ly)) return;
     const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xffffffffu - tr_.gtid[j]);
     unsigned long long* k = keys + ly * TS + lx;
     if (*reinterpret_cast<volatile unsigned long long*>(k) < key) atomicMax(k, key);
@@ -500,8 +540,8 @@ __device__ __forceinline__ void exact_sample(const TileRecs& tr_, unsigned long 
 #ifndef TR_TILE_CTAS
 #define TR_TILE_CTAS 4
 #endif
-template <int TS>
-__global__ void __launch_bounds__(TILE_THREADS, TR_TILE_CTAS) raster_tiles_kernel(const __grid_constant__ VisParams p) {
+template <int TS, bool CLIP>
+__global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_tiles_kernel(const __grid_constant__ VisParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     TileRecs& R = *reinterpret_cast<TileRecs*>(smem_raw + TS * TS * 8);
@@ -541,6 +581,10 @@ __global__ void __launch_bounds__(TILE_THREADS, TR_TILE_CTAS) raster_tiles_kerne
                         n_samples = (uint32_t)(bw * (y_hi - y_lo + 1));
                         R.box[tid] = (uint32_t)x_lo | ((uint32_t)y_lo << 6) | ((uint32_t)(bw - 1) << 12);
                         R.gtid[tid] = __ldg(p.work_prefix + e.x) + e.y;
+                        if (CLIP) {
+                            R.entry[tid] = e;
+                            R.clip_mat[tid] = (__ldg(&prim->draw_buffer_index) & 1u) ? __ldg(&inst->material_id) : 0xffffffffu;
+                        }
                         const double X0 = (double)tile_x0 + 0.5, Y0 = (double)tile_y0 + 0.5;
                         double cl[3], n_a = 0.0, n_b = 0.0, n_c = 0.0, det = 0.0, absdet = 0.0;
                         float max_z = 0.0f, min_w = s.W[0];
@@ -680,11 +724,11 @@ __global__ void __launch_bounds__(TILE_THREADS, TR_TILE_CTAS) raster_tiles_kerne
                     __syncwarp();
                     queue[lane] = spill;
                     qn -= 32u;
-                    exact_sample<TS>(R, keys, mine, tile_x0, tile_y0);
+                    exact_sample<TS, CLIP>(p, R, keys, mine, tile_x0, tile_y0);
                     __syncwarp();
                 }
             }
-            if (lane < qn) exact_sample<TS>(R, keys, queue[lane], tile_x0, tile_y0);
+            if (lane < qn) exact_sample<TS, CLIP>(p, R, keys, queue[lane], tile_x0, tile_y0);
             if (lane == 0 && n_exact) atomicAdd(p.stats + 2, (unsigned long long)n_exact);
             __syncthreads();  // the records are rewritten by the next round
             if (round + ROUND < count) {  // refresh the block minima: 4 threads per 8x8 block, 16 pixels each
@@ -879,13 +923,22 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
         p.material_id[l] = c->layer[l].material_id.as<uint32_t>();
     }
     p.scale1 = c->layer[1].scale.as<float>();
+    p.materials = nullptr;
+    if (c->prims_alpha_clip) {
+        if (!c->n_materials) return fail(TR_ERR_STATE, "tr_visibility: alpha-clip primitives need the materials (tr_set_materials)");
+        TR_TRY(upload_texture_table(c));
+        p.materials = c->materials.as<tr_material_info>();
+        p.textures = c->tex_table.as<TexDesc>();
+        p.n_textures = c->n_textures;
+    }
     for (int l = 0; l < 2; l++) {
         p.duv[l] = c->materials_textured ? c->layer[l].duv.as<float4>() : nullptr;
         p.ddepth[l] = c->materials_textured ? c->layer[l].ddepth.as<float2>() : nullptr;
     }
 
     const size_t tile_smem = (size_t)p.ts * p.ts * 8 + sizeof(TileRecs);
-    auto tile_kernel = p.ts == 64 ? raster_tiles_kernel<64> : raster_tiles_kernel<32>;
+    auto tile_kernel = p.materials ? (p.ts == 64 ? raster_tiles_kernel<64, true> : raster_tiles_kernel<32, true>)
+                                   : (p.ts == 64 ? raster_tiles_kernel<64, false> : raster_tiles_kernel<32, false>);
     TR_CUDA(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
     int per_sm = 0;
     TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel, TILE_THREADS, tile_smem));

@@ -125,6 +125,15 @@ int32_t ensure_layer(tr_ctx* c, int layer, bool with_position) {
     return TR_OK;
 }
 
+int32_t upload_texture_table(tr_ctx* c) {
+    if (c->tex_table_dirty || !c->tex_table.p) {
+        TR_TRY(c->tex_table.ensure(sizeof(trd::TexDesc) * TR_MAX_IMAGES));
+        TR_CUDA(cudaMemcpyAsync(c->tex_table.p, c->h_tex, sizeof(trd::TexDesc) * TR_MAX_IMAGES, cudaMemcpyHostToDevice, c->stream));
+        c->tex_table_dirty = false;
+    }
+    return TR_OK;
+}
+
 static trd::PyramidDesc pyramid_desc(const tr_ctx* c) {
     trd::PyramidDesc d{};
     d.base = c->pyramid.as<uint2>();
@@ -220,11 +229,7 @@ static int32_t fill_shade(tr_ctx* c, const tr_push_constants* pc, int layer, Sha
     s->position = g.has_position ? g.position.as<float>() : nullptr;
     if (c->materials_textured) {
         TR_TRY(ensure_layer(c, layer, g.has_position));
-        if (c->tex_table_dirty || !c->tex_table.p) {
-            TR_TRY(c->tex_table.ensure(sizeof(trd::TexDesc) * TR_MAX_IMAGES));
-            TR_CUDA(cudaMemcpyAsync(c->tex_table.p, c->h_tex, sizeof(trd::TexDesc) * TR_MAX_IMAGES, cudaMemcpyHostToDevice, c->stream));
-            c->tex_table_dirty = false;
-        }
+        TR_TRY(upload_texture_table(c));
         s->uv = g.uv.as<float>();
         s->duv = g.duv.as<float4>();
         s->ddepth = g.ddepth.as<float2>();
@@ -420,10 +425,13 @@ int32_t tr_set_instances(tr_ctx* c, const tr_instance* instances, uint32_t n) {
 int32_t tr_set_primitives(tr_ctx* c, const tr_primitive_info* prims, uint32_t n) {
     TR_CHECK_CTX(c);
     if (n && !prims) return fail(TR_ERR_INVALID_ARG, "tr_set_primitives: null");
-    for (uint32_t i = 0; i < n; i++)
-        if (prims[i].draw_buffer_index != 0 && prims[i].draw_buffer_index != 2)
-            return fail(TR_ERR_UNSUPPORTED, "tr_set_primitives: primitive %u uses alpha-clip draw buffer %u (needs textures; out of scope)",
-                        i, prims[i].draw_buffer_index);
+    bool clip = false;
+    for (uint32_t i = 0; i < n; i++) {
+        if (prims[i].draw_buffer_index > 3)
+            return fail(TR_ERR_INVALID_ARG, "tr_set_primitives: primitive %u names draw buffer %u (0..3)", i, prims[i].draw_buffer_index);
+        clip = clip || (prims[i].draw_buffer_index & 1u);
+    }
+    c->prims_alpha_clip = clip;
     TR_TRY(upload(c, c->primitives, prims, (size_t)n * sizeof(tr_primitive_info)));
     c->n_primitives = n;
     c->h_prim_tris.resize(n);

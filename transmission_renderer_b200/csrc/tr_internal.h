@@ -69,6 +69,7 @@ struct tr_ctx {
     trd::TexDesc h_tex[TR_MAX_IMAGES] = {};
     uint32_t n_textures = 0;          // highest bound index + 1
     bool tex_table_dirty = false;
+    bool prims_alpha_clip = false;    // some primitive uses draw buffer 1 or 3 (alpha clip): the rasteriser runs the alpha test
     bool materials_textured = false;  // some material binds a texture: derivative planes + textured shading variant
     tr::DevBuf mesh_pos, mesh_nrm, mesh_uv, mesh_idx;
     uint32_t n_vertices = 0, n_indices = 0;
@@ -164,5 +165,6 @@ int32_t launch_eval_ibl(uint32_t n, const trd::mat4& pv, const tr_ibl_volume_ref
 int32_t check_device_status(tr_ctx* c, const char* who);  // sticky device-side error bits -> TR_ERR_STATE
 void mat4_inverse_f64(const tr_mat4& m, tr_mat4* out);
 int32_t ensure_layer(tr_ctx* c, int layer, bool with_position);
+int32_t upload_texture_table(tr_ctx* c);  // descriptor table of the bound images -> device (if it changed)
 
 }  // namespace tr

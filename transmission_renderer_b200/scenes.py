@@ -529,3 +529,52 @@ def textured_sphere_scene(width, height, seed=0x5EED00A3, grid=5, uv_repeat=3.0)
     s["mesh"]["uvs"] = (s["mesh"]["uvs"] * f32(uv_repeat)).astype(f32)   # exercises the repeat wrap
     s["textures"] = textures
     return s
+
+
+def alpha_clip_scene(width, height, seed=0x5EED00A4):
+    """Row N3: draw buffers 1 (alpha clip) and 3 (transmission + alpha clip), src/model_loading.rs:68-78: perforated
+    spheres in front of solid ones and a perforated glass knot; the holes come from the diffuse texture's alpha
+    against `alpha_clipping_cutoff` (depth_pre_pass_alpha_clip, shader/src/lib.rs:269-293)."""
+    cam = Camera(width, height, (0.0, 3.0, 6.0), 0.0, -15.0)
+    meshes = MeshSet()
+    sphere = meshes.add(uv_sphere(32, 16), 0)
+    sphere_clip = meshes.add(uv_sphere(32, 16), 1)
+    quad = meshes.add(quad_mesh(1.0), 0)
+    knot_clip = meshes.add(torus_knot(n_u=256, n_v=32), 3)
+    knot = meshes.add(torus_knot(n_u=128, n_v=16), 2)
+    textures = procedural_textures()
+    grid = 5
+    n_s = grid * grid
+    mats = hashed_materials(n_s + 3, seed)
+    inst = []
+    for j in range(grid):
+        for i in range(grid):
+            k = j * grid + i
+            clip = (i + j) % 2 == 0
+            pos = ((i - (grid - 1) / 2) * 1.3, 0.6 + (j % 3) * 0.9, -(j * 1.2))
+            inst.append(make_instance(pos, 0.55, (0, 0, 0, 1), sphere_clip if clip else sphere, k))
+            if clip:
+                mats["textures"][k, TEX_SLOTS["diffuse"]] = 0
+                mats["alpha_clipping_cutoff"][k] = 0.55 + 0.1 * (k % 3)
+                mats["textures"][k, TEX_SLOTS["normal_map"]] = 2 if k % 4 == 0 else -1
+    ground, glass_clip, glass = n_s, n_s + 1, n_s + 2
+    mats["metallic_factor"][ground] = 0.0
+    mats["roughness_factor"][ground] = 0.7
+    mats["diffuse_factor"][ground] = (0.5, 0.5, 0.55, 1.0)
+    inst.append(make_instance((0.0, 0.0, -4.0), 30.0, (0, 0, 0, 1), quad, ground))
+    for m_id, alpha_factor in ((glass_clip, 1.0), (glass, 0.9)):
+        mats["metallic_factor"][m_id] = 0.0
+        mats["roughness_factor"][m_id] = 0.3
+        mats["diffuse_factor"][m_id] = (1.0, 1.0, 1.0, alpha_factor)
+        mats["transmission_factor"][m_id] = 1.0
+        mats["thickness_factor"][m_id] = 0.5
+        mats["attenuation_distance"][m_id] = 0.6
+        mats["attenuation_colour"][m_id] = (0.9, 0.5, 0.3, 0.0)
+    mats["textures"][glass_clip, TEX_SLOTS["diffuse"]] = 0
+    mats["alpha_clipping_cutoff"][glass_clip] = 0.6
+    inst.append(make_instance((-1.2, 2.2, 2.4), 1.3, (0.0, 0.0, 0.0, 1.0), knot_clip, glass_clip))
+    inst.append(make_instance((1.6, 2.0, 2.0), 1.1, (0.0, 0.38268343, 0.0, 0.92387953), knot, glass))
+    mesh, prims = meshes.arrays()
+    mesh["uvs"] = (mesh["uvs"] * f32(2.0)).astype(f32)
+    return dict(camera=cam, mesh=mesh, primitives=prims, instances=np.concatenate(inst), materials=mats,
+                lights=config2_lights(), uniforms=host.make_uniforms(width, height), textures=textures)
