@@ -21,6 +21,8 @@
 //     writes the same value to both targets, lib.rs:247-248).  With the
 //     peer-store path the odd lanes write that band into every peer GPU's
 //     mip 0 over NVLink, which is the all-gather fused into the shading kernel.
+#include <type_traits>
+
 #include "tr_internal.h"
 
 using namespace trd;
@@ -301,45 +303,51 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
         // every lane walks its own cluster's list (ascending light ids) through a private pointer; the warp takes the
         // smallest pending id each turn, so all lanes stay converged and each pixel still sums in ascending id order
         const uint32_t* const my_list = p.cluster_indices + my_base;
-        uint32_t my_i = 0;
-        uint32_t next = my_count ? __ldg(my_list) : 0xffffffffu;
-        while (true) {
-            const uint32_t m = __reduce_min_sync(0xffffffffu, next);
-            if (m == 0xffffffffu) break;
-            LightS l;
-            if (lights_in_smem) {
-                // explicit shared-window loads: 3 x 128 bit, address formed from a 32-bit base hoisted out of the loop
-                const uint32_t a = lights_saddr + m * (uint32_t)sizeof(LightS);
-                float4 q0, q1, q2;
-                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a));
-                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(a));
-                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a));
-                l.px = q0.x; l.py = q0.y; l.pz = q0.z; l.er = q0.w;
-                l.eg = q1.x; l.eb = q1.y; l.sx = q1.z; l.sy = q1.w;
-                l.sz = q2.x; l.cos_outer = q2.y; l.inv_eps = q2.z; l.is_spot = __float_as_uint(q2.w);
-            } else {
-                l = make_light_s(p.lights, m);
-            }
-            if (next == m) {
-                my_i++;
-                const uint32_t upcoming = my_i < my_count ? __ldg(my_list + my_i) : 0xffffffffu;  // issued early: hidden behind the BRDF
-                // light_direction_and_attenuation (glam-pbr lib.rs:12-23), fast regime; the exact chain is re-derived
-                // from `vec` inside the BRDF only where it matters (tr_device_pbr.cuh "adaptive exactness")
-                const f3 vec = sub3(mk3(l.px, l.py, l.pz), pos);
-                const float inv_d = frsqrt(dot3(vec, vec));
-                const f3 dir = scale3(vec, inv_d);
-                const float nol_raw = dot3(ps.n, dir), vol = dot3(ps.v, dir);
-                float factor = inv_d * inv_d;
-                if (!TRANS && l.is_spot) {  // lighting.rs:201-203; the transmissive loop has no spotlight factor (:58-92)
-                    float theta = -dot3(dir, mk3(l.sx, l.sy, l.sz));
-                    factor *= fmaxf((theta - l.cos_outer) * l.inv_eps, 0.0f);
+        // the loop is instantiated twice so that the (launch-uniform) choice between the shared-memory light table and
+        // the global fallback for > MAX_SMEM_LIGHTS lights costs nothing per light
+        auto light_loop = [&](auto in_smem_tag) {
+            constexpr bool IN_SMEM = decltype(in_smem_tag)::value;
+            uint32_t my_i = 0;
+            uint32_t next = my_count ? __ldg(my_list) : 0xffffffffu;
+            while (true) {
+                const uint32_t m = __reduce_min_sync(0xffffffffu, next);
+                if (m == 0xffffffffu) break;
+                LightS l;
+                if (IN_SMEM) {
+                    // explicit shared-window loads: 3 x 128 bit, address formed from a 32-bit base hoisted out of the loop
+                    const uint32_t a = lights_saddr + m * (uint32_t)sizeof(LightS);
+                    float4 q0, q1, q2;
+                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a));
+                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(a));
+                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a));
+                    l.px = q0.x; l.py = q0.y; l.pz = q0.z; l.er = q0.w;
+                    l.eg = q1.x; l.eb = q1.y; l.sx = q1.z; l.sy = q1.w;
+                    l.sz = q2.x; l.cos_outer = q2.y; l.inv_eps = q2.z; l.is_spot = __float_as_uint(q2.w);
+                } else {
+                    l = make_light_s(p.lights, m);
                 }
-                const f3 li = scale3(mk3(l.er, l.eg, l.eb), factor);
-                brdf_point_light(ps, vec, nol_raw, vol, li, sum_d, spec);
-                if (TRANS) btdf_point_light(ps, vec, nol_raw, vol, li, sum_t);
-                next = upcoming;
+                if (next == m) {
+                    my_i++;
+                    const uint32_t upcoming = my_i < my_count ? __ldg(my_list + my_i) : 0xffffffffu;  // issued early: hidden behind the BRDF
+                    // light_direction_and_attenuation (glam-pbr lib.rs:12-23), fast regime; the exact chain is re-derived
+                    // from `vec` inside the BRDF only where it matters (tr_device_pbr.cuh "adaptive exactness")
+                    const f3 vec = sub3(mk3(l.px, l.py, l.pz), pos);
+                    const float inv_d = frsqrt(dot3(vec, vec));
+                    const f3 dir = scale3(vec, inv_d);
+                    const float nol_raw = dot3(ps.n, dir), vol = dot3(ps.v, dir);
+                    float factor = inv_d * inv_d;
+                    if (!TRANS && l.is_spot) {  // lighting.rs:201-203; the transmissive loop has no spotlight factor (:58-92)
+                        float theta = -dot3(dir, mk3(l.sx, l.sy, l.sz));
+                        factor *= fmaxf((theta - l.cos_outer) * l.inv_eps, 0.0f);
+                    }
+                    brdf_point_light(ps, vec, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_d, spec);
+                    if (TRANS) btdf_point_light(ps, vec, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_t);
+                    next = upcoming;
+                }
             }
-        }
+        };
+        if (lights_in_smem) light_loop(std::true_type{});
+        else light_loop(std::false_type{});
 
         // ------------------------------------------------------------ epilogue
         float4 out = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // clear colour, main.rs:1592-1602

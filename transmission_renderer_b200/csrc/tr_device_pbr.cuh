@@ -196,21 +196,23 @@ TRD float ggx_lobe(float noh_num, float opv, float nol, float nov, float a2, flo
 
 // basic_brdf (lib.rs:377-423) for a point light at offset `vec`; `l` = vec / |vec| (fast), nol_raw = n.l, vol = v.l.
 // Accumulates sum(li * kd) (to be multiplied by c_diff / pi once, after the loop) and sum(li * F * D * V).
-TRD void brdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vol, f3 light, f3& diffuse_sum, f3& specular_acc) {
+// `colour` * `factor` is the light's intensity at the fragment (emission x attenuation x spotlight factor).
+TRD void brdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vol, f3 colour, float factor, f3& diffuse_sum,
+                          f3& specular_acc) {
     float voh;
     float nol = fmaxf(nol_raw, TR_F32_EPSILON);
     float dv = ggx_lobe(s.nov_raw + nol_raw, 1.0f + vol, nol, s.nov, s.a2, s.a2m1, s.one_m_a2, s.s_nov, s.a2_2pi,
                         [&]() { return exact_noh(s, exact_light_dir(vec)); }, voh);
     f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
-    f3 li = scale3(light, nol);
+    float w = factor * nol;                                   // light_intensity * n.l, per channel below
     float kd = 1.0f - max_element3(fresnel);
-    diffuse_sum = fma3(li, kd, diffuse_sum);
-    specular_acc = fma3(mul3(li, fresnel), dv, specular_acc);
+    diffuse_sum = fma3(colour, w * kd, diffuse_sum);
+    specular_acc = fma3(mul3(colour, fresnel), w * dv, specular_acc);
 }
 
 // transmission_btdf (lib.rs:200-233) for the same light: l' = l - 2 (n.l) n is a reflection, so it is unit,
 // n.l' = -n.l and v.l' = v.l - 2 (n.l)(n.v).  Accumulates sum(light * (1 - F) * D * V) (times base colour after the loop).
-TRD void btdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vol, f3 light, f3& transmission_sum) {
+TRD void btdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vol, f3 colour, float factor, f3& transmission_sum) {
     float voh;
     float nolm = fmaxf(-nol_raw, TR_F32_EPSILON);
     float vlm = fmaf(-2.0f * nol_raw, s.nov_raw, vol);
@@ -221,8 +223,9 @@ TRD void btdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vo
                             return exact_noh(s, lmx);
                         }, voh);
     f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
-    f3 t = mk3((1.0f - fresnel.x) * dv, (1.0f - fresnel.y) * dv, (1.0f - fresnel.z) * dv);
-    transmission_sum = add3(transmission_sum, mul3(light, t));
+    float w = factor * dv;
+    f3 t = mk3(fmaf(-fresnel.x, w, w), fmaf(-fresnel.y, w, w), fmaf(-fresnel.z, w, w));   // (1 - F) * w
+    transmission_sum = fma3v(colour, t, transmission_sum);
 }
 
 // ---- contract-shaped wrappers (used by the tr_eval_* batch evaluators) ----
