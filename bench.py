@@ -305,15 +305,34 @@ def run_b200(args, wl):
     m = scene["mesh"]
     r.set_mesh(m["positions"], m["normals"], m["uvs"], m["indices"])
     r.build_clusters(cam.write_cluster_data())
-    exchange = args.exchange if world > 1 else "none"
-    from transmission_renderer_b200 import parallel
-    parallel.init_bands(r, rank, world, group=cpu_group, exchange=args.exchange)
-    y0, y1 = host.band_rows(H, rank, world)
+    from transmission_renderer_b200 import parallel, scenes
+    groups = max(1, min(args.view_groups, world))
+    if world % groups or args.views % groups:
+        raise SystemExit("--view-groups must divide both the GPU count and --views")
+    bands = world // groups                      # ranks per view group = bands per frame
+    group_id, band_rank = rank // bands, rank % bands
+    exchange = args.exchange if bands > 1 else "none"
+    band_group = cpu_group
+    if groups > 1 and bands > 1:                 # one gloo group per view group for the unique-id / IPC-handle exchange
+        for g in range(groups):
+            sub = dist.new_group(ranks=list(range(g * bands, (g + 1) * bands)), backend="gloo")
+            if g == group_id:
+                band_group = sub
+    parallel.init_bands(r, band_rank, bands, group=band_group, exchange=args.exchange)
+    y0, y1 = host.band_rows(H, band_rank, bands)
     if args.emulate_band and world == 1:
         eb_r, eb_n = (int(x) for x in args.emulate_band.split("/"))
         y0, y1 = host.band_rows(H, eb_r, eb_n)
         r.set_band(y0, y1)
     fp = cam.frame_params(host.default_tonemap_params())
+    # views of this rank's group: orbit in yaw around the scene centre (configs[4]); view 0 is the scene's own camera
+    my_fps = [fp]
+    if args.views > 1:
+        my_fps = []
+        for v in range(group_id, args.views, groups):
+            vc = scenes.Camera(W, H, tuple(cam.position), 360.0 * v / args.views, -10.0)
+            my_fps.append(vc.frame_params(host.default_tonemap_params()))
+    frames_per_step = len(my_fps)
 
     def sync():
         stream.synchronize()
@@ -332,7 +351,8 @@ def run_b200(args, wl):
     # ------------------------------------------------------------------ resident: inputs already in HBM
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
-            r.frame(fp)
+            for f in my_fps:
+                r.frame(f)
         sync()
         r.enable_timing(True)
         launches0 = Renderer.launch_count()
@@ -342,7 +362,8 @@ def run_b200(args, wl):
         t_wall0 = time.time()
         ev0.record(stream)
         for _ in range(args.steps):
-            r.frame(fp)
+            for f in my_fps:
+                r.frame(f)
         ev1.record(stream)
         sync()
         t_wall1 = time.time()
@@ -353,7 +374,7 @@ def run_b200(args, wl):
         rstats = r.raster_stats()
         r.enable_timing(False)
     ms_per_step = ms_total / args.steps
-    value = W * H / (ms_per_step * 1e-3) / 1e6
+    value = W * H * args.views / (ms_per_step * 1e-3) / 1e6
     passes = {k[:-3]: v / max(n_timed, 1) for k, v in totals.items()}
     if sampler:
         clocks = sampler.summary(t_wall0, t_wall1)
@@ -372,13 +393,15 @@ def run_b200(args, wl):
     h2d = inst_host.nbytes + lights_host.nbytes + fp.nbytes
     d2h = (y1 - y0) * W * 4
 
-    def e2e_step(i):
+    def e2e_step(j):
         # frame i: inputs up, frame, band read-back enqueued behind it on the copy stream; then hand frame i-1's band
         # (other pinned buffer) to the consumer — like the reference presenting frame n-1 while recording frame n
-        r.set_instances(inst_host)
-        r.set_lights(lights_host)
-        r.frame(fp)
-        r.read_srgb8_async(out_host[i & 1])
+        for k, f in enumerate(my_fps):
+            i = j * frames_per_step + k
+            r.set_instances(inst_host)
+            r.set_lights(lights_host)
+            r.frame(f)
+            r.read_srgb8_async(out_host[i & 1])
 
     with torch.cuda.stream(stream):
         for i in range(max(args.warmup, 3)):
@@ -394,7 +417,7 @@ def run_b200(args, wl):
         sync()
         barrier()
         e2e_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
-    e2e_value = W * H / (e2e_ms * 1e-3) / 1e6
+    e2e_value = W * H * args.views / (e2e_ms * 1e-3) / 1e6
     if sampler:
         sampler.stop()
 
@@ -430,12 +453,14 @@ def run_b200(args, wl):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "width": W, "height": H, "instances": wl["n_instances"], "lights": wl["n_lights"],
-                       "parallelism": f"bands{world}", "exchange": exchange,
+                       "parallelism": f"bands{bands}" + (f"xviews{groups}" if groups > 1 else ""), "views": args.views,
+                       "exchange": exchange,
                        "l2": "inputs larger than L2: ~0.9 GB of G-buffer, visibility and frame planes are touched per frame vs 126 MB L2",
                        "coverage_opaque": work["coverage_opaque"], "coverage_transmissive": work["coverage_transmissive"],
                        "mean_lights_opaque": work["mean_lights_opaque"], "mean_lights_transmissive": work["mean_lights_transmissive"]},
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} | {"samples": clocks["samples"]},
-            "e2e": {"value": e2e_value, "unit": "Mpx/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": "Mpx/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d) * frames_per_step,
+                    "d2h_bytes_per_step": int(d2h) * frames_per_step},
             "gpu_launches": int(launches),
             "passes_ms": passes,
             "kernels": kernels,
@@ -446,7 +471,7 @@ def run_b200(args, wl):
             "raster_stats_per_frame": {k: v / (args.steps + max(args.warmup, 3)) for k, v in rstats.items()},
         }
         # ---- CPU baseline: the oracle port on the box's host cores, bounded sample, N=1 only; doubles as a live parity check
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and args.views == 1 and not args.no_cpu_baseline:
             opaque16 = r.read_pyramid_level(0)
             gpu_hdr = r.read_hdr()
             cpu = cpu_sample(scene, lut, opaque16)
@@ -478,6 +503,10 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
                     help="N>1: opaque bands by fused peer stores over NVLink (default) or by an NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--views", type=int, default=1,
+                    help="camera views per step (BASELINE configs[4]: 64 orbit views); a step then renders all of them")
+    ap.add_argument("--view-groups", type=int, default=1,
+                    help="N ranks = view-groups x bands: each group of N/view-groups ranks renders its share of the views band-parallel")
     ap.add_argument("--emulate-band", default=None, metavar="R/N",
                     help="profiling aid (1 GPU): render only band R of N without any exchange, e.g. 3/8")
     args = ap.parse_args()
