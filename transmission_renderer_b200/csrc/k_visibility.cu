@@ -477,6 +477,7 @@ struct TileRecs {
     uint32_t clip_mat[ROUND];  // material id of an alpha-clip triangle, 0xffffffff otherwise
     uint2 entry[ROUND];        // (slot, tri): the alpha test re-reads the triangle's uvs
     uint32_t box[ROUND];   // x_lo | y_lo << 6 | (bw - 1) << 12
+    uint32_t magic[ROUND]; // ceil(2^20 / bw): row of a box sample = (k * magic) >> 20
     uint32_t off[ROUND + 1];
     uint32_t queue[TILE_THREADS / 32][64];
     uint32_t warp_tot[TILE_THREADS / 32];
@@ -547,8 +548,20 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
     TileRecs& R = *reinterpret_cast<TileRecs*>(smem_raw + TS * TS * 8);
     __shared__ uint32_t s_item;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t* queue = R.queue[warp];
+    // 32-bit shared-window addresses of the hot structures, made opaque to the optimiser so that they live in registers:
+    // otherwise every access in the sample loop re-derives its address (S2R + LEA + ...), which costs more than the loads
+    uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(&R), keys_s = (uint32_t)__cvta_generic_to_shared(keys);
+    uint32_t queue_s = (uint32_t)__cvta_generic_to_shared(queue), lane_p = lane;
+    asm volatile("mov.u32 %0, %0;" : "+r"(recs_s));
+    asm volatile("mov.u32 %0, %0;" : "+r"(keys_s));
+    asm volatile("mov.u32 %0, %0;" : "+r"(queue_s));
+    asm volatile("mov.u32 %0, %0;" : "+r"(lane_p));
+    const uint32_t lt_mask = (1u << lane_p) - 1u;
+    auto lds_u32 = [](uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
+    auto lds_f32 = [](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
+    auto sts_u32 = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); };
+#define REC(field) (recs_s + (uint32_t)offsetof(TileRecs, field))
 
     while (true) {
         __syncthreads();
@@ -580,6 +593,7 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                         const int bw = x_hi - x_lo + 1;
                         n_samples = (uint32_t)(bw * (y_hi - y_lo + 1));
                         R.box[tid] = (uint32_t)x_lo | ((uint32_t)y_lo << 6) | ((uint32_t)(bw - 1) << 12);
+                        R.magic[tid] = (1048576u + (uint32_t)bw - 1u) / (uint32_t)bw;
                         R.gtid[tid] = __ldg(p.work_prefix + e.x) + e.y;
                         if (CLIP) {
                             R.entry[tid] = e;
@@ -670,34 +684,40 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
             uint32_t bx = 0, by = 0, bw = 1, magic = 0;
             bool first = true;
             for (uint32_t sbase = warp * 32u; sbase < total; sbase += TILE_THREADS) {
-                const uint32_t sidx = sbase + lane;
+                const uint32_t sidx = sbase + lane_p;
                 bool survive = false;
                 uint32_t q = 0;
                 if (sidx < total) {
                     if (first || sidx >= j_end) {
-                        if (first || sidx >= R.off[min(j + 9u, (uint32_t)ROUND)]) {  // far jump: binary search for the owner of sidx
+                        if (first || sidx >= lds_u32(REC(off) + 4u * min(j + 9u, (uint32_t)ROUND))) {  // far jump: binary search
                             uint32_t lo = first ? 0u : j, hi = ROUND;
                             while (hi - lo > 1) {
                                 const uint32_t mid = (lo + hi) >> 1;
-                                if (R.off[mid] <= sidx) lo = mid; else hi = mid;
+                                if (lds_u32(REC(off) + 4u * mid) <= sidx) lo = mid; else hi = mid;
                             }
                             j = lo;
                         } else {
-                            do { j++; } while (sidx >= R.off[j + 1]);
+                            do { j++; } while (sidx >= lds_u32(REC(off) + 4u * (j + 1u)));
                         }
                         first = false;
-                        j_end = R.off[j + 1];
-                        j_off = R.off[j];
-                        a0 = R.ea[0][j]; a1 = R.ea[1][j]; a2 = R.ea[2][j];
-                        b0 = R.eb[0][j]; b1 = R.eb[1][j]; b2 = R.eb[2][j];
-                        c0 = R.ec[0][j]; c1 = R.ec[1][j]; c2 = R.ec[2][j];
-                        t0 = R.ebound[0][j]; t1 = R.ebound[1][j]; t2 = R.ebound[2][j];
-                        pd0 = R.d0[j]; pgx = R.gx[j]; pgy = R.gy[j]; pmg = R.margin[j];
-                        const uint32_t box = R.box[j];
+                        const uint32_t rj = recs_s + 4u * j;  // field [i][j] sits at offsetof(field) + 4 (ROUND i + j)
+                        j_end = lds_u32(rj + (uint32_t)offsetof(TileRecs, off) + 4u);
+                        j_off = lds_u32(rj + (uint32_t)offsetof(TileRecs, off));
+                        a0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ea)); a1 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ea) + 4u * ROUND);
+                        a2 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ea) + 8u * ROUND);
+                        b0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, eb)); b1 = lds_f32(rj + (uint32_t)offsetof(TileRecs, eb) + 4u * ROUND);
+                        b2 = lds_f32(rj + (uint32_t)offsetof(TileRecs, eb) + 8u * ROUND);
+                        c0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ec)); c1 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ec) + 4u * ROUND);
+                        c2 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ec) + 8u * ROUND);
+                        t0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ebound)); t1 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ebound) + 4u * ROUND);
+                        t2 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ebound) + 8u * ROUND);
+                        pd0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, d0)); pgx = lds_f32(rj + (uint32_t)offsetof(TileRecs, gx));
+                        pgy = lds_f32(rj + (uint32_t)offsetof(TileRecs, gy)); pmg = lds_f32(rj + (uint32_t)offsetof(TileRecs, margin));
+                        const uint32_t box = lds_u32(rj + (uint32_t)offsetof(TileRecs, box));
+                        magic = lds_u32(rj + (uint32_t)offsetof(TileRecs, magic));
                         bx = box & 63u;
                         by = (box >> 6) & 63u;
                         bw = (box >> 12) + 1u;
-                        magic = (1048576u + bw - 1u) / bw;
                     }
                     const uint32_t k = sidx - j_off;
                     const uint32_t ry = (k * magic) >> 20;
@@ -707,28 +727,28 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                     const float e1 = fmaf(a1, fx, fmaf(b1, fy, c1));
                     const float e2 = fmaf(a2, fx, fmaf(b2, fy, c2));
                     if (!(e0 < -t0 || e1 < -t1 || e2 < -t2)) {
-                        const float cur = __uint_as_float(reinterpret_cast<volatile uint32_t*>(keys)[(ly * TS + lx) * 2 + 1]);
+                        const float cur = __uint_as_float(lds_u32(keys_s + (ly * TS + lx) * 8u + 4u));  // depth half of the key
                         const float dz = fmaf(pgx, fx, fmaf(pgy, fy, pd0));
                         survive = !(dz + pmg < cur);
                         q = j | (lx << 8) | (ly << 14);
                     }
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, survive);
-                if (survive) queue[qn + __popc(m & lt_mask)] = q;
+                if (survive) sts_u32(queue_s + 4u * (qn + __popc(m & lt_mask)), q);
                 qn += __popc(m);
                 n_exact += __popc(m);
                 __syncwarp();
                 if (qn >= 32u) {
-                    const uint32_t mine = queue[lane];
-                    const uint32_t spill = lane + 32u < qn ? queue[lane + 32u] : 0u;
+                    const uint32_t mine = lds_u32(queue_s + 4u * lane_p);
+                    const uint32_t spill = lane_p + 32u < qn ? lds_u32(queue_s + 4u * (lane_p + 32u)) : 0u;
                     __syncwarp();
-                    queue[lane] = spill;
+                    sts_u32(queue_s + 4u * lane_p, spill);
                     qn -= 32u;
                     exact_sample<TS, CLIP>(p, R, keys, mine, tile_x0, tile_y0);
                     __syncwarp();
                 }
             }
-            if (lane < qn) exact_sample<TS, CLIP>(p, R, keys, queue[lane], tile_x0, tile_y0);
+            if (lane_p < qn) exact_sample<TS, CLIP>(p, R, keys, lds_u32(queue_s + 4u * lane_p), tile_x0, tile_y0);
             if (lane == 0 && n_exact) atomicAdd(p.stats + 2, (unsigned long long)n_exact);
             __syncthreads();  // the records are rewritten by the next round
             if (round + ROUND < count) {  // refresh the block minima: 4 threads per 8x8 block, 16 pixels each
