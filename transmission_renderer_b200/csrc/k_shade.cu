@@ -299,8 +299,13 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             // sun, lighting.rs:37-53 / 171-177 (factor == 1.0 without ray queries)
             f3 sun_dir = mk3(p.uniforms.sun_dir.x, p.uniforms.sun_dir.y, p.uniforms.sun_dir.z);
             f3 sun_int = mk3(p.uniforms.sun_intensity.x, p.uniforms.sun_intensity.y, p.uniforms.sun_intensity.z);
-            brdf_light(ps, sun_dir, sun_int, diff, spec);
-            if (TRANS) trans = mul3(sun_int, btdf_light(ps, sun_dir));
+            // the sun's direction is given, so its exact chain starts at the halfway vector; same adaptive rule as the clustered lights
+            {
+                auto exact_sun = [&]() { return sun_dir; };
+                const float nol_raw = dot3(ps.n, sun_dir), vol = dot3(ps.v, sun_dir);
+                brdf_light_fast(ps, exact_sun, nol_raw, vol, sun_int, 1.0f, sum_d, spec);
+                if (TRANS) btdf_light_fast(ps, exact_sun, nol_raw, vol, sun_int, 1.0f, sum_t);
+            }
         }
 
         // ------------------------------------------------------------ clustered lights
@@ -338,8 +343,9 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
                     float theta = -dot3(dir, mk3(l.sx, l.sy, l.sz));
                     factor *= fmaxf((theta - l.cos_outer) * l.inv_eps, 0.0f);
                 }
-                brdf_point_light(ps, vec, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_d, spec);
-                if (TRANS) btdf_point_light(ps, vec, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_t);
+                auto exact_dir = [&]() { return exact_light_dir(vec); };
+                brdf_light_fast(ps, exact_dir, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_d, spec);
+                if (TRANS) btdf_light_fast(ps, exact_dir, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_t);
             };
             // 93-96 % of the warps of the 4K workload have all their covered pixels in ONE cluster: the list is then walked
             // with warp-uniform indices (no merge, no per-lane cursor); uncovered lanes just compute along

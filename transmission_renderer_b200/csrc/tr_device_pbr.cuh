@@ -179,30 +179,39 @@ TRD float exact_noh(const PixelShading& s, f3 l) {
 //   n.h = (n.v + n.l') / sqrt(2 opv),   v.h = opv / sqrt(2 opv)
 // and the halfway vector is never formed.  Returns d_ggx * v_smith_ggx_correlated = (a^2 / 2 pi) / (f^2 ggx)
 // (lib.rs:101-133 merged into one reciprocal; ggx > 0 always because n.v and n.l' are clamped to EPSILON).
-template <typename ExactNoh>
+// `exact()` returns (n.h, n.l') of the exact chain.  It replaces the fast n.h inside highlights (f < TR_EXACT_F) and — for
+// the transmission lobe only (GGX_GUARD), whose value has no n.l' factor and therefore grows like 1/ggx — also the fast
+// n.l' where the Smith denominator is so small that 1e-7 of n.l' matters (grazing light on a pixel whose n.v is clamped).
+#ifndef TR_EXACT_GGX
+#define TR_EXACT_GGX 0.005f
+#endif
+template <bool GGX_GUARD, typename Exact>
 TRD float ggx_lobe(float noh_num, float opv, float nol, float nov, float a2, float a2m1, float one_m_a2, float s_nov,
-                   float a2_2pi, ExactNoh exact, float& voh) {
+                   float a2_2pi, Exact exact, float& voh) {
     float inv_h = frsqrt(opv + opv);
     float noh = fmaxf(noh_num * inv_h, TR_F32_EPSILON);
     voh = fmaxf(opv * inv_h, TR_F32_EPSILON);
     float f = fmaf(noh * noh, a2m1, 1.0f);
-    if (f < TR_EXACT_F) {
-        noh = exact();
-        f = xadd(xmul(xmul(noh, noh), a2m1), 1.0f);
-    }
     float ggx = fmaf(nol, s_nov, nov * fsqrt(fmaf(nol * nol, one_m_a2, a2)));
+    if (f < TR_EXACT_F || (GGX_GUARD && ggx < TR_EXACT_GGX)) {
+        const float2 e = exact();
+        f = xadd(xmul(xmul(e.x, e.x), a2m1), 1.0f);
+        if (GGX_GUARD) ggx = fmaf(e.y, s_nov, nov * fsqrt(fmaf(e.y * e.y, one_m_a2, a2)));
+    }
     return a2_2pi * frcp(f * f * ggx);
 }
 
 // basic_brdf (lib.rs:377-423) for a point light at offset `vec`; `l` = vec / |vec| (fast), nol_raw = n.l, vol = v.l.
 // Accumulates sum(li * kd) (to be multiplied by c_diff / pi once, after the loop) and sum(li * F * D * V).
 // `colour` * `factor` is the light's intensity at the fragment (emission x attenuation x spotlight factor).
-TRD void brdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vol, f3 colour, float factor, f3& diffuse_sum,
-                          f3& specular_acc) {
+// `exact_dir()` returns the unit light direction of the exact chain (only evaluated inside highlights).
+template <typename ExactDir>
+TRD void brdf_light_fast(const PixelShading& s, ExactDir exact_dir, float nol_raw, float vol, f3 colour, float factor, f3& diffuse_sum,
+                         f3& specular_acc) {
     float voh;
     float nol = fmaxf(nol_raw, TR_F32_EPSILON);
-    float dv = ggx_lobe(s.nov_raw + nol_raw, 1.0f + vol, nol, s.nov, s.a2, s.a2m1, s.one_m_a2, s.s_nov, s.a2_2pi,
-                        [&]() { return exact_noh(s, exact_light_dir(vec)); }, voh);
+    float dv = ggx_lobe<false>(s.nov_raw + nol_raw, 1.0f + vol, nol, s.nov, s.a2, s.a2m1, s.one_m_a2, s.s_nov, s.a2_2pi,
+                               [&]() { return make_float2(exact_noh(s, exact_dir()), 0.0f); }, voh);
     f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
     float w = factor * nol;                                   // light_intensity * n.l, per channel below
     float kd = 1.0f - max_element3(fresnel);
@@ -212,16 +221,17 @@ TRD void brdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vo
 
 // transmission_btdf (lib.rs:200-233) for the same light: l' = l - 2 (n.l) n is a reflection, so it is unit,
 // n.l' = -n.l and v.l' = v.l - 2 (n.l)(n.v).  Accumulates sum(light * (1 - F) * D * V) (times base colour after the loop).
-TRD void btdf_point_light(const PixelShading& s, f3 vec, float nol_raw, float vol, f3 colour, float factor, f3& transmission_sum) {
+template <typename ExactDir>
+TRD void btdf_light_fast(const PixelShading& s, ExactDir exact_dir, float nol_raw, float vol, f3 colour, float factor, f3& transmission_sum) {
     float voh;
     float nolm = fmaxf(-nol_raw, TR_F32_EPSILON);
     float vlm = fmaf(-2.0f * nol_raw, s.nov_raw, vol);
-    float dv = ggx_lobe(s.nov_raw - nol_raw, 1.0f + vlm, nolm, s.nov, s.at2, s.at2m1, s.one_m_at2, s.s_nov_t, s.at2_2pi,
-                        [&]() {
-                            f3 lx = exact_light_dir(vec);
-                            f3 lmx = xnormalize3(xadd3(lx, xscale3(xscale3(s.n, 2.0f), -xdot3(lx, s.n))));
-                            return exact_noh(s, lmx);
-                        }, voh);
+    float dv = ggx_lobe<true>(s.nov_raw - nol_raw, 1.0f + vlm, nolm, s.nov, s.at2, s.at2m1, s.one_m_at2, s.s_nov_t, s.at2_2pi,
+                              [&]() {
+                                  f3 lx = exact_dir();
+                                  f3 lmx = xnormalize3(xadd3(lx, xscale3(xscale3(s.n, 2.0f), -xdot3(lx, s.n))));
+                                  return make_float2(exact_noh(s, lmx), fmaxf(xdot3(s.n, lmx), TR_F32_EPSILON));
+                              }, voh);
     f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
     float w = factor * dv;
     f3 t = mk3(fmaf(-fresnel.x, w, w), fmaf(-fresnel.y, w, w), fmaf(-fresnel.z, w, w));   // (1 - F) * w
