@@ -624,3 +624,53 @@ def test_alpha_clip_frame(oracle, ggx_lut, size):
     g0_solid, g1_solid = oracle.visibility(s["mesh"], s["instances"], s["primitives"], vis2, cam.push_constants())
     assert (g0_solid["material_id"] != ref["g0"]["material_id"]).mean() > 0.01
     assert (g1_solid["depth"] != ref["g1"]["depth"]).mean() > 0.002
+
+
+# ------------------------------------------------------------------------------ adversarial shading inputs
+def test_random_gbuffer_stress(oracle, ggx_lut):
+    """Random G-buffer pixels that hit the ill-conditioned corners of the lobes on purpose: normals facing away from the
+    viewer (n.v clamped to EPSILON), grazing lights, roughness down to 0.05, lights a few centimetres from the surface.
+    Both shading passes against the oracle: relative L2 of the frame and the share of pixels off by more than 1e-3."""
+    w, h = 256, 192
+    rng = np.random.default_rng(11)
+    cam = scenes.Camera(w, h, (0.0, 2.0, 5.0), 0.0, -5.0)
+    uniforms = host.make_uniforms(w, h)
+    pc = cam.push_constants()
+    # positions: unproject random depths between 1.5 m and 12 m
+    dist = rng.uniform(1.5, 12.0, (h, w))
+    zn, zf = float(host.Z_NEAR), float(host.Z_FAR)
+    a = zn / (zf - zn)
+    depth = (zf * a / dist - a).astype(f32)
+    n = _rand_unit(rng, h * w).reshape(h, w, 3).astype(f32) * rng.uniform(0.5, 2.0, (h, w, 1)).astype(f32)  # un-normalised, any facing
+    n_mat = 48
+    mats = scenes.hashed_materials(n_mat, 21, roughness_range=(0.05, 1.0))
+    tmats = scenes.hashed_materials(n_mat, 22, True, (0.05, 0.6))
+    materials = np.concatenate([mats, tmats])
+    mid = rng.integers(0, n_mat, (h, w)).astype(np.uint32)
+    g0 = dict(depth=depth, normal=n, uv=None, material_id=mid, scale=None, position=None)
+    g1 = dict(depth=depth, normal=n, uv=None, material_id=(mid + n_mat).astype(np.uint32),
+              scale=rng.uniform(0.5, 2.0, (h, w)).astype(f32), position=None)
+    lights = scenes.hashed_point_lights(40, 99, box=((-6, 0.2, -8), (6, 5, 4)), intensity=(2.0, 30.0))
+    _, counts, indices = oracle_cluster_lights(oracle, cam, uniforms, lights)
+    assert counts.max() > 8
+    sc = oracle_scene(pc, uniforms, materials, lights, counts, indices)
+    o32, o16 = oracle.shade_opaque_frame(g0, sc)
+    levels = oracle.build_pyramid(o16)
+    t32, _ = oracle.shade_transmission_frame(g1, sc, levels, ggx_lut, o32, o16)
+    with Renderer(w, h, f32_debug=True) as r:
+        gpu_setup(r, ggx_lut, uniforms, materials, lights)
+        r.set_cluster_lights(counts, indices)
+        r.set_gbuffer(0, g0)
+        r.set_gbuffer(1, g1)
+        r.shade_opaque(pc)
+        got_o = r.read_hdr_f32()
+        r.generate_mips()
+        r.shade_transmission(pc)
+        got_t = r.read_hdr_f32()
+    for name, got, ref in (("opaque", got_o, o32), ("transmission", got_t, t32)):
+        e = rel_l2(got[..., :3], ref[..., :3])
+        ok = np.isfinite(ref[..., :3]) & np.isfinite(got[..., :3])
+        rel = np.abs(got[..., :3] - ref[..., :3])[ok] / (np.abs(ref[..., :3])[ok] + 1e-3)
+        bad = float((rel > 1e-3).mean())
+        print(f"stress {name}: rel-L2 {e:.2e}, share of values off by > 1e-3: {bad:.2e}, worst {rel.max():.2e}")
+        assert e < REL_L2_TOL and bad < 1e-4
