@@ -333,7 +333,10 @@ __device__ __forceinline__ uint32_t find_slot_warp(const VisParams& p, uint32_t 
 
 // ---- pass A1: set up every triangle of the visible instances once, keep the survivors (front-facing,
 // on-screen, inside the band) as compact records and count them into the per-tile bin lists.
-__global__ void __launch_bounds__(256) bin_count_kernel(const __grid_constant__ VisParams p) {
+#ifndef TR_BIN_CTAS
+#define TR_BIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __grid_constant__ VisParams p) {
     const uint32_t n_visible = p.scalars[0], total = p.scalars[1];
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < total; base += gridDim.x * blockDim.x) {
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 }
 
 // ---- pass A3: scatter the surviving triangles into their bin lists
-__global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ VisParams p) {
+__global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_fill_kernel(const __grid_constant__ VisParams p) {
     const uint32_t n = min(*p.rec_count, p.rec_capacity);
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
@@ -1063,9 +1066,9 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     uint32_t tile_grid = (uint32_t)(c->sm_count * per_sm);
     if (tile_grid > 2 * p.n_tiles) tile_grid = 2 * p.n_tiles;
 
-    bin_count_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
+    bin_count_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     bin_scan_kernel<<<1, 1024, 0, c->stream>>>(p);
-    bin_fill_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(p);
+    bin_fill_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     tile_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
     const dim3 res_grid((c->width + RES_W - 1) / RES_W, (c->band_y1 - c->band_y0 + RES_H - 1) / RES_H, 1);
     if (c->materials_textured) resolve_kernel<true><<<res_grid, RES_W * RES_H, 0, c->stream>>>(p);
