@@ -92,7 +92,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -482,7 +482,7 @@ def run_b200(args, wl):
             a = oracle.f16_to_f32(gpu_hdr[cpu.y0:cpu.y1])[..., :3].astype(np.float64)
             b = oracle.f16_to_f32(cpu.runner.hdr16[cpu.y0:cpu.y1])[..., :3].astype(np.float64)
             ok = np.isfinite(a) & np.isfinite(b)
-            rel = float(np.linalg.norm((a - b)[ok]) / max(np.linalg.norm(b[ok]), 1e-30))
+            rel = float(np.linalg.norm(a[ok] - b[ok]) / max(np.linalg.norm(b[ok]), 1e-30))
             line["cpu_baseline"] = {"value": cpu.pixels / best / 1e6, "unit": "Mpx/s", "cores": cpu.cores, "kind": "port",
                                     "sample": cpu.describe(), "parity_rel_l2_vs_gpu_band": rel}
     r.close()
