@@ -43,7 +43,13 @@ struct VisParams {
     const float* slot_z;          // [n_visible] nearest view depth of the instance in each slot
     mat4 proj_view;
     float row_y_norm, row_w_norm;  // |rows 1 and 3 of proj_view (xyz)|: how far a unit world offset moves clip y / w
-    uint32_t band_cull;            // the band is a strict part of the frame: skip instances that cannot reach it
+    uint32_t band_cull;            // the band is a strict part of the frame: the work list holds only instances that can reach it
+    const uint32_t* list_prefix;   // [n_list + 1] exclusive triangle prefix of the work list (K1's, or the band's own)
+    const uint32_t* list_slots;    // [n_list] visible slot of each entry; nullptr = identity
+    const uint32_t* list_scalars;  // [0] n_list, [1] triangles in the list
+    uint32_t* band_prefix;         // outputs of band_filter_kernel
+    uint32_t* band_slots;
+    uint32_t* band_scalars;
     uint32_t width, height, y0, y1;
     unsigned long long* vis[2];
     // sort-middle binning state
@@ -323,12 +329,85 @@ __device__ __forceinline__ uint32_t depth_bucket(const VisParams& p, uint32_t sl
 
 // slot of the first lane's work item by binary search, the other lanes walk forward from it (they are
 // almost always in the same or the next instance)
-__device__ __forceinline__ uint32_t find_slot_warp(const VisParams& p, uint32_t base, uint32_t w, uint32_t n_visible) {
-    uint32_t slot = 0;
-    if ((threadIdx.x & 31) == 0) slot = find_slot(p, base, n_visible);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    while (slot + 1 < n_visible && __ldg(p.work_prefix + slot + 1) <= w) slot++;
-    return slot;
+__device__ __forceinline__ uint32_t find_entry_warp(const uint32_t* prefix, uint32_t base, uint32_t w, uint32_t n) {
+    uint32_t e = 0;
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t lo = 0, hi = n;  // largest entry with prefix[entry] <= base
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(prefix + mid) <= base) lo = mid; else hi = mid;
+        }
+        e = lo;
+    }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    while (e + 1 < n && __ldg(prefix + e + 1) <= w) e++;
+    return e;
+}
+
+// conservative rows of an instance's bounding sphere: clip(C + d) = clip(C) + M d, |d| <= r
+__device__ __forceinline__ bool instance_on_band(const VisParams& p, const tr_instance* inst, const tr_primitive_info* prim) {
+    const float4 sph = __ldg(reinterpret_cast<const float4*>(prim));
+    const float4 ts = __ldg(reinterpret_cast<const float4*>(inst)), rot = __ldg(reinterpret_cast<const float4*>(inst) + 1);
+    const f3 c = xadd3(mk3(ts.x, ts.y, ts.z), xscale3(xquat_mul3(rot.x, rot.y, rot.z, rot.w, mk3(sph.x, sph.y, sph.z)), ts.w));
+    const f4 cc = xmat4_mul(p.proj_view, c.x, c.y, c.z, 1.0f);
+    const float r = fabsf(sph.w * ts.w) * 1.01f + 1e-3f;
+    const float w_lo = cc.w - r * p.row_w_norm, w_hi = cc.w + r * p.row_w_norm;
+    if (!(w_lo > 0.0f)) return true;
+    const float y_lo = cc.y - r * p.row_y_norm, y_hi = cc.y + r * p.row_y_norm;
+    const float n_lo = fminf(y_lo / w_lo, y_lo / w_hi), n_hi = fmaxf(y_hi / w_lo, y_hi / w_hi);
+    const float half_h = 0.5f * (float)p.height;
+    return (n_hi + 1.0f) * half_h + 2.0f >= (float)p.y0 && (n_lo + 1.0f) * half_h - 2.0f <= (float)p.y1;
+}
+
+// ---- pass A0 (band-sharded frames only): the band's own work list — visible instances whose bounding sphere can reach
+// the band's rows, with their exclusive triangle prefix — so that pass A1 does not walk the whole scene's triangles on
+// every rank.  One CTA (the visible set is a few thousand instances).
+__global__ void __launch_bounds__(1024) band_filter_kernel(const __grid_constant__ VisParams p) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const uint32_t n_visible = p.scalars[0], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t chunk = 0; chunk < n_visible; chunk += 1024) {
+        const uint32_t slot = chunk + tid;
+        bool on = false;
+        uint32_t tris = 0;
+        if (slot < n_visible) {
+            const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
+            const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+            on = instance_on_band(p, inst, prim);
+            if (on) tris = __ldg(p.work_prefix + slot + 1) - __ldg(p.work_prefix + slot);
+        }
+        const unsigned long long v = ((unsigned long long)tris << 24) | (on ? 1ull : 0ull);
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long off = s_carry, tot = 0;
+        for (uint32_t k = 0; k < 32; k++) {
+            if (k < warp) off += s_warp[k];
+            tot += s_warp[k];
+        }
+        const unsigned long long excl = off + incl - v;
+        if (on) {
+            const uint32_t k = (uint32_t)(excl & 0xffffffull);
+            p.band_slots[k] = slot;
+            p.band_prefix[k] = (uint32_t)(excl >> 24);
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const uint32_t n = (uint32_t)(s_carry & 0xffffffull), t = (uint32_t)(s_carry >> 24);
+        p.band_scalars[0] = n;
+        p.band_scalars[1] = t;
+        p.band_prefix[n] = t;
+    }
 }
 
 // ---- pass A1: set up every triangle of the visible instances once, keep the survivors (front-facing,
@@ -337,38 +416,22 @@ __device__ __forceinline__ uint32_t find_slot_warp(const VisParams& p, uint32_t 
 #define TR_BIN_CTAS 3
 #endif
 __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __grid_constant__ VisParams p) {
-    const uint32_t n_visible = p.scalars[0], total = p.scalars[1];
+    const uint32_t n_list = p.list_scalars[0], total = p.list_scalars[1];
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < total; base += gridDim.x * blockDim.x) {
         const uint32_t w = base + lane;
         bool keep = false;
         uint32_t slot = 0, tri = 0, range = 0, layer = 0;
         TriSetup s{};
-        const uint32_t wslot = find_slot_warp(p, base, min(w, total - 1), n_visible);
+        const uint32_t entry = find_entry_warp(p.list_prefix, base, min(w, total - 1), n_list);
         if (w < total) {
-            slot = wslot;
-            tri = w - __ldg(p.work_prefix + slot);
+            slot = p.list_slots ? __ldg(p.list_slots + entry) : entry;
+            tri = w - __ldg(p.list_prefix + entry);
             const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
             const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
             const uint32_t bucket = __ldg(&prim->draw_buffer_index);
             layer = bucket >> 1;  // draw buffers 0/1 (opaque, alpha clip) -> layer 0, 2/3 -> the transmissive layer
-            bool on_band = true;
-            if (p.band_cull) {
-                // conservative rows of the instance's bounding sphere: clip(C + d) = clip(C) + M d, |d| <= r
-                const float4 sph = __ldg(reinterpret_cast<const float4*>(prim));
-                const float4 ts = __ldg(reinterpret_cast<const float4*>(inst)), rot = __ldg(reinterpret_cast<const float4*>(inst) + 1);
-                const f3 c = xadd3(mk3(ts.x, ts.y, ts.z), xscale3(xquat_mul3(rot.x, rot.y, rot.z, rot.w, mk3(sph.x, sph.y, sph.z)), ts.w));
-                const f4 cc = xmat4_mul(p.proj_view, c.x, c.y, c.z, 1.0f);
-                const float r = fabsf(sph.w * ts.w) * 1.01f + 1e-3f;
-                const float w_lo = cc.w - r * p.row_w_norm, w_hi = cc.w + r * p.row_w_norm;
-                if (w_lo > 0.0f) {
-                    const float y_lo = cc.y - r * p.row_y_norm, y_hi = cc.y + r * p.row_y_norm;
-                    const float n_lo = fminf(y_lo / w_lo, y_lo / w_hi), n_hi = fmaxf(y_hi / w_lo, y_hi / w_hi);
-                    const float half_h = 0.5f * (float)p.height;
-                    on_band = (n_hi + 1.0f) * half_h + 2.0f >= (float)p.y0 && (n_lo + 1.0f) * half_h - 2.0f <= (float)p.y1;
-                }
-            }
-            if (on_band && bucket < 4u && setup_triangle(p, inst, prim, tri, s)) {
+            if (bucket < 4u && setup_triangle(p, inst, prim, tri, s)) {
                 keep = true;
                 layer |= depth_bucket(p, slot) << 1;  // layer | depth bucket << 1 travels with the record
                 range = (uint32_t)(s.x_lo / p.ts) | ((uint32_t)(s.x_hi / p.ts) << 8) |
@@ -1066,6 +1129,21 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     uint32_t tile_grid = (uint32_t)(c->sm_count * per_sm);
     if (tile_grid > 2 * p.n_tiles) tile_grid = 2 * p.n_tiles;
 
+    p.list_prefix = p.work_prefix;
+    p.list_slots = nullptr;
+    p.list_scalars = p.scalars;
+    int extra_launch = 0;
+    if (p.band_cull && c->n_instances <= (1u << 17)) {  // the single-CTA filter is meant for visible sets of this size
+        TR_TRY(c->band_list.ensure(((size_t)c->n_instances * 2 + 1 + 4) * 4));
+        p.band_slots = c->band_list.as<uint32_t>();
+        p.band_prefix = p.band_slots + c->n_instances;
+        p.band_scalars = p.band_prefix + c->n_instances + 1;
+        band_filter_kernel<<<1, 1024, 0, c->stream>>>(p);
+        p.list_prefix = p.band_prefix;
+        p.list_slots = p.band_slots;
+        p.list_scalars = p.band_scalars;
+        extra_launch = 1;
+    }
     bin_count_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     bin_scan_kernel<<<1, 1024, 0, c->stream>>>(p);
     bin_fill_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
@@ -1073,7 +1151,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     const dim3 res_grid((c->width + RES_W - 1) / RES_W, (c->band_y1 - c->band_y0 + RES_H - 1) / RES_H, 1);
     if (c->materials_textured) resolve_kernel<true><<<res_grid, RES_W * RES_H, 0, c->stream>>>(p);
     else resolve_kernel<false><<<res_grid, RES_W * RES_H, 0, c->stream>>>(p);
-    count_launches(5);
+    count_launches(5 + extra_launch);
     TR_CUDA(cudaGetLastError());
     for (int l = 0; l < 2; l++) {
         c->layer[l].valid = true;

@@ -90,7 +90,7 @@ struct tr_ctx {
 
     // frame targets
     tr::GLayer layer[2];
-    tr::DevBuf vis[2], bin_entries, bin_state, tri_records, dev_status;  // sort-middle rasteriser state (k_visibility.cu)
+    tr::DevBuf vis[2], bin_entries, bin_state, tri_records, dev_status, band_list;  // sort-middle rasteriser state (k_visibility.cu)
     tr::DevBuf hdr, hdr_f32, pyramid, srgb8, mip_counter;
     uint32_t levels = 0, level_w[tr::kMaxLevels] = {}, level_h[tr::kMaxLevels] = {}, level_off[tr::kMaxLevels] = {};
     bool opaque_valid = false, mips_valid = false, hdr_valid = false, srgb_valid = false;
