@@ -680,3 +680,40 @@ def test_random_gbuffer_stress(oracle, ggx_lut):
         bad = float((rel > 1e-3).mean())
         print(f"stress {name}: rel-L2 {e:.2e}, share of values off by > 1e-3: {bad:.2e}, worst {rel.max():.2e}")
         assert e < REL_L2_TOL and bad < 1e-4
+
+
+def test_more_lights_than_the_shared_table(oracle, ggx_lut):
+    """1 200 lights: more than the 1 024-entry shared-memory light table of the shading kernels, so the launch takes the
+    global-memory light path (the huge far clusters overflow their 128-entry lists, which both sides clamp alike)."""
+    w, h = 320, 180
+    cam = scenes.Camera(w, h, (0.0, 3.0, 6.0), 0.0, -15.0)
+    uniforms = host.make_uniforms(w, h)
+    lights = scenes.hashed_point_lights(1200, 4242, box=((-40, 0.3, -60), (40, 8, 10)), intensity=(0.2, 1.5))
+    rng = np.random.default_rng(2)
+    centres = np.stack([rng.uniform(-4, 4, 12), rng.uniform(0.5, 3.0, 12), rng.uniform(-6, 1, 12)], -1)
+    g0 = scenes.raycast_spheres(cam, centres, rng.uniform(0.4, 0.9, 12), np.arange(12))
+    g1 = scenes.raycast_spheres(cam, centres[:4] + np.array([0.3, 0.2, 2.0]), rng.uniform(0.3, 0.6, 4), 12 + np.arange(4), scale_plane=True)
+    keep = g1["depth"] > g0["depth"]
+    g1["depth"] = np.where(keep, g1["depth"], 0).astype(f32)
+    g1["material_id"] = np.where(keep, g1["material_id"], 0xFFFFFFFF).astype(np.uint32)
+    mats = np.concatenate([scenes.hashed_materials(12, 5), scenes.hashed_materials(4, 6, True, (0.2, 0.5))])
+    pc = cam.push_constants()
+    _, counts, indices = oracle_cluster_lights(oracle, cam, uniforms, lights)
+    assert counts.max() > 8
+    sc = oracle_scene(pc, uniforms, mats, lights, counts, indices)
+    o32, o16 = oracle.shade_opaque_frame(g0, sc)
+    levels = oracle.build_pyramid(o16)
+    t32, _ = oracle.shade_transmission_frame(g1, sc, levels, ggx_lut, o32, o16)
+    with Renderer(w, h, f32_debug=True) as r:
+        gpu_setup(r, ggx_lut, uniforms, mats, lights)
+        r.build_clusters(cam.write_cluster_data())
+        r.assign_lights(cam.assign_lights())
+        gc, gi = r.read_cluster_lights(len(counts))
+        np.testing.assert_array_equal(gc, counts)
+        r.set_gbuffer(0, g0)
+        r.set_gbuffer(1, g1)
+        r.shade_opaque(pc)
+        r.generate_mips()
+        r.shade_transmission(pc)
+        got = r.read_hdr_f32()
+    assert rel_l2(got[..., :3], t32[..., :3]) < REL_L2_TOL
