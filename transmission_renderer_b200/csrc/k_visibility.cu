@@ -59,6 +59,7 @@ struct VisParams {
     uint32_t* bin_count;          // [n_lists], list = (layer * n_tiles + tile) * DEPTH_BUCKETS + bucket
     uint32_t* bin_start;          // [n_lists + 1]
     uint32_t* bin_cursor;         // [n_lists]
+    uint32_t* scan_totals;        // [SCAN_CTAS] slice totals of the scan, zeroed per frame
     uint2* bin_entries;           // (slot, tri), grouped by list
     uint32_t bin_capacity;
     uint4* records;               // surviving triangles: (slot, tri, tile range, layer)
@@ -278,9 +279,12 @@ __device__ __forceinline__ uint32_t find_slot(const VisParams& p, uint32_t w, ui
 // 4 tiles.  Called by all 32 lanes of a warp together: boxes of up to 16 tiles are walked by their own lane,
 // larger ones (a triangle crossing the camera plane spans the whole band) by the whole warp, one tile per
 // lane, so that no single thread ever walks thousands of tiles.
-template <typename F>
+// f(list, payload) handles one (triangle, list) pair; g(list, payload, peers) handles the lanes of a warp whose
+// single-tile triangles all go to the same list (the common case: neighbouring triangles of one mesh), so that they
+// can share one atomic.
+template <typename F, typename G>
 __device__ __forceinline__ void bin_triangle(const VisParams& p, bool keep, const TriSetup& s, uint32_t range, uint32_t layer,
-                                             uint2 payload, F f) {
+                                             uint2 payload, F f, G g) {
     const uint32_t lane = threadIdx.x & 31;
     const int tx0 = range & 0xff, tx1 = (range >> 8) & 0xff, ty0 = (range >> 16) & 0xff, ty1 = range >> 24;
     const int ntx = tx1 - tx0 + 1, n_tiles = ntx * (ty1 - ty0 + 1);
@@ -292,7 +296,13 @@ __device__ __forceinline__ void bin_triangle(const VisParams& p, bool keep, cons
         }
         f((((lay & 1u) * p.n_tiles + (uint32_t)ty * p.tiles_x + (uint32_t)tx) * DEPTH_BUCKETS) + (lay >> 1), pl);
     };
-    if (keep && n_tiles <= 16)
+    const bool single = keep && n_tiles == 1;
+    const uint32_t single_mask = __ballot_sync(0xffffffffu, single);
+    if (single) {
+        const uint32_t list = (((layer & 1u) * p.n_tiles + (uint32_t)ty0 * p.tiles_x + (uint32_t)tx0) * DEPTH_BUCKETS) + (layer >> 1);
+        g(list, payload, __match_any_sync(single_mask, list));
+    }
+    if (keep && n_tiles > 1 && n_tiles <= 16)
         for (int ty = ty0; ty <= ty1; ty++)
             for (int tx = tx0; tx <= tx1; tx++) visit(s, tx, ty, n_tiles > 4, layer, payload);
     uint32_t big = __ballot_sync(0xffffffffu, keep && n_tiles > 16);
@@ -438,7 +448,10 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __gri
                         ((uint32_t)(s.y_lo / p.ts - (int)p.tile_row0) << 16) | ((uint32_t)(s.y_hi / p.ts - (int)p.tile_row0) << 24);
             }
         }
-        bin_triangle(p, keep, s, range, layer, make_uint2(0, 0), [&](uint32_t list, uint2) { atomicAdd(p.bin_count + list, 1u); });
+        bin_triangle(p, keep, s, range, layer, make_uint2(0, 0), [&](uint32_t list, uint2) { atomicAdd(p.bin_count + list, 1u); },
+                     [&](uint32_t list, uint2, uint32_t peers) {
+                         if (lane == (uint32_t)__ffs(peers) - 1u) atomicAdd(p.bin_count + list, (uint32_t)__popc(peers));
+                     });
         const uint32_t mask = __ballot_sync(0xffffffffu, keep);
         if (mask) {
             uint32_t first = 0;
@@ -453,35 +466,64 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __gri
     }
 }
 
-// ---- pass A2: exclusive scan of the bin counts (one CTA; 4 lists per thread per step, 128-bit accesses)
+// ---- pass A2: exclusive scan of the bin counts.  SCAN_CTAS co-resident CTAs (far fewer than SMs) each scan a contiguous
+// slice, publish its total, and add the totals of the slices before it (which they wait for; all CTAs are running, so
+// the wait cannot deadlock).
+constexpr int SCAN_CTAS = 32;
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ VisParams p) {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    const uint32_t n = p.n_lists, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // n is a multiple of 4
-    if (tid == 0) s_carry = 0;
+    __shared__ uint32_t s_carry, s_prev;
+    const uint32_t n = p.n_lists, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // n is a multiple of 32
+    const uint32_t per = ((n / 4 + SCAN_CTAS - 1) / SCAN_CTAS) * 4;                      // lists per CTA, a multiple of 4
+    const uint32_t begin = min(blockIdx.x * per, n), end = min(begin + per, n);
+    // pass 1: this slice's total
+    uint32_t sum = 0;
+    for (uint32_t i = begin + tid * 4; i < end; i += 4096) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p.bin_count + i);
+        sum += q.x + q.y + q.z + q.w;
+    }
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if (lane == 0) s_warp[warp] = sum;
     __syncthreads();
-    for (uint32_t chunk = 0; chunk < n; chunk += 4096) {
+    if (tid == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 32; k++) t += s_warp[k];
+        // flag in the top bit: totals are < 2^31 (bin_capacity is 2^24 and larger sums only set the overflow bit)
+        atomicExch(p.scan_totals + blockIdx.x, 0x80000000u | min(t, 0x7fffffffu));
+        uint32_t prev = 0;
+        for (uint32_t b = 0; b < blockIdx.x; b++) {
+            uint32_t v;
+            do { v = *reinterpret_cast<volatile uint32_t*>(p.scan_totals + b); } while (!(v & 0x80000000u));
+            prev += v & 0x7fffffffu;
+        }
+        s_prev = prev;
+        s_carry = 0;
+    }
+    __syncthreads();
+    // pass 2: exclusive scan of the slice on top of s_prev
+    for (uint32_t chunk = begin; chunk < end; chunk += 4096) {
         const uint32_t i0 = chunk + tid * 4;
-        const uint4 q = i0 < n ? *reinterpret_cast<const uint4*>(p.bin_count + i0) : make_uint4(0, 0, 0, 0);
-        const uint32_t sum = q.x + q.y + q.z + q.w;
-        uint32_t incl = sum;
+        const uint4 q = i0 < end ? *reinterpret_cast<const uint4*>(p.bin_count + i0) : make_uint4(0, 0, 0, 0);
+        const uint32_t s4 = q.x + q.y + q.z + q.w;
+        uint32_t incl = s4;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= (uint32_t)d) incl += o;
         }
+        __syncthreads();
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        uint32_t off = s_carry, tot = 0;
+        uint32_t off = s_prev + s_carry, tot = 0;
 #pragma unroll
         for (uint32_t k = 0; k < 32; k++) {
             const uint32_t t = s_warp[k];
             if (k < warp) off += t;
             tot += t;
         }
-        if (i0 < n) {
+        if (i0 < end) {
             uint4 o;
-            o.x = off + incl - sum;
+            o.x = off + incl - s4;
             o.y = o.x + q.x;
             o.z = o.y + q.y;
             o.w = o.z + q.z;
@@ -492,9 +534,10 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
         if (tid == 0) s_carry += tot;
         __syncthreads();
     }
-    if (tid == 0) {
-        p.bin_start[n] = s_carry;
-        if (s_carry > p.bin_capacity) atomicOr(p.status, 2u);
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        const uint32_t total = s_prev + s_carry;
+        p.bin_start[n] = total;
+        if (total > p.bin_capacity) atomicOr(p.status, 2u);
     }
 }
 
@@ -518,6 +561,13 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_fill_kernel(const __grid
         }
         bin_triangle(p, keep, s, rec.z, rec.w, make_uint2(rec.x, rec.y), [&](uint32_t list, uint2 slot_tri) {
             const uint32_t pos = atomicAdd(p.bin_cursor + list, 1u);
+            if (pos < p.bin_capacity) p.bin_entries[pos] = slot_tri;
+        }, [&](uint32_t list, uint2 slot_tri, uint32_t peers) {
+            const int leader = __ffs(peers) - 1;
+            uint32_t first = 0;
+            if ((int)lane == leader) first = atomicAdd(p.bin_cursor + list, (uint32_t)__popc(peers));
+            first = __shfl_sync(peers, first, leader);
+            const uint32_t pos = first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
             if (pos < p.bin_capacity) p.bin_entries[pos] = slot_tri;
         });
     }
@@ -1059,7 +1109,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     // state block: [bin_count L][rec_count, ticket, pad, pad][bin_start L+1][bin_cursor L]; the first two parts are zeroed per frame
     const size_t n_lists = (size_t)2 * p.n_tiles * DEPTH_BUCKETS;
     p.n_lists = (uint32_t)n_lists;
-    const size_t zero_bytes = (n_lists + 4) * 4;
+    const size_t zero_bytes = (n_lists + 4 + 32) * 4;  // bin_count, rec_count/ticket, scan totals
     TR_TRY(c->bin_state.ensure(zero_bytes + (2 * n_lists + 4) * 4));
     if (!c->dev_status.p) {
         TR_TRY(c->dev_status.ensure(64));
@@ -1070,7 +1120,8 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.bin_count = st;
     p.rec_count = st + n_lists;
     p.tile_ticket = st + n_lists + 1;
-    p.bin_start = st + n_lists + 4;
+    p.scan_totals = st + n_lists + 4;
+    p.bin_start = st + n_lists + 4 + 32;
     p.bin_cursor = p.bin_start + n_lists + 4;  // keeps 16-byte alignment (n_lists is a multiple of 16)
     p.bin_entries = c->bin_entries.as<uint2>();
     p.records = c->tri_records.as<uint4>();
@@ -1145,7 +1196,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
         extra_launch = 1;
     }
     bin_count_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
-    bin_scan_kernel<<<1, 1024, 0, c->stream>>>(p);
+    bin_scan_kernel<<<SCAN_CTAS, 1024, 0, c->stream>>>(p);
     bin_fill_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     tile_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
     const dim3 res_grid((c->width + RES_W - 1) / RES_W, (c->band_y1 - c->band_y0 + RES_H - 1) / RES_H, 1);
