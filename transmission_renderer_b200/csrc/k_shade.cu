@@ -382,12 +382,23 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
         // ------------------------------------------------------------ epilogue
         float4 out = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // clear colour, main.rs:1592-1602
         if (covered) {
-            diff = add3(diff, mul3(sum_d, ps.c_diff_pi));   // diffuse_brdf's c_diff / pi, once for all clustered lights
-            if (TRANS) trans = add3(trans, mul3(sum_t, ps.base));
+            f3 base = ps.base, c_diff_pi = ps.c_diff_pi;
+            if (!TEX) {
+                // untextured materials: re-read the few factors that are only needed after the light loop instead of
+                // keeping them in registers across it (nine registers the loop can use)
+                const float4 dfac = __ldg(reinterpret_cast<const float4*>(&mat->diffuse_factor));
+                const float4 emis = __ldg(reinterpret_cast<const float4*>(&mat->emissive_factor));
+                const float metallic = __ldg(&mat->metallic_factor);
+                base = mk3(dfac.x, dfac.y, dfac.z);
+                c_diff_pi = scale3(lerp3(base, splat3(0.0f), metallic), TR_FRAC_1_PI);
+                emission = mk3(emis.x, emis.y, emis.z);
+            }
+            diff = add3(diff, mul3(sum_d, c_diff_pi));   // diffuse_brdf's c_diff / pi, once for all clustered lights
+            if (TRANS) trans = add3(trans, mul3(sum_t, base));
             if (TRANS) {
                 const float4 acol = __ldg(reinterpret_cast<const float4*>(&mat->attenuation_colour));
                 IblVolumeRefractionParams ip;
-                ip.material_params.diffuse_colour = ps.base;
+                ip.material_params.diffuse_colour = base;
                 ip.material_params.metallic = 0.0f;
                 ip.material_params.perceptual_roughness = roughness_px;
                 ip.material_params.index_of_refraction = __ldg(&mat->index_of_refraction);
