@@ -93,7 +93,8 @@ static int32_t alloc_frame(tr_ctx* c) {
         w = w / 2 > 1 ? w / 2 : 1;
         h = h / 2 > 1 ? h / 2 : 1;
     }
-    TR_TRY(c->pyramid.ensure((size_t)off * 8));
+    c->barrier_flags_offset = (size_t)off * 8;  // 256 bytes of cross-GPU barrier words live behind the last mip level
+    TR_TRY(c->pyramid.ensure((size_t)off * 8 + 256));
     TR_TRY(c->hdr.ensure(npx * 8));
     TR_TRY(c->srgb8.ensure(npx * 4));
     if (c->flags & TR_FLAG_HDR_F32_DEBUG) TR_TRY(c->hdr_f32.ensure(npx * 16));
@@ -373,6 +374,7 @@ int32_t tr_resize(tr_ctx* c, uint32_t width, uint32_t height) {
     TR_CHECK_CTX(c);
     if (width == 0 || height == 0) return fail(TR_ERR_INVALID_ARG, "tr_resize: empty framebuffer");
     TR_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->peers_attached) return fail(TR_ERR_STATE, "tr_resize: detach the peer mappings first (tr_comm_destroy); they name the old frame buffers");
     c->width = width;
     c->height = height;
     c->band_y0 = 0;

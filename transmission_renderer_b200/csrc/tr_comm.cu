@@ -5,8 +5,9 @@
 // because the refraction fetch of glam-pbr lib.rs:330-337 reads arbitrary texels.  Two ways:
 //   (a) NCCL all-gather, in place in the full-frame buffer (baseline);
 //   (b) peer stores: K4's odd lanes write the band straight into every peer's mip 0 over
-//       NVLink (CUDA IPC mappings), so the exchange overlaps shading tile by tile and the only
-//       collective left is a 4-byte all-reduce used as a cross-GPU barrier.
+//       NVLink (CUDA IPC mappings), so the exchange overlaps shading tile by tile; what is left is a
+//       cross-GPU barrier, done with release/acquire flag words in the same peer memory (no NCCL call
+//       in the frame loop).
 // NCCL is resolved at run time (dlsym on the already-loaded libnccl.so.2 of the host process,
 // e.g. torch's, else dlopen) so single-GPU users need no NCCL at all.
 #include <dlfcn.h>
@@ -74,9 +75,37 @@ static void band_of(const tr_ctx* c, int r, uint32_t* y0, uint32_t* y1) {
     *y1 = (uint32_t)(((uint64_t)(r + 1) * c->height) / c->n_ranks);
 }
 
-// cross-GPU barrier on the context's stream: a 4-byte all-reduce
+namespace {
+struct PeerFlags {
+    uint32_t* p[kMaxPeers];
+};
+// Barrier over NVLink peer memory: thread t tells rank t "rank `rank` has reached epoch e" with a release store into
+// that rank's words, then waits (acquire loads on its own words) until rank t has said the same.  The opaque pass's peer
+// stores of this rank completed with its kernel, i.e. before this kernel started, so a rank that leaves the barrier
+// sees every band in its own mip 0.
+__global__ void peer_barrier_kernel(PeerFlags f, int rank, int n_ranks, uint32_t epoch) {
+    const int t = threadIdx.x;
+    if (t >= n_ranks) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[t] + rank), "r"(epoch) : "memory");
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.p[rank] + t) : "memory");
+    } while ((int32_t)(v - epoch) < 0);
+}
+}  // namespace
+
+// cross-GPU barrier on the context's stream: flags in peer memory when the peer mappings exist, else a 4-byte all-reduce
 int32_t comm_barrier(tr_ctx* c) {
     if (c->n_ranks <= 1) return TR_OK;
+    if (c->peers_attached) {
+        PeerFlags f{};
+        for (int r = 0; r < c->n_ranks; r++) f.p[r] = c->peer_flags[r];
+        peer_barrier_kernel<<<1, 32, 0, c->stream>>>(f, c->rank, c->n_ranks, ++c->barrier_epoch);
+        count_launches(1);
+        TR_CUDA(cudaGetLastError());
+        return TR_OK;
+    }
     if (!c->nccl_comm) return fail(TR_ERR_STATE, "communicator not initialised (tr_comm_init)");
     uint32_t* scratch = c->mip_counter.as<uint32_t>() + 2;
     int rc = g_nccl.all_reduce(scratch, scratch, 1, kNcclInt32, kNcclSum, c->nccl_comm, c->stream);
@@ -173,6 +202,10 @@ int32_t tr_peer_export(tr_ctx* c, uint8_t handle[TR_IPC_HANDLE_BYTES]) {
     if (!c || !handle) return fail(TR_ERR_INVALID_ARG, "tr_peer_export: null");
     TR_CUDA(cudaSetDevice(c->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == TR_IPC_HANDLE_BYTES, "IPC handle size");
+    // the barrier words behind the pyramid start at epoch 0, before any peer can map them
+    TR_CUDA(cudaStreamSynchronize(c->stream));
+    TR_CUDA(cudaMemset(c->pyramid.as<unsigned char>() + c->barrier_flags_offset, 0, 256));
+    c->barrier_epoch = 0;
     cudaIpcMemHandle_t h;
     TR_CUDA(cudaIpcGetMemHandle(&h, c->pyramid.p));
     memcpy(handle, &h, sizeof(h));
@@ -186,6 +219,7 @@ int32_t tr_peer_attach(tr_ctx* c, int32_t rank, int32_t n_ranks, const uint8_t* 
     for (int r = 0; r < n_ranks; r++) {
         if (r == rank) {
             c->peer_mip0[r] = c->pyramid.as<uint2>() + c->level_off[0];
+            c->peer_flags[r] = reinterpret_cast<uint32_t*>(c->pyramid.as<unsigned char>() + c->barrier_flags_offset);
             continue;
         }
         cudaIpcMemHandle_t h;
@@ -193,6 +227,7 @@ int32_t tr_peer_attach(tr_ctx* c, int32_t rank, int32_t n_ranks, const uint8_t* 
         void* p = nullptr;
         TR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         c->peer_mip0[r] = reinterpret_cast<uint2*>(p) + c->level_off[0];
+        c->peer_flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(p) + c->barrier_flags_offset);
     }
     c->peers_attached = true;
     return TR_OK;

@@ -110,6 +110,9 @@ struct tr_ctx {
     int rank = 0, n_ranks = 1;
     void* nccl_comm = nullptr;
     void* peer_mip0[tr::kMaxPeers] = {};  // peer mip-0 bases (self included) for the peer-store path
+    uint32_t* peer_flags[tr::kMaxPeers] = {};  // every rank's barrier words (self included), behind its pyramid
+    size_t barrier_flags_offset = 0;      // byte offset of the barrier words inside the pyramid allocation
+    uint32_t barrier_epoch = 0;
     bool peers_attached = false;
 };
 
