@@ -394,7 +394,7 @@ def visibility(mesh, instances, primitives, visible_ids, push_constants, y0=0, y
                          C.c_uint32(y0), C.c_uint32(y1), _p(a["depth"]), _p(a["normal"]), _p(a["uv"]),
                          _p(a["material_id"]), _p(b["depth"]), _p(b["normal"]), _p(b["uv"]), _p(b["material_id"]),
                          _p(b["scale"]), _p(a["duv"]), _p(a["ddepth"]), _p(b["duv"]), _p(b["ddepth"]),
-                         _p(mats), C.addressof(tex_arr) if textures else None, C.c_uint32(len(textures or [])))
+                         _p(mats), C.c_void_p(C.addressof(tex_arr)) if textures else None, C.c_uint32(len(textures or [])))
     a["scale"] = None
     return a, b
 

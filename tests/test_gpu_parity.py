@@ -632,6 +632,37 @@ def test_alpha_clip_frame(oracle, ggx_lut, size):
     assert (g1_solid["depth"] != ref["g1"]["depth"]).mean() > 0.002
 
 
+# ------------------------------------------------------------------------------ row N4: an ingested glTF asset
+def test_ingested_gltf_frame(oracle, ggx_lut, tmp_path):
+    """A glTF file (node hierarchy, all four draw buffers, textures bound through base colour / metallic-roughness /
+    normal / specular slots, KHR transmission + volume + ior) goes through gltf_ingest (mirror of src/model_loading.rs)
+    into the C ABI; G-buffer planes bit for bit, whole frame within tolerance against the oracle on the same arrays."""
+    from test_gltf_ingest import _asset
+    from transmission_renderer_b200 import gltf_ingest
+    path, _ = _asset(tmp_path)
+    w, h = 640, 360
+    s = gltf_ingest.finish(gltf_ingest.load_gltf(path))
+    s.update(camera=scenes.Camera(w, h, (0.0, 3.0, 6.0), 0.0, -15.0), lights=scenes.config2_lights(),
+             uniforms=host.make_uniforms(w, h))
+    ref = _textured_reference(oracle, ggx_lut, s)
+    cam = s["camera"]
+    with Renderer(w, h, f32_debug=True) as r:
+        r.set_textures(s["textures"])
+        _upload_scene(r, ggx_lut, s)
+        r.frame(cam.frame_params(host.default_tonemap_params()))
+        for layer, g in ((0, ref["g0"]), (1, ref["g1"])):
+            got = r.read_gbuffer(layer, derivatives=True)
+            for k in ("depth", "normal", "uv", "material_id", "duv", "ddepth"):
+                a, b_ = got[k], np.asarray(g[k]).reshape(got[k].shape)
+                assert a.tobytes() == b_.tobytes(), f"layer {layer} plane {k}: {(a != b_).sum()} values differ"
+        got32 = r.read_hdr_f32()
+    assert set(np.unique(ref["g0"]["material_id"][ref["g0"]["depth"] > 0])) == {0, 1, 4}
+    assert set(np.unique(ref["g1"]["material_id"][ref["g1"]["depth"] > 0])) == {2, 3}
+    e_t = rel_l2(got32[..., :3], ref["t32"][..., :3])
+    print(f"ingested glTF {w}x{h}: final fp32 rel-L2 {e_t:.2e}")
+    assert e_t < REL_L2_TOL
+
+
 # ------------------------------------------------------------------------------ adversarial shading inputs
 def test_random_gbuffer_stress(oracle, ggx_lut):
     """Random G-buffer pixels that hit the ill-conditioned corners of the lobes on purpose: normals facing away from the
