@@ -56,7 +56,7 @@ typedef struct TR_ALIGN16 {
     tr_mat4 proj_view;
     tr_vec3a view_position;
     tr_uvec2 framebuffer_size;
-    uint64_t acceleration_structure_address; /* must be 0 (ray queries out of scope) */
+    uint64_t acceleration_structure_address; /* 0 = no ray queries, else the handle of tr_build_acceleration_structures */
 } tr_push_constants;
 
 /* shared-structs/src/lib.rs:35-41 */
@@ -283,7 +283,7 @@ TR_STATIC_ASSERT(sizeof(tr_ibl_volume_refraction_params) == 104, "IblVolumeRefra
 typedef enum {
     TR_OK = 0,
     TR_ERR_INVALID_ARG = -1,
-    TR_ERR_UNSUPPORTED = -2, /* e.g. alpha-clip draw buffers, debug_clusters != 0, RT address != 0 */
+    TR_ERR_UNSUPPORTED = -2, /* e.g. debug_clusters != 0 */
     TR_ERR_CUDA = -3,
     TR_ERR_NCCL = -4,
     TR_ERR_OOM = -5,
@@ -375,6 +375,29 @@ TR_API int32_t tr_set_texture(tr_ctx* ctx, uint32_t index, const uint8_t* const*
 /* vertex bindings 0..2 + index buffer (pipelines.rs:291-307, main.rs:2516-2557). */
 TR_API int32_t tr_set_mesh(tr_ctx* ctx, const float* positions, const float* normals, const float* uvs,
                            uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices);
+
+/* ------------------------------------------------------------------ */
+/* Ray-queried shadows — the `--ray-tracing` option (src/main.rs:84,   */
+/* 577-658) and the RayQueryKHR variant of the fragment shaders          */
+/* (shader/src/lighting.rs:22-32, 64-71, 97-125, 154-165, 186-195).      */
+/* ------------------------------------------------------------------ */
+/* build_acceleration_structures_from_primitives + build_top_level_acceleration_structure_from_instances
+ * (src/acceleration_structures.rs:6-186, called at src/main.rs:594-649): one bottom-level structure per primitive
+ * over the bound mesh, one top-level structure over the bound instances whose primitive has draw_buffer_index < 2
+ * (src/main.rs:614-625).  *address is what the reference puts in PushConstants.acceleration_structure_address
+ * (src/main.rs:856-859); passing it to tr_frame / tr_shade_* turns the shadow rays on, 0 leaves them off.
+ * Rebinding the mesh or the primitives invalidates it. */
+TR_API int32_t tr_build_acceleration_structures(tr_ctx* ctx, uint64_t* address);
+/* update_top_level_acceleration_structure_from_instances (src/acceleration_structures.rs:188-263, src/main.rs:1332-1345):
+ * after tr_set_instances.  The handle may change; it is returned again. */
+TR_API int32_t tr_update_top_level_acceleration_structure(tr_ctx* ctx, uint64_t* address);
+/* trace_shadow_ray (lighting.rs:97-125) for a batch of rays given in host memory: origins/directions [n*3], t_max [n];
+ * lit[i] = 1 when nothing is hit between t_min = 0.001 and t_max[i], else 0. */
+TR_API int32_t tr_trace_shadow_rays(tr_ctx* ctx, uint32_t n, const float* origins, const float* directions,
+                                    const float* t_max, uint8_t* lit);
+/* Parity hook: the occluded-ray bits the last shading pass of `layer` used, [5][h*w] words (band rows are written):
+ * planes 0-3 bit i = the ray towards the i-th light of the pixel's cluster list, plane 4 bit 0 = the sun ray. */
+TR_API int32_t tr_read_shadow_mask(tr_ctx* ctx, int32_t layer, uint32_t* mask);
 
 /* ------------------------------------------------------------------ */
 /* Per-frame passes, in record() order (src/main.rs:1551-2263).        */

@@ -132,6 +132,18 @@ typedef struct {
 v4 orc_sample_texture(const orc_texture* t, v2 uv, v2 duv_dx, v2 duv_dy);
 float orc_srgb8_to_linear(uint8_t c);
 
+/* ---- ray-queried shadows (oracle/shadow.c; lighting.rs:97-125, src/acceleration_structures.rs) ---- */
+typedef struct orc_mesh_s orc_mesh;
+typedef struct orc_accel orc_accel;
+orc_accel* orc_accel_build(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_inst, const tr_primitive_info* prims,
+                           uint32_t n_prims);
+void orc_accel_free(orc_accel* a);
+uint32_t orc_accel_instance_count(const orc_accel* a); /* instances in the top-level set (draw_buffer_index < 2) */
+float orc_trace_shadow(const orc_accel* a, v3 origin, v3 direction, float t_max);       /* 1 lit, 0 occluded */
+float orc_trace_shadow_brute(const orc_accel* a, v3 origin, v3 direction, float t_max); /* same, no trees */
+void orc_trace_shadow_rays(const orc_accel* a, uint32_t n, const float* origins, const float* directions, const float* t_max,
+                           int brute, uint8_t* lit);
+
 typedef struct {
     const tr_push_constants* pc;
     const tr_uniforms* uniforms;
@@ -144,6 +156,7 @@ typedef struct {
     uint32_t n_clusters;
     const orc_texture* textures; /* may be NULL when no material binds one */
     uint32_t n_textures;
+    const orc_accel* accel; /* NULL: no ray queries (acceleration_structure_address == 0) */
 } orc_scene;
 
 /* what the 2x2 quad gave the reference's fragment stage implicitly: differences to the right / lower neighbour */
@@ -167,6 +180,8 @@ void orc_shade_opaque_frame(const orc_gbuffer* g, const orc_scene* s, uint32_t y
                             uint16_t* hdr_f16, uint16_t* opaque_f16);
 void orc_shade_transmission_frame(const orc_gbuffer* g, const orc_scene* s, const orc_pyramid* fb, const orc_lut* lut,
                                   uint32_t y0, uint32_t y1, float* hdr_f32, uint16_t* hdr_f16);
+/* occluded-ray bits of a layer: [5][h*w], planes 0-3 = cluster-list position, plane 4 bit 0 = sun */
+void orc_shadow_mask_frame(const orc_gbuffer* g, const orc_scene* s, uint32_t y0, uint32_t y1, uint32_t* mask);
 
 /* ---- mip chain (src/main.rs:2054-2063, 2590-2592; Appendix E) -------- */
 uint32_t orc_mip_levels_for_size(uint32_t w, uint32_t h);
@@ -182,13 +197,13 @@ void orc_tonemap_frame(const uint16_t* hdr_f16, uint32_t w, uint32_t h, uint32_t
                        const tr_baked_lottes_tonemapper_params* p, uint8_t* rgba8);
 
 /* ---- visibility (software stand-in for the rasteriser) ---- */
-typedef struct {
+struct orc_mesh_s {
     const float* positions; /* [n_vertices*3] */
     const float* normals;   /* [n_vertices*3] */
     const float* uvs;       /* [n_vertices*2] */
     const uint32_t* indices;
     uint32_t n_vertices, n_indices;
-} orc_mesh;
+};
 void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_inst, const tr_primitive_info* prims,
                     uint32_t n_prims, const uint32_t* visible_ids, uint32_t n_visible, const tr_push_constants* pc,
                     uint32_t y0, uint32_t y1, float* depth0, float* normal0, float* uv0, uint32_t* mat0, float* depth1,

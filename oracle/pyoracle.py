@@ -49,7 +49,7 @@ class Scene(C.Structure):
     _fields_ = [("pc", C.c_void_p), ("uniforms", C.c_void_p), ("materials", C.c_void_p), ("n_materials", C.c_uint32),
                 ("lights", C.c_void_p), ("n_lights", C.c_uint32), ("cluster_light_counts", C.c_void_p),
                 ("cluster_light_indices", C.c_void_p), ("n_clusters", C.c_uint32), ("textures", C.c_void_p),
-                ("n_textures", C.c_uint32)]
+                ("n_textures", C.c_uint32), ("accel", C.c_void_p)]
 
 
 class Mesh(C.Structure):
@@ -321,8 +321,57 @@ def _scene_struct(sc):
     k.tex, k.tex_keep = make_texture_array(sc.get("textures") or [])
     n_tex = len(sc.get("textures") or [])
     s = Scene(k.pc.ctypes.data, k.u.ctypes.data, k.m.ctypes.data, len(k.m), k.l.ctypes.data, len(sc["lights"]),
-              k.cc.ctypes.data, k.ci.ctypes.data, len(k.cc), C.addressof(k.tex) if n_tex else None, n_tex)
+              k.cc.ctypes.data, k.ci.ctypes.data, len(k.cc), C.addressof(k.tex) if n_tex else None, n_tex,
+              sc["accel"].handle if sc.get("accel") is not None else None)
     return s, k
+
+
+# ---- ray-queried shadows (oracle/shadow.c) ----------------------------------------
+class Accel:
+    """orc_accel: bottom-level trees per primitive + the top-level set of instances with draw_buffer_index < 2."""
+
+    def __init__(self, mesh, instances, primitives):
+        L = lib()
+        L.orc_accel_build.restype = C.c_void_p
+        L.orc_accel_instance_count.argtypes = [C.c_void_p]
+        L.orc_accel_instance_count.restype = C.c_uint32
+        self._keep = [_c(mesh["positions"], np.float32), _c(mesh["normals"], np.float32), _c(mesh["uvs"], np.float32),
+                      _c(mesh["indices"], np.uint32), _c(instances, abi.instance), _c(primitives, abi.primitive_info)]
+        pos, nrm, uv, idx, inst, prims = self._keep
+        m = Mesh(pos.ctypes.data, nrm.ctypes.data, uv.ctypes.data, idx.ctypes.data, len(pos), len(idx))
+        self.handle = L.orc_accel_build(C.byref(m), _p(inst), C.c_uint32(len(inst)), _p(prims), C.c_uint32(len(prims)))
+        self.n_instances = L.orc_accel_instance_count(self.handle)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L = lib()
+                L.orc_accel_free.argtypes = [C.c_void_p]
+                L.orc_accel_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def trace(self, origins, directions, t_max, brute=False):
+        """(n,3), (n,3), (n,) -> (n,) uint8, 1 = lit, 0 = occluded (trace_shadow_ray, lighting.rs:97-125)."""
+        o, d, t = _c(origins, np.float32).reshape(-1, 3), _c(directions, np.float32).reshape(-1, 3), _c(t_max, np.float32).reshape(-1)
+        out = np.zeros(len(o), np.uint8)
+        L = lib()
+        L.orc_trace_shadow_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_trace_shadow_rays(self.handle, len(o), o.ctypes.data, d.ctypes.data, t.ctypes.data, 1 if brute else 0, out.ctypes.data)
+        return out
+
+
+def shadow_mask_frame(gbuffer, scene, y0=0, y1=None):
+    """(5, h, w) uint32: occluded-ray bits per pixel (planes 0-3: position in the cluster's light list, plane 4: the sun)."""
+    pc = scene["push_constants"]
+    w, h = int(pc["framebuffer_size"][0, 0]), int(pc["framebuffer_size"][0, 1])
+    y1 = h if y1 is None else y1
+    g, kg = _gbuffer_struct(gbuffer, w, h)
+    s, ks = _scene_struct(scene)
+    out = np.zeros((5, h, w), np.uint32)
+    lib().orc_shadow_mask_frame(C.byref(g), C.byref(s), C.c_uint32(y0), C.c_uint32(y1), _p(out))
+    return out
 
 
 def shade_opaque_frame(gbuffer, scene, y0=0, y1=None):

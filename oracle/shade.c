@@ -355,7 +355,10 @@ v4 orc_fragment(v3 position, v3 normal_in, v2 uv, uint32_t material_id, v4 frag_
     uint32_t num_lights = cluster < s->n_clusters ? s->cluster_light_counts[cluster] : 0u;
 
     v3 sun_dir = from_a(s->uniforms->sun_dir);
-    v3 sun_intensity = v3_scale(from_a(s->uniforms->sun_intensity), 1.0f); /* lighting.rs:168-173 */
+    float sun_factor = 1.0f;
+    if (s->accel) /* lighting.rs:154-165; "todo: ambient lighting via probes or idk!" */
+        sun_factor = f_max(orc_trace_shadow(s->accel, position, sun_dir, 10000.0f), 0.1f);
+    v3 sun_intensity = v3_scale(from_a(s->uniforms->sun_intensity), sun_factor); /* lighting.rs:168-173 */
     orc_brdf_result sum = orc_basic_brdf(normal, sun_dir, sun_intensity, view, mp);
 
     uint32_t offset = cluster * TR_MAX_LIGHTS_PER_CLUSTER;
@@ -365,6 +368,7 @@ v4 orc_fragment(v3 position, v3 normal_in, v2 uv, uint32_t material_id, v4 frag_
         float distance, attenuation;
         orc_light_direction_and_attenuation(position, light_position(light), &direction, &distance, &attenuation);
         float factor = 1.0f;
+        if (s->accel) factor *= orc_trace_shadow(s->accel, position, direction, distance); /* lighting.rs:186-195 */
         if (light->spotlight_direction_and_outer_angle.w != 0.0f) factor *= orc_spotlight_factor(light, direction);
         v3 emission_l = v3_scale(light_emission(light), factor);
         orc_brdf_result r = orc_basic_brdf(normal, direction, v3_scale(emission_l, attenuation), view, mp);
@@ -401,7 +405,8 @@ v4 orc_fragment_transmission(v3 position, v3 normal_in, v2 uv, uint32_t material
 
     /* lighting.rs:37-53 */
     v3 sun_dir = from_a(s->uniforms->sun_dir);
-    v3 sun_intensity = v3_scale(from_a(s->uniforms->sun_intensity), 1.0f);
+    float sun_factor = s->accel ? orc_trace_shadow(s->accel, position, sun_dir, 10000.0f) : 1.0f; /* lighting.rs:25-35 */
+    v3 sun_intensity = v3_scale(from_a(s->uniforms->sun_intensity), sun_factor);
     orc_brdf_result sum = orc_basic_brdf(normal, sun_dir, sun_intensity, view, mp);
     v3 transmission = v3_mul(sun_intensity, orc_transmission_btdf(mp, normal, view, sun_dir));
 
@@ -412,7 +417,8 @@ v4 orc_fragment_transmission(v3 position, v3 normal_in, v2 uv, uint32_t material
         v3 direction;
         float distance, attenuation;
         orc_light_direction_and_attenuation(position, light_position(light), &direction, &distance, &attenuation);
-        v3 emission_l = v3_scale(light_emission(light), 1.0f);
+        float factor = s->accel ? orc_trace_shadow(s->accel, position, direction, distance) : 1.0f; /* lighting.rs:64-75 */
+        v3 emission_l = v3_scale(light_emission(light), factor);
         orc_brdf_result r = orc_basic_brdf(normal, direction, v3_scale(emission_l, attenuation), view, mp);
         sum.diffuse = v3_add(sum.diffuse, r.diffuse);
         sum.specular = v3_add(sum.specular, r.specular);
@@ -528,6 +534,40 @@ void orc_shade_transmission_frame(const orc_gbuffer* g, const orc_scene* s, cons
             orc_frag_derivatives d = decode_derivatives(g, &inv_pv, x, y, depth, pos);
             v4 c = orc_fragment_transmission(pos, n, uv, g->material_id[i], scale, fc, s, fb, lut, &d);
             store_px(hdr_f32, hdr_f16, NULL, i, c);
+        }
+    }
+}
+
+/* Which shadow rays of a layer are occluded, as the product's shadow pass stores them: plane 0..3 = bit i set when the
+ * ray towards the i-th light of the pixel's cluster list is occluded, plane 4 bit 0 = the sun ray.  mask: [5][h*w]. */
+void orc_shadow_mask_frame(const orc_gbuffer* g, const orc_scene* s, uint32_t y0, uint32_t y1, uint32_t* mask) {
+    tr_mat4 inv;
+    orc_mat4_inverse(&s->pc->proj_view, &inv);
+    m4 inv_pv;
+    memcpy(&inv_pv, &inv, sizeof(m4));
+    const size_t plane = (size_t)g->width * g->height;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t yy = (int64_t)y0; yy < (int64_t)y1; yy++) {
+        uint32_t y = (uint32_t)yy;
+        for (uint32_t x = 0; x < g->width; x++) {
+            size_t i = (size_t)y * g->width + x;
+            float depth = g->depth[i];
+            uint32_t m[5] = {0, 0, 0, 0, 0};
+            if (depth != 0.0f && s->accel) {
+                v3 pos = decode_position(g, &inv_pv, x, y, depth);
+                v4 fc = v4_new((float)x + 0.5f, (float)y + 0.5f, depth, 1.0f);
+                uint32_t cluster = cluster_index(fc, s->uniforms);
+                uint32_t num_lights = cluster < s->n_clusters ? s->cluster_light_counts[cluster] : 0u;
+                if (orc_trace_shadow(s->accel, pos, from_a(s->uniforms->sun_dir), 10000.0f) == 0.0f) m[4] = 1u;
+                for (uint32_t k = 0; k < num_lights; k++) {
+                    const tr_light* light = &s->lights[s->cluster_light_indices[cluster * TR_MAX_LIGHTS_PER_CLUSTER + k]];
+                    v3 direction;
+                    float distance, attenuation;
+                    orc_light_direction_and_attenuation(pos, light_position(light), &direction, &distance, &attenuation);
+                    if (orc_trace_shadow(s->accel, pos, direction, distance) == 0.0f) m[k >> 5] |= 1u << (k & 31u);
+                }
+            }
+            for (int k = 0; k < 5; k++) mask[(size_t)k * plane + i] = m[k];
         }
     }
 }

@@ -535,7 +535,7 @@ def test_error_behaviour():
         pc["acceleration_structure_address"] = 1
         with pytest.raises(TrError) as e:
             r.shade_opaque(pc)
-        assert e.value.status == -2                                   # ray-query shadows
+        assert e.value.status == -1                                   # not a handle of tr_build_acceleration_structures
         bad = scenes.Camera(32, 32).push_constants()
         with pytest.raises(TrError) as e:
             r.shade_opaque(bad)

@@ -21,7 +21,8 @@ _LIB = None
 EXPORTS = [
     "tr_create", "tr_destroy", "tr_resize", "tr_set_band", "tr_last_error", "tr_version", "tr_set_stream", "tr_sync",
     "tr_set_instances", "tr_set_primitives", "tr_set_materials", "tr_set_lights", "tr_set_uniforms", "tr_set_ggx_lut", "tr_set_texture",
-    "tr_set_mesh", "tr_cull", "tr_build_clusters", "tr_assign_lights", "tr_visibility", "tr_shade_opaque",
+    "tr_set_mesh", "tr_build_acceleration_structures", "tr_update_top_level_acceleration_structure", "tr_trace_shadow_rays",
+    "tr_read_shadow_mask", "tr_cull", "tr_build_clusters", "tr_assign_lights", "tr_visibility", "tr_shade_opaque",
     "tr_allgather_opaque", "tr_generate_mips", "tr_shade_transmission", "tr_tonemap", "tr_frame", "tr_set_gbuffer",
     "tr_read_gbuffer", "tr_set_opaque_frame", "tr_set_hdr", "tr_set_cluster_lights", "tr_read_visible_instances",
     "tr_read_instance_counts", "tr_read_draws", "tr_read_cluster_aabbs", "tr_read_cluster_lights", "tr_read_hdr",

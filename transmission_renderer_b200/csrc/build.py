@@ -9,9 +9,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libtr.so")
-SOURCES = ["tr_api.cu", "tr_comm.cu", "k_shade.cu", "k_mips.cu", "k_tonemap.cu", "k_eval.cu", "k_cull.cu",
-           "k_clusters.cu", "k_visibility.cu", "k_peak.cu"]
-HEADERS = ["tr_internal.h", "tr_device_math.cuh", "tr_device_pbr.cuh", os.path.join("..", "..", "include", "tr_abi.h")]
+SOURCES = ["tr_api.cu", "tr_comm.cu", "k_shade.cu", "k_shade_shadow.cu", "k_accel.cu", "k_mips.cu", "k_tonemap.cu", "k_eval.cu",
+           "k_cull.cu", "k_clusters.cu", "k_visibility.cu", "k_peak.cu"]
+HEADERS = ["tr_internal.h", "tr_device_math.cuh", "tr_device_pbr.cuh", "tr_device_accel.cuh",
+           os.path.join("..", "..", "include", "tr_abi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
               "-fPIC,-fvisibility=hidden,-ffp-contract=off", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

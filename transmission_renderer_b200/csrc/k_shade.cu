@@ -21,9 +21,18 @@
 //     writes the same value to both targets, lib.rs:247-248).  With the
 //     peer-store path the odd lanes write that band into every peer GPU's
 //     mip 0 over NVLink, which is the all-gather fused into the shading kernel.
+//   * ray-queried shadows (lighting.rs:22-32, 64-71, 154-165, 186-195): this file is compiled a second time as
+//     k_shade_shadow.cu with TR_SHADE_SHADOW=1.  That translation unit holds the shadow pass (one thread per pixel
+//     traces the sun ray and one ray per light of the pixel's cluster list, tr_device_accel.cuh, and stores the
+//     occluded-ray bits) and the shading kernels instantiated to read those bits; the instantiations without ray
+//     queries are untouched by it.
 #include <type_traits>
 
 #include "tr_internal.h"
+
+#ifndef TR_SHADE_SHADOW
+#define TR_SHADE_SHADOW 0
+#endif
 
 using namespace trd;
 
@@ -116,7 +125,7 @@ constexpr int kLightUnroll = TR_LIGHT_UNROLL;
 #ifndef TR_SHADE_CTAS_TRANS
 #define TR_SHADE_CTAS_TRANS 3
 #endif
-template <bool TRANS, bool HAS_POS, bool F32OUT, bool TEX>
+template <bool TRANS, bool HAS_POS, bool F32OUT, bool TEX, bool SHADOW>
 __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_CTAS_OPAQUE)) shade_kernel(const __grid_constant__ tr::ShadeLaunch p) {
     using L = StageLayout<TRANS, HAS_POS>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -202,6 +211,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
         uint32_t my_count = 0, my_base = 0;
         float model_scale = 1.0f;
         float roughness_px = 0.0f, transmission_px = 0.0f, thickness_px = 0.0f;  // after their textures (lib.rs:71-77, 120-124)
+        uint32_t occl0 = 0, occl1 = 0, occl2 = 0, occl3 = 0;  // SHADOW: occluded-ray bits by position in the cluster's list
 
         if (covered) {
             const uint32_t py = g / p.width, px = g - py * p.width;
@@ -300,11 +310,20 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             f3 sun_dir = mk3(p.uniforms.sun_dir.x, p.uniforms.sun_dir.y, p.uniforms.sun_dir.z);
             f3 sun_int = mk3(p.uniforms.sun_intensity.x, p.uniforms.sun_intensity.y, p.uniforms.sun_intensity.z);
             // the sun's direction is given, so its exact chain starts at the halfway vector; same adaptive rule as the clustered lights
-            {
+            float sun_factor = 1.0f;
+            if (SHADOW) {
+                occl0 = __ldg(p.shadow_mask + g);
+                occl1 = __ldg(p.shadow_mask + (size_t)p.shadow_plane + g);
+                occl2 = __ldg(p.shadow_mask + (size_t)p.shadow_plane * 2 + g);
+                occl3 = __ldg(p.shadow_mask + (size_t)p.shadow_plane * 3 + g);
+                // opaque pass: factor.max(0.1), lighting.rs:154-165; transmissive pass: the factor as it is, :25-35
+                if (__ldg(p.shadow_mask + (size_t)p.shadow_plane * 4 + g) & 1u) sun_factor = TRANS ? 0.0f : 0.1f;
+            }
+            if (!SHADOW || sun_factor != 0.0f) {
                 auto exact_sun = [&]() { return sun_dir; };
                 const float nol_raw = dot3(ps.n, sun_dir), vol = dot3(ps.v, sun_dir);
-                brdf_light_fast(ps, exact_sun, nol_raw, vol, sun_int, 1.0f, sum_d, spec);
-                if (TRANS) btdf_light_fast(ps, exact_sun, nol_raw, vol, sun_int, 1.0f, sum_t);
+                brdf_light_fast(ps, exact_sun, nol_raw, vol, sun_int, sun_factor, sum_d, spec);
+                if (TRANS) btdf_light_fast(ps, exact_sun, nol_raw, vol, sun_int, sun_factor, sum_t);
             }
         }
 
@@ -347,6 +366,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
                 brdf_light_fast(ps, exact_dir, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_d, spec);
                 if (TRANS) btdf_light_fast(ps, exact_dir, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_t);
             };
+            auto occluded_word = [&](uint32_t i) { return i < 64u ? (i < 32u ? occl0 : occl1) : (i < 96u ? occl2 : occl3); };
             // 93-96 % of the warps of the 4K workload have all their covered pixels in ONE cluster: the list is then walked
             // with warp-uniform indices (no merge, no per-lane cursor); uncovered lanes just compute along
             const uint32_t key = covered ? my_base : 0xffffffffu;
@@ -355,8 +375,15 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
                 if (first != 0xffffffffu) {
                     const uint32_t count = __reduce_max_sync(0xffffffffu, covered ? my_count : 0u);
                     const uint32_t* list = p.cluster_indices + first;
+                    if (SHADOW) {
+                        for (uint32_t i = 0; i < count; i++) {
+                            const LightS l = load_light(__ldg(list + i));
+                            if (!((occluded_word(i) >> (i & 31u)) & 1u)) shade_light(l);  // an occluded light adds nothing
+                        }
+                    } else {
 #pragma unroll kLightUnroll
-                    for (uint32_t i = 0; i < count; i++) shade_light(load_light(__ldg(list + i)));
+                        for (uint32_t i = 0; i < count; i++) shade_light(load_light(__ldg(list + i)));
+                    }
                 }
                 return;
             }
@@ -369,9 +396,10 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
                 if (m == 0xffffffffu) break;
                 const LightS l = load_light(m);
                 if (next == m) {
+                    const bool occluded = SHADOW && ((occluded_word(my_i) >> (my_i & 31u)) & 1u);
                     my_i++;
                     const uint32_t upcoming = my_i < my_count ? __ldg(my_list + my_i) : 0xffffffffu;  // issued early: hidden behind the BRDF
-                    shade_light(l);
+                    if (!occluded) shade_light(l);
                     next = upcoming;
                 }
             }
@@ -457,15 +485,18 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
     }
 }
 
+constexpr bool kShadow = TR_SHADE_SHADOW != 0;
+
 template <bool TRANS, bool HAS_POS, bool F32OUT, bool TEX>
 int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
+    if (kShadow != (p.shadow_mask != nullptr)) return tr::fail(TR_ERR_STATE, "shade kernel variant and shadow mask disagree");
     using L = StageLayout<TRANS, HAS_POS>;
     const uint32_t n_px = p.px_end - p.px_begin;
     if (n_px == 0) return TR_OK;
     const uint32_t n_tiles = (n_px + TILE - 1) / TILE;
     const uint32_t n_smem_lights = p.n_lights <= (uint32_t)MAX_SMEM_LIGHTS ? p.n_lights : 0u;
     const size_t smem = 128 + (size_t)STAGES * L::kBytes + (size_t)n_smem_lights * sizeof(LightS);
-    auto kern = shade_kernel<TRANS, HAS_POS, F32OUT, TEX>;
+    auto kern = shade_kernel<TRANS, HAS_POS, F32OUT, TEX, kShadow>;
     TR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE, smem));
@@ -495,7 +526,63 @@ int32_t launch_any(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
 
 }  // namespace
 
+#if TR_SHADE_SHADOW
+// The shadow pass: one thread per pixel of the band.  Ray set-up in the exact regime, in the oracle's operation order
+// (orc_shadow_mask_frame): origin = the fragment's world position, direction / t_max from
+// light_direction_and_attenuation (glam-pbr lib.rs:12-23), the sun with t_max 10 000.
+template <bool HAS_POS>
+__global__ void __launch_bounds__(128) shadow_mask_kernel(const __grid_constant__ tr::ShadeLaunch p) {
+    const uint32_t g = p.px_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.px_end) return;
+    const float depth = __ldg(p.depth + g);
+    uint32_t m[5] = {0u, 0u, 0u, 0u, 0u};
+    if (depth != 0.0f) {
+        const uint32_t py = g / p.width, px = g - py * p.width;
+        const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+        f3 pos;
+        if (HAS_POS) {
+            pos = mk3(__ldg(p.position + (size_t)g * 3), __ldg(p.position + (size_t)g * 3 + 1), __ldg(p.position + (size_t)g * 3 + 2));
+        } else {
+            float ndc_x = xsub(xmul(xdiv(fx, (float)p.width), 2.0f), 1.0f);
+            float ndc_y = xsub(xmul(xdiv(fy, (float)p.height), 2.0f), 1.0f);
+            f4 h = xmat4_mul(p.inv_proj_view, ndc_x, ndc_y, depth, 1.0f);
+            pos = mk3(xdiv(h.x, h.w), xdiv(h.y, h.w), xdiv(h.z, h.w));
+        }
+        const f3 sun_dir = mk3(p.uniforms.sun_dir.x, p.uniforms.sun_dir.y, p.uniforms.sun_dir.z);
+        if (accel_occluded(p.accel, pos, sun_dir, kSunTMax)) m[4] = 1u;
+        const uint32_t cluster = cluster_index(fx, fy, depth, p.uniforms);
+        if (cluster < p.n_clusters) {
+            const uint32_t count = min(__ldg(p.cluster_counts + cluster), TR_MAX_LIGHTS_PER_CLUSTER);
+            const uint32_t* list = p.cluster_indices + (size_t)cluster * TR_MAX_LIGHTS_PER_CLUSTER;
+            for (uint32_t i = 0; i < count; i++) {
+                const float4 lp = __ldg(reinterpret_cast<const float4*>(p.lights + __ldg(list + i)));
+                const f3 vec = xsub3(mk3(lp.x, lp.y, lp.z), pos);
+                const float dist = xsqrt(xdot3(vec, vec));
+                if (accel_occluded(p.accel, pos, xdivs3(vec, dist), dist)) m[i >> 5] |= 1u << (i & 31u);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) p.shadow_mask[(size_t)p.shadow_plane * k + g] = m[k];
+}
+#endif
+
 namespace tr {
+#if TR_SHADE_SHADOW
+int32_t launch_shade_opaque_shadowed(const ShadeLaunch& p, int sm_count, cudaStream_t s) { return launch_any<false>(p, sm_count, s); }
+int32_t launch_shade_transmission_shadowed(const ShadeLaunch& p, int sm_count, cudaStream_t s) { return launch_any<true>(p, sm_count, s); }
+int32_t launch_shadow_mask(const ShadeLaunch& p, int sm_count, cudaStream_t s) {
+    const uint32_t n_px = p.px_end - p.px_begin;
+    if (n_px == 0) return TR_OK;
+    if (!p.shadow_mask) return fail(TR_ERR_STATE, "shadow pass without a mask buffer");
+    if (p.position) shadow_mask_kernel<true><<<(n_px + 127) / 128, 128, 0, s>>>(p);
+    else shadow_mask_kernel<false><<<(n_px + 127) / 128, 128, 0, s>>>(p);
+    count_launches(1);
+    TR_CUDA(cudaGetLastError());
+    return TR_OK;
+}
+#else
 int32_t launch_shade_opaque(const ShadeLaunch& p, int sm_count, cudaStream_t s) { return launch_any<false>(p, sm_count, s); }
 int32_t launch_shade_transmission(const ShadeLaunch& p, int sm_count, cudaStream_t s) { return launch_any<true>(p, sm_count, s); }
+#endif
 }  // namespace tr

@@ -193,8 +193,14 @@ static int32_t sum_frame_times(tr_ctx* c, int slot, tr_frame_times* out) {
 
 static int32_t check_pc(const tr_ctx* c, const tr_push_constants* pc, const char* who) {
     if (!pc) return fail(TR_ERR_INVALID_ARG, "%s: null push constants", who);
-    if (pc->acceleration_structure_address != 0)
-        return fail(TR_ERR_UNSUPPORTED, "%s: ray-query shadows are out of scope (acceleration_structure_address != 0)", who);
+    if (pc->acceleration_structure_address != 0) {  // the `--ray-tracing` variant of the fragment shaders, lib.rs:100-102
+        if (!c->accel_blas_valid || pc->acceleration_structure_address != (uint64_t)(uintptr_t)c->accel_tlas.p)
+            return fail(TR_ERR_INVALID_ARG, "%s: acceleration_structure_address is not the handle of tr_build_acceleration_structures "
+                        "(or the mesh / primitives changed since)", who);
+        if (!c->accel_tlas_valid)
+            return fail(TR_ERR_STATE, "%s: instances changed since the top-level structure was built "
+                        "(tr_update_top_level_acceleration_structure)", who);
+    }
     if (pc->framebuffer_size.x != c->width || pc->framebuffer_size.y != c->height)
         return fail(TR_ERR_INVALID_ARG, "%s: framebuffer_size %ux%u does not match the context %ux%u", who,
                     pc->framebuffer_size.x, pc->framebuffer_size.y, c->width, c->height);
@@ -257,6 +263,13 @@ static int32_t fill_shade(tr_ctx* c, const tr_push_constants* pc, int layer, Sha
     s->hdr_f32 = (c->flags & TR_FLAG_HDR_F32_DEBUG) ? c->hdr_f32.as<float4>() : nullptr;
     s->pyramid = pyramid_desc(c);
     s->lut = lut_desc(c);
+    if (pc->acceleration_structure_address != 0) {
+        const size_t plane = (size_t)c->width * c->height;
+        TR_TRY(c->shadow_mask[layer].ensure(plane * 5 * 4));
+        s->shadow_mask = c->shadow_mask[layer].as<uint32_t>();
+        s->shadow_plane = (uint32_t)plane;
+        s->accel = accel_desc(c);
+    }
     return TR_OK;
 }
 
@@ -340,7 +353,8 @@ int32_t tr_destroy(tr_ctx* c) {
                       &c->mesh_uv, &c->mesh_idx, &c->visible_ids, &c->cull_scalars, &c->draws[0], &c->draws[1],
                       &c->draws[2], &c->draws[3], &c->work_prefix, &c->slot_z, &c->cluster_aabbs, &c->cluster_counts,
                       &c->cluster_indices, &c->vis[0], &c->vis[1], &c->bin_entries, &c->bin_state, &c->tri_records, &c->dev_status, &c->band_list, &c->hdr, &c->hdr_f32, &c->pyramid,
-                      &c->srgb8, &c->mip_counter};
+                      &c->srgb8, &c->mip_counter, &c->accel_tlas, &c->accel_blas, &c->accel_inst, &c->accel_tris,
+                      &c->shadow_mask[0], &c->shadow_mask[1]};
     for (DevBuf* b : bufs) b->release();
     for (DevBuf& b : c->tex_data) b.release();
     c->tex_table.release();
@@ -421,6 +435,7 @@ int32_t tr_set_instances(tr_ctx* c, const tr_instance* instances, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) c->h_inst_prim[i] = instances[i].primitive_id;
     c->tri_bound_valid = false;
     c->cull_valid = false;
+    c->accel_tlas_valid = false;  // src/main.rs:1263-1345: an instance write is followed by a top-level update
     return TR_OK;
 }
 
@@ -440,6 +455,7 @@ int32_t tr_set_primitives(tr_ctx* c, const tr_primitive_info* prims, uint32_t n)
     for (uint32_t i = 0; i < n; i++) c->h_prim_tris[i] = prims[i].index_count / 3u;
     c->tri_bound_valid = false;
     c->cull_valid = false;
+    c->accel_blas_valid = c->accel_tlas_valid = false;
     return TR_OK;
 }
 
@@ -560,6 +576,65 @@ int32_t tr_set_mesh(tr_ctx* c, const float* positions, const float* normals, con
     TR_TRY(upload(c, c->mesh_idx, indices, (size_t)n_indices * 4));
     c->n_vertices = n_vertices;
     c->n_indices = n_indices;
+    c->accel_blas_valid = c->accel_tlas_valid = false;
+    return TR_OK;
+}
+
+// ------------------------------------------------------------------ ray-queried shadows
+int32_t tr_build_acceleration_structures(tr_ctx* c, uint64_t* address) {
+    TR_CHECK_CTX(c);
+    if (!address) return fail(TR_ERR_INVALID_ARG, "tr_build_acceleration_structures: null");
+    *address = 0;
+    TR_TRY(accel_build(c));
+    *address = (uint64_t)(uintptr_t)c->accel_tlas.p;
+    return TR_OK;
+}
+
+int32_t tr_update_top_level_acceleration_structure(tr_ctx* c, uint64_t* address) {
+    TR_CHECK_CTX(c);
+    TR_TRY(accel_build_tlas(c));
+    if (address) *address = (uint64_t)(uintptr_t)c->accel_tlas.p;
+    return TR_OK;
+}
+
+int32_t tr_trace_shadow_rays(tr_ctx* c, uint32_t n, const float* origins, const float* directions, const float* t_max, uint8_t* lit) {
+    TR_CHECK_CTX(c);
+    if (!c->accel_blas_valid || !c->accel_tlas_valid) return fail(TR_ERR_STATE, "tr_trace_shadow_rays: acceleration structures not built");
+    if (n && (!origins || !directions || !t_max || !lit)) return fail(TR_ERR_INVALID_ARG, "tr_trace_shadow_rays: null");
+    if (!n) return TR_OK;
+    DevBuf o, d, t, out;
+    int32_t st = TR_OK;
+    auto run = [&]() -> int32_t {
+        TR_TRY(o.ensure((size_t)n * 12));
+        TR_TRY(d.ensure((size_t)n * 12));
+        TR_TRY(t.ensure((size_t)n * 4));
+        TR_TRY(out.ensure(n));
+        TR_CUDA(cudaMemcpyAsync(o.p, origins, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        TR_CUDA(cudaMemcpyAsync(d.p, directions, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        TR_CUDA(cudaMemcpyAsync(t.p, t_max, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        TR_TRY(launch_trace_rays(c, n, o.as<float>(), d.as<float>(), t.as<float>(), out.as<uint8_t>()));
+        TR_CUDA(cudaMemcpyAsync(lit, out.p, n, cudaMemcpyDeviceToHost, c->stream));
+        TR_CUDA(cudaStreamSynchronize(c->stream));
+        return TR_OK;
+    };
+    st = run();
+    cudaStreamSynchronize(c->stream);
+    o.release(); d.release(); t.release(); out.release();
+    return st;
+}
+
+int32_t tr_read_shadow_mask(tr_ctx* c, int32_t layer, uint32_t* mask) {
+    TR_CHECK_CTX(c);
+    if (layer < 0 || layer > 1 || !mask) return fail(TR_ERR_INVALID_ARG, "tr_read_shadow_mask: bad argument");
+    const size_t plane = (size_t)c->width * c->height;
+    if (c->shadow_mask[layer].bytes < plane * 20) return fail(TR_ERR_STATE, "tr_read_shadow_mask: layer %d was not shaded with ray queries", layer);
+    // band rows only; the rest of the caller's buffer is left untouched
+    for (int k = 0; k < 5; k++) {
+        const size_t off = plane * k + (size_t)c->band_y0 * c->width;
+        TR_CUDA(cudaMemcpyAsync(mask + off, c->shadow_mask[layer].as<uint32_t>() + off, (size_t)(c->band_y1 - c->band_y0) * c->width * 4,
+                                cudaMemcpyDeviceToHost, c->stream));
+    }
+    TR_CUDA(cudaStreamSynchronize(c->stream));
     return TR_OK;
 }
 
@@ -609,7 +684,12 @@ int32_t tr_shade_opaque(tr_ctx* c, const tr_push_constants* pc) {
         s.opaque[s.n_opaque++] = mip0;
     }
     pass_begin(c, P_OPAQUE);
-    TR_TRY(launch_shade_opaque(s, c->sm_count, c->stream));
+    if (s.shadow_mask) {
+        TR_TRY(launch_shadow_mask(s, c->sm_count, c->stream));
+        TR_TRY(launch_shade_opaque_shadowed(s, c->sm_count, c->stream));
+    } else {
+        TR_TRY(launch_shade_opaque(s, c->sm_count, c->stream));
+    }
     pass_end(c, P_OPAQUE);
     c->opaque_valid = true;
     c->hdr_valid = true;
@@ -650,7 +730,12 @@ int32_t tr_shade_transmission(tr_ctx* c, const tr_push_constants* pc) {
         c->hdr_valid = true;
     }
     pass_begin(c, P_TRANS);
-    TR_TRY(launch_shade_transmission(s, c->sm_count, c->stream));
+    if (s.shadow_mask) {
+        TR_TRY(launch_shadow_mask(s, c->sm_count, c->stream));
+        TR_TRY(launch_shade_transmission_shadowed(s, c->sm_count, c->stream));
+    } else {
+        TR_TRY(launch_shade_transmission(s, c->sm_count, c->stream));
+    }
     pass_end(c, P_TRANS);
     return TR_OK;
 }

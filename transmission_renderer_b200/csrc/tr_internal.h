@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/tr_abi.h"
+#include "tr_device_accel.cuh"
 #include "tr_device_pbr.cuh"
 
 namespace tr {
@@ -95,6 +96,13 @@ struct tr_ctx {
     uint32_t levels = 0, level_w[tr::kMaxLevels] = {}, level_h[tr::kMaxLevels] = {}, level_off[tr::kMaxLevels] = {};
     bool opaque_valid = false, mips_valid = false, hdr_valid = false, srgb_valid = false;
 
+    // ray-queried shadows (k_accel.cu): bottom-level trees per primitive, top-level tree over the shadow-casting instances
+    tr::DevBuf accel_tlas, accel_blas, accel_inst, accel_tris, shadow_mask[2];
+    uint32_t accel_n_instances = 0;
+    bool accel_blas_valid = false, accel_tlas_valid = false;
+    std::vector<float> h_prim_box;                                  // object-space box per primitive (lo, hi)
+    std::vector<uint32_t> h_prim_root, h_prim_tri_base, h_prim_bucket;
+
     // timing (profiling.rs zone taxonomy)
     bool timing = false;
     cudaEvent_t (*ev_begin)[tr::P_COUNT] = nullptr, (*ev_end)[tr::P_COUNT] = nullptr;  // [kTimingRing][P_COUNT], lazily created
@@ -148,10 +156,23 @@ struct ShadeLaunch {
     int n_opaque;
     trd::PyramidDesc pyramid;
     trd::LutDesc lut;
+    // ray-queried shadows: occluded-ray bits per pixel, written by the shadow pass and read by the shading kernel.
+    // Five planes of `shadow_plane` words: 0-3 = position in the cluster's light list, 4 = the sun.  nullptr: no ray queries.
+    uint32_t* shadow_mask;
+    uint32_t shadow_plane;
+    trd::AccelDesc accel;
 };
 
 int32_t launch_shade_opaque(const ShadeLaunch& p, int sm_count, cudaStream_t s);
 int32_t launch_shade_transmission(const ShadeLaunch& p, int sm_count, cudaStream_t s);
+// the same kernels instantiated with the shadow-mask reads, plus the pass that traces the rays (k_shade_shadow.cu)
+int32_t launch_shade_opaque_shadowed(const ShadeLaunch& p, int sm_count, cudaStream_t s);
+int32_t launch_shade_transmission_shadowed(const ShadeLaunch& p, int sm_count, cudaStream_t s);
+int32_t launch_shadow_mask(const ShadeLaunch& p, int sm_count, cudaStream_t s);
+trd::AccelDesc accel_desc(const tr_ctx* c);
+int32_t accel_build(tr_ctx* c);       // bottom-level structures of every primitive, then the top level
+int32_t accel_build_tlas(tr_ctx* c);  // top level only (instances moved)
+int32_t launch_trace_rays(tr_ctx* c, uint32_t n, const float* d_origins, const float* d_directions, const float* d_t_max, uint8_t* d_lit);
 int32_t launch_generate_mips(uint2* pyramid, uint32_t levels, const uint32_t* w, const uint32_t* h, const uint32_t* off,
                              uint32_t* counter, int sm_count, cudaStream_t s);
 int32_t launch_tonemap(const uint2* hdr, uchar4* out, uint32_t px_begin, uint32_t px_end,

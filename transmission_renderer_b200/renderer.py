@@ -124,6 +124,33 @@ class Renderer:
         p, n, u, i = _c(positions, np.float32), _c(normals, np.float32), _c(uvs, np.float32), _c(indices, np.uint32)
         _check(_lib().tr_set_mesh(self._ctx, _p(p), _p(n), _p(u), C.c_uint32(len(p)), _p(i), C.c_uint32(i.size)))
 
+    # -- ray-queried shadows (`--ray-tracing`, src/main.rs:577-658) ---------------------------
+    def build_acceleration_structures(self):
+        """Bottom-level structures of every primitive + the top level over the instances with draw_buffer_index < 2.
+        Returns the handle to put into PushConstants.acceleration_structure_address (src/main.rs:856-859)."""
+        a = C.c_uint64(0)
+        _check(_lib().tr_build_acceleration_structures(self._ctx, C.byref(a)))
+        return a.value
+
+    def update_top_level_acceleration_structure(self):
+        a = C.c_uint64(0)
+        _check(_lib().tr_update_top_level_acceleration_structure(self._ctx, C.byref(a)))
+        return a.value
+
+    def trace_shadow_rays(self, origins, directions, t_max):
+        """(n,3), (n,3), (n,) -> (n,) uint8: 1 = lit, 0 = occluded (trace_shadow_ray, lighting.rs:97-125)."""
+        o, d = _c(origins, np.float32).reshape(-1, 3), _c(directions, np.float32).reshape(-1, 3)
+        t = _c(t_max, np.float32).reshape(-1)
+        out = np.zeros(len(o), np.uint8)
+        _check(_lib().tr_trace_shadow_rays(self._ctx, C.c_uint32(len(o)), _p(o), _p(d), _p(t), _p(out)))
+        return out
+
+    def read_shadow_mask(self, layer):
+        """(5, h, w) uint32 occluded-ray bits of the last shading pass of `layer` (band rows)."""
+        out = np.zeros((5, self.height, self.width), np.uint32)
+        _check(_lib().tr_read_shadow_mask(self._ctx, C.c_int32(layer), _p(out)))
+        return out
+
     # -- passes, in record() order --------------------------------------------------------
     def cull(self, culling_pc):
         _check(_lib().tr_cull(self._ctx, _p(_c(culling_pc, abi.culling_push_constants))))

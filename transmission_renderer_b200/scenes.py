@@ -178,8 +178,10 @@ class Camera:
         self.perspective = host.perspective_matrix_reversed(width, height)
         self.proj_view = (self.perspective.astype(f32) @ self.view.astype(f32)).astype(f32)   # main.rs:1188-1195
 
-    def push_constants(self):
-        return host.make_push_constants(self.proj_view, self.position, self.width, self.height)
+    def push_constants(self, acceleration_structure_address=0):
+        pc = host.make_push_constants(self.proj_view, self.position, self.width, self.height)
+        pc["acceleration_structure_address"] = acceleration_structure_address
+        return pc
 
     def culling(self):
         return host.make_culling_push_constants(self.view, self.perspective)
@@ -190,11 +192,11 @@ class Camera:
     def assign_lights(self):
         return host.make_assign_lights_push_constants(self.view, self.rotation)
 
-    def frame_params(self, tonemap=None, flags=0):
+    def frame_params(self, tonemap=None, flags=0, acceleration_structure_address=0):
         f = np.zeros(1, dtype=abi.frame_params)
         f["culling"] = self.culling()
         f["assign_lights"] = self.assign_lights()
-        f["push_constants"] = self.push_constants()
+        f["push_constants"] = self.push_constants(acceleration_structure_address)
         f["tonemap"] = host.default_tonemap_params() if tonemap is None else tonemap
         f["flags"] = flags
         return f
@@ -578,3 +580,58 @@ def alpha_clip_scene(width, height, seed=0x5EED00A4):
     mesh["uvs"] = (mesh["uvs"] * f32(2.0)).astype(f32)
     return dict(camera=cam, mesh=mesh, primitives=prims, instances=np.concatenate(inst), materials=mats,
                 lights=config2_lights(), uniforms=host.make_uniforms(width, height), textures=textures)
+
+
+# --------------------------------------------------------------------------- ray-queried shadows (`--ray-tracing`)
+def shadow_scene(width, height, seed=0x5EED00A5):
+    """Occluders over a ground quad, lit by the sun, point lights and a spotlight placed so that shadows fall inside the
+    view: spheres and rotated boxes (draw buffer 0), an alpha-clip sphere (buffer 1: casts, src/main.rs:617-620), and a
+    frosted-glass knot (buffer 2: receives shadows but casts none)."""
+    cam = Camera(width, height, (0.0, 3.2, 6.5), 0.0, -20.0)
+    meshes = MeshSet()
+    sphere = meshes.add(uv_sphere(32, 16), 0)
+    box = meshes.add(box_mesh(), 0)
+    quad = meshes.add(quad_mesh(1.0), 0)
+    sphere_clip = meshes.add(uv_sphere(24, 12), 1)
+    knot = meshes.add(torus_knot(n_u=192, n_v=24), 2)
+    mats = hashed_materials(8, seed)
+    mats["metallic_factor"][:6] = 0.0
+    mats["diffuse_factor"][6] = (0.55, 0.55, 0.6, 1.0)   # ground
+    mats["roughness_factor"][6] = 0.8
+    mats["metallic_factor"][6] = 0.0
+    glass = 7
+    mats["diffuse_factor"][glass] = (1.0, 1.0, 1.0, 1.0)
+    mats["metallic_factor"][glass] = 0.0
+    mats["roughness_factor"][glass] = 0.3
+    mats["transmission_factor"][glass] = 1.0
+    mats["thickness_factor"][glass] = 0.5
+    mats["attenuation_distance"][glass] = 0.8
+    mats["attenuation_colour"][glass] = (0.8, 0.9, 0.5, 0.0)
+    s45 = (0.0, 0.38268343, 0.0, 0.92387953)
+    tilt = (0.25881905, 0.0, 0.0, 0.96592583)
+    inst = [
+        make_instance((0.0, 0.0, -3.0), 25.0, (0, 0, 0, 1), quad, 6),
+        make_instance((-2.2, 0.9, -1.0), 0.9, (0, 0, 0, 1), sphere, 0),
+        make_instance((1.8, 0.6, 0.4), 0.6, s45, box, 1),
+        make_instance((0.2, 1.9, -2.6), 0.7, tilt, box, 2),
+        make_instance((3.4, 1.2, -2.0), 0.5, (0, 0, 0, 1), sphere, 3),
+        make_instance((-0.6, 0.45, 1.6), 0.45, (0, 0, 0, 1), sphere_clip, 4),
+        make_instance((-3.6, 2.4, -3.4), 0.35, s45, box, 5),
+        make_instance((0.6, 1.3, 2.4), 0.9, (0.0, 0.0, 0.0, 1.0), knot, glass),
+    ]
+    lights = np.concatenate([
+        host.light_new_point((0.0, 4.5, 1.0), (1.0, 0.95, 0.9), 40.0),
+        host.light_new_point((-4.0, 1.2, 1.5), (1.0, 0.3, 0.2), 25.0),
+        host.light_new_point((4.5, 2.0, 1.0), (0.2, 0.4, 1.0), 30.0),
+        host.light_new_point((0.5, 0.4, -1.2), (0.3, 1.0, 0.4), 8.0),
+        host.light_new_spot((2.5, 5.0, 2.5), (1.0, 1.0, 0.8), 80.0, _unit((-0.35, -0.85, -0.4)), 0.35, 0.55),
+        host.light_new_point((-1.5, 3.0, -5.0), (0.9, 0.7, 1.0), 35.0),
+    ])
+    mesh, prims = meshes.arrays()
+    return dict(camera=cam, mesh=mesh, primitives=prims, instances=np.concatenate(inst), materials=mats,
+                lights=lights, uniforms=host.make_uniforms(width, height))
+
+
+def _unit(v):
+    v = np.asarray(v, np.float64)
+    return tuple((v / np.linalg.norm(v)).astype(f32))
