@@ -305,6 +305,11 @@ def run_b200(args, wl):
     m = scene["mesh"]
     r.set_mesh(m["positions"], m["normals"], m["uvs"], m["indices"])
     r.build_clusters(cam.write_cluster_data())
+    as_handle, as_build_ms = 0, None
+    if args.ray_tracing:                          # the reference's `--ray-tracing` option (src/main.rs:84, 577-658)
+        t0 = time.perf_counter()
+        as_handle = r.build_acceleration_structures()
+        as_build_ms = (time.perf_counter() - t0) * 1e3
     from transmission_renderer_b200 import parallel, scenes
     groups = max(1, min(args.view_groups, world))
     if world % groups or args.views % groups:
@@ -324,14 +329,14 @@ def run_b200(args, wl):
         eb_r, eb_n = (int(x) for x in args.emulate_band.split("/"))
         y0, y1 = host.band_rows(H, eb_r, eb_n)
         r.set_band(y0, y1)
-    fp = cam.frame_params(host.default_tonemap_params())
+    fp = cam.frame_params(host.default_tonemap_params(), acceleration_structure_address=as_handle)
     # views of this rank's group: orbit in yaw around the scene centre (configs[4]); view 0 is the scene's own camera
     my_fps = [fp]
     if args.views > 1:
         my_fps = []
         for v in range(group_id, args.views, groups):
             vc = scenes.Camera(W, H, tuple(cam.position), 360.0 * v / args.views, -10.0)
-            my_fps.append(vc.frame_params(host.default_tonemap_params()))
+            my_fps.append(vc.frame_params(host.default_tonemap_params(), acceleration_structure_address=as_handle))
     frames_per_step = len(my_fps)
 
     def sync():
@@ -400,6 +405,8 @@ def run_b200(args, wl):
             i = j * frames_per_step + k
             r.set_instances(inst_host)
             r.set_lights(lights_host)
+            if args.ray_tracing:     # an instance write is followed by the top-level update, src/main.rs:1263-1345
+                f["push_constants"]["acceleration_structure_address"] = r.update_top_level_acceleration_structure()
             r.frame(f)
             r.read_srgb8_async(out_host[i & 1])
 
@@ -454,7 +461,7 @@ def run_b200(args, wl):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "width": W, "height": H, "instances": wl["n_instances"], "lights": wl["n_lights"],
                        "parallelism": f"bands{bands}" + (f"xviews{groups}" if groups > 1 else ""), "views": args.views,
-                       "exchange": exchange,
+                       "exchange": exchange, "ray_queries": bool(args.ray_tracing),
                        "l2": "inputs larger than L2: ~0.9 GB of G-buffer, visibility and frame planes are touched per frame vs 126 MB L2",
                        "coverage_opaque": work["coverage_opaque"], "coverage_transmissive": work["coverage_transmissive"],
                        "mean_lights_opaque": work["mean_lights_opaque"], "mean_lights_transmissive": work["mean_lights_transmissive"]},
@@ -471,7 +478,10 @@ def run_b200(args, wl):
             "raster_stats_per_frame": {k: v / (args.steps + max(args.warmup, 3)) for k, v in rstats.items()},
         }
         # ---- CPU baseline: the oracle port on the box's host cores, bounded sample, N=1 only; doubles as a live parity check
-        if world == 1 and args.views == 1 and not args.no_cpu_baseline:
+        if as_build_ms is not None:
+            line["acceleration_structure_build_ms"] = as_build_ms
+            line["roofline"]["note"] = "shading passes include the shadow-ray pass; its traversal work is not in the algorithmic flop count"
+        if world == 1 and args.views == 1 and not args.no_cpu_baseline and not args.ray_tracing:
             opaque16 = r.read_pyramid_level(0)
             gpu_hdr = r.read_hdr()
             cpu = cpu_sample(scene, lut, opaque16)
@@ -503,6 +513,8 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
                     help="N>1: opaque bands by fused peer stores over NVLink (default) or by an NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ray-tracing", action="store_true",
+                    help="ray-queried shadows on (the reference's --ray-tracing option); off for the headline metric")
     ap.add_argument("--views", type=int, default=1,
                     help="camera views per step (BASELINE configs[4]: 64 orbit views); a step then renders all of them")
     ap.add_argument("--view-groups", type=int, default=1,
