@@ -63,6 +63,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -129,7 +132,8 @@ template <bool TRANS, bool HAS_POS, bool F32OUT, bool TEX, bool SHADOW>
 __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_CTAS_OPAQUE)) shade_kernel(const __grid_constant__ tr::ShadeLaunch p) {
     using L = StageLayout<TRANS, HAS_POS>;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // STAGES barriers
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // STAGES barriers: the TMA engine has filled the stage
+    uint64_t* empty = full + STAGES;                              // STAGES barriers: every warp has read what it needs of it
     unsigned char* stage_base = smem + 128;
     LightS* s_lights = reinterpret_cast<LightS*>(stage_base + STAGES * L::kBytes);
 
@@ -142,7 +146,10 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
     asm volatile("mov.u32 %0, %0;" : "+r"(lights_saddr));  // opaque to the optimiser: keep it in a register instead of re-deriving it per light
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], TILE / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (lights_in_smem)
@@ -170,8 +177,13 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
     if (tid == 0)
         for (int s = 0; s < STAGES; s++) issue(blockIdx.x + s * gridDim.x, s);
 
-    uint32_t phase_bits = 0;
-    int stage = 0;
+    // The staged planes are only read in the prologue of a tile.  Each warp releases the stage right after it (empty
+    // barrier), and thread 0 refills the stage of the PREVIOUS tile once all warps have released it — there is no
+    // CTA-wide barrier per tile, so warps with short light lists run ahead (up to the depth of the ring) instead of
+    // waiting for the slowest warp of every tile (barrier stalls were ~1 of the ~5 resident warps per scheduler).
+    uint32_t phase_bits = 0, empty_bits = 0;
+    int stage = 0, prev_stage = -1;
+    uint32_t prev_t = 0;
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const uint32_t start = tile_start(t), n = tile_count(t);
         unsigned char* sb = stage_base + stage * L::kBytes;
@@ -185,6 +197,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             mbar_wait(&full[stage], (phase_bits >> stage) & 1u);
             phase_bits ^= 1u << stage;
         } else {  // ragged tile (unaligned start or size): plain coalesced loads
+            __syncthreads();  // every warp is past its last use of this stage
             for (uint32_t i = tid; i < n; i += TILE) {
                 s_depth[i] = p.depth[start + i];
                 s_mat[i] = p.material_id[start + i];
@@ -326,6 +339,17 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
                 if (TRANS) btdf_light_fast(ps, exact_sun, nol_raw, vol, sun_int, sun_factor, sum_t);
             }
         }
+
+        // this warp is done with the stage; thread 0 refills the previous tile's stage when everybody has released it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (tid == 0 && prev_stage >= 0) {
+            mbar_wait(&empty[prev_stage], (empty_bits >> prev_stage) & 1u);
+            empty_bits ^= 1u << prev_stage;
+            issue(prev_t + STAGES * gridDim.x, prev_stage);
+        }
+        prev_stage = stage;
+        prev_t = t;
 
         // ------------------------------------------------------------ clustered lights
         const uint32_t* const my_list = p.cluster_indices + my_base;
@@ -479,8 +503,6 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             }
         }
 
-        __syncthreads();  // every thread is done with this stage's shared memory
-        if (tid == 0) issue(t + STAGES * gridDim.x, stage);
         stage = stage + 1 == STAGES ? 0 : stage + 1;
     }
 }
