@@ -66,6 +66,7 @@ int32_t build_range(std::vector<AccelNode>& nodes, std::vector<Item>& items, uin
     *out_box = box;
     if (count <= leaf_max) return (int32_t) ~(first | ((count - 1u) << 28));
 
+    // widest centroid axis: used by the median fallback
     int axis = 0;
     float ext = cbox.hi[0] - cbox.lo[0];
     for (int k = 1; k < 3; k++)
@@ -75,47 +76,56 @@ int32_t build_range(std::vector<AccelNode>& nodes, std::vector<Item>& items, uin
         }
     uint32_t mid = 0;
     if (depth < kSahDepth && ext > 0.0f && count > 4u) {
-        // binned surface-area heuristic on the widest centroid axis
-        uint32_t bin_n[kBins] = {};
-        Box bin_b[kBins];
-        for (int b = 0; b < kBins; b++) bin_b[b] = box_empty();
-        const float scale = (float)kBins / ext;
-        auto bin_of = [&](const Item& it) {
-            int b = (int)(((it.box.lo[axis] + it.box.hi[axis]) - cbox.lo[axis]) * scale);
-            return b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-        };
-        for (uint32_t i = 0; i < count; i++) {
-            const int b = bin_of(items[first + i]);
-            bin_n[b]++;
-            box_union(bin_b[b], items[first + i].box);
-        }
-        float right_area[kBins];
-        uint32_t right_n[kBins];
-        Box acc = box_empty();
-        uint32_t n = 0;
-        for (int b = kBins - 1; b > 0; b--) {
-            box_union(acc, bin_b[b]);
-            n += bin_n[b];
-            right_area[b] = box_area(acc);
-            right_n[b] = n;
-        }
-        acc = box_empty();
-        n = 0;
+        // binned surface-area heuristic, best split over the three axes
         float best = std::numeric_limits<float>::infinity();
-        int best_split = -1;
-        for (int b = 0; b < kBins - 1; b++) {
-            box_union(acc, bin_b[b]);
-            n += bin_n[b];
-            if (n == 0 || right_n[b + 1] == 0) continue;
-            const float cost = box_area(acc) * (float)n + right_area[b + 1] * (float)right_n[b + 1];
-            if (cost < best) {
-                best = cost;
-                best_split = b;
+        int best_axis = -1, best_split = -1;
+        float best_scale = 0.0f;
+        for (int ax = 0; ax < 3; ax++) {
+            const float e = cbox.hi[ax] - cbox.lo[ax];
+            if (!(e > 0.0f)) continue;
+            uint32_t bin_n[kBins] = {};
+            Box bin_b[kBins];
+            for (int b = 0; b < kBins; b++) bin_b[b] = box_empty();
+            const float scale = (float)kBins / e;
+            for (uint32_t i = 0; i < count; i++) {
+                const Item& it = items[first + i];
+                int b = (int)(((it.box.lo[ax] + it.box.hi[ax]) - cbox.lo[ax]) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                bin_n[b]++;
+                box_union(bin_b[b], it.box);
+            }
+            float right_area[kBins];
+            uint32_t right_n[kBins];
+            Box acc = box_empty();
+            uint32_t n = 0;
+            for (int b = kBins - 1; b > 0; b--) {
+                box_union(acc, bin_b[b]);
+                n += bin_n[b];
+                right_area[b] = box_area(acc);
+                right_n[b] = n;
+            }
+            acc = box_empty();
+            n = 0;
+            for (int b = 0; b < kBins - 1; b++) {
+                box_union(acc, bin_b[b]);
+                n += bin_n[b];
+                if (n == 0 || right_n[b + 1] == 0) continue;
+                const float cost = box_area(acc) * (float)n + right_area[b + 1] * (float)right_n[b + 1];
+                if (cost < best) {
+                    best = cost;
+                    best_axis = ax;
+                    best_split = b;
+                    best_scale = scale;
+                }
             }
         }
-        if (best_split >= 0) {
-            auto it = std::partition(items.begin() + first, items.begin() + first + count,
-                                     [&](const Item& x) { return bin_of(x) <= best_split; });
+        if (best_axis >= 0) {
+            const int ax = best_axis;
+            auto it = std::partition(items.begin() + first, items.begin() + first + count, [&](const Item& x) {
+                int b = (int)(((x.box.lo[ax] + x.box.hi[ax]) - cbox.lo[ax]) * best_scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                return b <= best_split;
+            });
             mid = (uint32_t)(it - (items.begin() + first));
         }
     }
