@@ -4,12 +4,11 @@
 //   K4  `fragment`              shader/src/lib.rs:164-249 + lighting.rs:145-220
 //   K6  `fragment_transmission` shader/src/lib.rs:37-162  + lighting.rs:13-95
 // B200 design (DESIGN.md "K4/K6"):
-//   * persistent CTAs, one per SM slot, walking 256-pixel tiles of the band in
-//     flattened row-major order, so every G-buffer plane of a tile is ONE
-//     contiguous run in HBM;
-//   * each plane of the next tiles is staged into shared memory by the TMA
-//     engine (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a
-//     4-deep ring, so HBM latency is hidden without needing occupancy;
+//   * persistent CTAs; every WARP walks its own strided sequence of 32-pixel runs of the band in flattened
+//     row-major order, so every G-buffer plane of a run is ONE contiguous range in HBM;
+//   * each plane of the warp's next runs is staged into shared memory by the TMA engine (cp.async.bulk +
+//     mbarrier complete_tx, SASS UBLKCP) through the warp's own 4-deep ring, so HBM latency is hidden without
+//     needing occupancy and no warp ever waits for another one;
 //   * lights are converted once per CTA into a compact shared-memory table;
 //     the per-pixel cluster lists (ascending light id) are walked with a
 //     warp-wide sorted merge (redux.min) so a warp stays converged while every
@@ -38,7 +37,9 @@ using namespace trd;
 
 namespace {
 
-constexpr int TILE = 256;  // pixels per tile == threads per CTA
+constexpr int TILE = 256;   // threads per CTA
+constexpr int CHUNK = 32;   // pixels per work item: one warp, one pixel per lane
+constexpr int WARPS = TILE / 32;
 constexpr int STAGES = 4;
 constexpr int MAX_SMEM_LIGHTS = 1024;
 
@@ -63,9 +64,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -83,11 +81,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template <bool TRANS, bool HAS_POS>
 struct StageLayout {
     static constexpr int kDepth = 0;
-    static constexpr int kNormal = kDepth + TILE * 4;
-    static constexpr int kMat = kNormal + TILE * 12;
-    static constexpr int kScale = kMat + TILE * 4;
-    static constexpr int kPos = kScale + (TRANS ? TILE * 4 : 0);
-    static constexpr int kBytes = kPos + (HAS_POS ? TILE * 12 : 0);
+    static constexpr int kNormal = kDepth + CHUNK * 4;
+    static constexpr int kMat = kNormal + CHUNK * 12;
+    static constexpr int kScale = kMat + CHUNK * 4;
+    static constexpr int kPos = kScale + (TRANS ? CHUNK * 4 : 0);
+    static constexpr int kBytes = kPos + (HAS_POS ? CHUNK * 12 : 0);
 };
 
 __device__ __forceinline__ LightS make_light_s(const tr_light* lights, uint32_t i) {
@@ -132,35 +130,37 @@ template <bool TRANS, bool HAS_POS, bool F32OUT, bool TEX, bool SHADOW>
 __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS : TR_SHADE_CTAS_OPAQUE)) shade_kernel(const __grid_constant__ tr::ShadeLaunch p) {
     using L = StageLayout<TRANS, HAS_POS>;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // STAGES barriers: the TMA engine has filled the stage
-    uint64_t* empty = full + STAGES;                              // STAGES barriers: every warp has read what it needs of it
-    unsigned char* stage_base = smem + 128;
-    LightS* s_lights = reinterpret_cast<LightS*>(stage_base + STAGES * L::kBytes);
-
+    // Every warp runs its own pipeline: a ring of STAGES small stages (32 pixels of every G-buffer plane each), its own
+    // `full` mbarriers, its own sequence of 32-pixel runs of the band (strided over all warps of the grid).  Lane 0 refills
+    // a stage as soon as its warp has read it.  Nothing in the loop synchronises warps with each other, so a warp whose
+    // pixels see long light lists never holds the others up (with one 256-pixel tile per CTA and a barrier per tile, ~1 of
+    // the ~5 resident warps per scheduler sat at that barrier).
     const int tid = threadIdx.x;
-    const uint32_t lane = tid & 31;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem) + warp * STAGES;   // this warp's STAGES barriers (256 B reserved for all)
+    unsigned char* stage_base = smem + 256 + (size_t)warp * STAGES * L::kBytes;
+    LightS* s_lights = reinterpret_cast<LightS*>(smem + 256 + (size_t)WARPS * STAGES * L::kBytes);
+
     const uint32_t n_px = p.px_end - p.px_begin;
-    const uint32_t n_tiles = (n_px + TILE - 1) / TILE;
+    const uint32_t n_tiles = (n_px + CHUNK - 1) / CHUNK;
+    const uint32_t first_tile = blockIdx.x * WARPS + warp, tile_stride = gridDim.x * WARPS;
     const bool lights_in_smem = p.n_lights <= MAX_SMEM_LIGHTS;
     uint32_t lights_saddr = smem_u32(s_lights);
     asm volatile("mov.u32 %0, %0;" : "+r"(lights_saddr));  // opaque to the optimiser: keep it in a register instead of re-deriving it per light
 
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], TILE / 32);
-        }
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (lights_in_smem)
         for (uint32_t i = tid; i < p.n_lights; i += TILE) s_lights[i] = make_light_s(p.lights, i);
     __syncthreads();
 
-    auto tile_start = [&](uint32_t t) { return p.px_begin + t * TILE; };
-    auto tile_count = [&](uint32_t t) { return min((uint32_t)TILE, p.px_end - tile_start(t)); };
+    auto tile_start = [&](uint32_t t) { return p.px_begin + t * CHUNK; };
+    auto tile_count = [&](uint32_t t) { return min((uint32_t)CHUNK, p.px_end - tile_start(t)); };
     auto tile_bulk = [&](uint32_t t) { return ((tile_start(t) & 3u) == 0u) && ((tile_count(t) & 3u) == 0u); };
 
-    auto issue = [&](uint32_t t, int s) {  // thread 0 only
+    auto issue = [&](uint32_t t, int s) {  // lane 0 only
         if (t >= n_tiles || !tile_bulk(t)) return;
         const uint32_t start = tile_start(t), n = tile_count(t);
         unsigned char* sb = stage_base + s * L::kBytes;
@@ -174,17 +174,12 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
         if (HAS_POS) bulk_g2s(sb + L::kPos, p.position + (size_t)start * 3, n * 12, &full[s]);
     };
 
-    if (tid == 0)
-        for (int s = 0; s < STAGES; s++) issue(blockIdx.x + s * gridDim.x, s);
+    if (lane == 0)
+        for (int s = 0; s < STAGES; s++) issue(first_tile + s * tile_stride, s);
 
-    // The staged planes are only read in the prologue of a tile.  Each warp releases the stage right after it (empty
-    // barrier), and thread 0 refills the stage of the PREVIOUS tile once all warps have released it — there is no
-    // CTA-wide barrier per tile, so warps with short light lists run ahead (up to the depth of the ring) instead of
-    // waiting for the slowest warp of every tile (barrier stalls were ~1 of the ~5 resident warps per scheduler).
-    uint32_t phase_bits = 0, empty_bits = 0;
-    int stage = 0, prev_stage = -1;
-    uint32_t prev_t = 0;
-    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    uint32_t phase_bits = 0;
+    int stage = 0;
+    for (uint32_t t = first_tile; t < n_tiles; t += tile_stride) {
         const uint32_t start = tile_start(t), n = tile_count(t);
         unsigned char* sb = stage_base + stage * L::kBytes;
         float* s_depth = reinterpret_cast<float*>(sb + L::kDepth);
@@ -196,24 +191,23 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
         if (tile_bulk(t)) {
             mbar_wait(&full[stage], (phase_bits >> stage) & 1u);
             phase_bits ^= 1u << stage;
-        } else {  // ragged tile (unaligned start or size): plain coalesced loads
-            __syncthreads();  // every warp is past its last use of this stage
-            for (uint32_t i = tid; i < n; i += TILE) {
-                s_depth[i] = p.depth[start + i];
-                s_mat[i] = p.material_id[start + i];
-                if (TRANS) s_scale[i] = p.scale[start + i];
+        } else {  // ragged run (unaligned start or size): plain loads into the warp's own stage
+            if (lane < n) {
+                s_depth[lane] = p.depth[start + lane];
+                s_mat[lane] = p.material_id[start + lane];
+                if (TRANS) s_scale[lane] = p.scale[start + lane];
+                for (int k = 0; k < 3; k++) {
+                    s_normal[lane * 3 + k] = p.normal[(size_t)(start + lane) * 3 + k];
+                    if (HAS_POS) s_pos[lane * 3 + k] = p.position[(size_t)(start + lane) * 3 + k];
+                }
             }
-            for (uint32_t i = tid; i < n * 3; i += TILE) {
-                s_normal[i] = p.normal[(size_t)start * 3 + i];
-                if (HAS_POS) s_pos[i] = p.position[(size_t)start * 3 + i];
-            }
-            __syncthreads();
+            __syncwarp();
         }
 
         // ------------------------------------------------------------ per-pixel prologue
-        const bool active = (uint32_t)tid < n;
-        const uint32_t g = start + tid;
-        const float depth = active ? s_depth[tid] : 0.0f;
+        const bool active = lane < n;
+        const uint32_t g = start + lane;
+        const float depth = active ? s_depth[lane] : 0.0f;
         const bool covered = active && depth != 0.0f;
 
         PixelShading ps;
@@ -230,7 +224,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             const uint32_t py = g / p.width, px = g - py * p.width;
             const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
             if (HAS_POS) {
-                pos = mk3(s_pos[tid * 3], s_pos[tid * 3 + 1], s_pos[tid * 3 + 2]);
+                pos = mk3(s_pos[lane * 3], s_pos[lane * 3 + 1], s_pos[lane * 3 + 2]);
             } else {
                 // G-buffer decode (oracle: decode_position in oracle/shade.c), exact regime
                 float ndc_x = xsub(xmul(xdiv(fx, (float)p.width), 2.0f), 1.0f);
@@ -238,7 +232,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
                 f4 h = xmat4_mul(p.inv_proj_view, ndc_x, ndc_y, depth, 1.0f);
                 pos = mk3(xdiv(h.x, h.w), xdiv(h.y, h.w), xdiv(h.z, h.w));
             }
-            mat = p.materials + s_mat[tid];
+            mat = p.materials + s_mat[lane];
             float4 dfac = __ldg(reinterpret_cast<const float4*>(&mat->diffuse_factor));
             const float4 emis = __ldg(reinterpret_cast<const float4*>(&mat->emissive_factor));
             const float4 scol = __ldg(reinterpret_cast<const float4*>(&mat->specular_colour_factor));
@@ -256,7 +250,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
 
             f3 view_pos = mk3(p.view_position[0], p.view_position[1], p.view_position[2]);
             f3 v = xnormalize3(xsub3(view_pos, pos));                                    // lib.rs:196-197
-            const f3 n_in = mk3(s_normal[tid * 3], s_normal[tid * 3 + 1], s_normal[tid * 3 + 2]);
+            const f3 n_in = mk3(s_normal[lane * 3], s_normal[lane * 3 + 1], s_normal[lane * 3 + 2]);
             f3 nrm;
             if (TEX) {
                 // texture-mapped material (exact regime, oracle/shade.c): lib.rs:66-77,120-124,190-194; lighting.rs:222-313
@@ -311,7 +305,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             mp.diffuse_colour = mk3(dfac.x, dfac.y, dfac.z);
             roughness_px = mp.perceptual_roughness;
             ps = make_pixel_shading(mp, nrm, v, TRANS);
-            if (TRANS) model_scale = s_scale[tid];
+            if (TRANS) model_scale = s_scale[lane];
 
             const uint32_t cluster = cluster_index(fx, fy, depth, p.uniforms);
             if (cluster < p.n_clusters) {
@@ -340,16 +334,9 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             }
         }
 
-        // this warp is done with the stage; thread 0 refills the previous tile's stage when everybody has released it
+        // the staged planes are only read above: refill the stage right away with the run STAGES turns ahead
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        if (tid == 0 && prev_stage >= 0) {
-            mbar_wait(&empty[prev_stage], (empty_bits >> prev_stage) & 1u);
-            empty_bits ^= 1u << prev_stage;
-            issue(prev_t + STAGES * gridDim.x, prev_stage);
-        }
-        prev_stage = stage;
-        prev_t = t;
+        if (lane == 0) issue(t + STAGES * tile_stride, stage);
 
         // ------------------------------------------------------------ clustered lights
         const uint32_t* const my_list = p.cluster_indices + my_base;
@@ -481,7 +468,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             const bool vec_ok = (start & 1u) == 0u;
             if (active) {
                 if (F32OUT) p.hdr_f32[g] = out;
-                const bool has_partner = vec_ok && (((lane & 1u) != 0u) || ((uint32_t)tid + 1u < n));
+                const bool has_partner = vec_ok && (((lane & 1u) != 0u) || (lane + 1u < n));
                 if (has_partner) {
                     if ((lane & 1u) == 0u) {
                         *reinterpret_cast<uint4*>(p.hdr + g) = make_uint4(packed.x, packed.y, other_x, other_y);
@@ -515,9 +502,9 @@ int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
     using L = StageLayout<TRANS, HAS_POS>;
     const uint32_t n_px = p.px_end - p.px_begin;
     if (n_px == 0) return TR_OK;
-    const uint32_t n_tiles = (n_px + TILE - 1) / TILE;
+    const uint32_t n_tiles = (n_px + TILE - 1) / TILE;   // CTAs worth of 32-pixel runs
     const uint32_t n_smem_lights = p.n_lights <= (uint32_t)MAX_SMEM_LIGHTS ? p.n_lights : 0u;
-    const size_t smem = 128 + (size_t)STAGES * L::kBytes + (size_t)n_smem_lights * sizeof(LightS);
+    const size_t smem = 256 + (size_t)WARPS * STAGES * L::kBytes + (size_t)n_smem_lights * sizeof(LightS);
     auto kern = shade_kernel<TRANS, HAS_POS, F32OUT, TEX, kShadow>;
     TR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
