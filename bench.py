@@ -398,17 +398,22 @@ def run_b200(args, wl):
     h2d = inst_host.nbytes + lights_host.nbytes + fp.nbytes
     d2h = (y1 - y0) * W * 4
 
+    e2e_skip = set(filter(None, os.environ.get("TR_E2E_SKIP", "").split(",")))   # diagnosis only: inst, lights, readback
+
     def e2e_step(j):
         # frame i: inputs up, frame, band read-back enqueued behind it on the copy stream; then hand frame i-1's band
         # (other pinned buffer) to the consumer — like the reference presenting frame n-1 while recording frame n
         for k, f in enumerate(my_fps):
             i = j * frames_per_step + k
-            r.set_instances(inst_host)
-            r.set_lights(lights_host)
+            if "inst" not in e2e_skip:
+                r.set_instances(inst_host)
+            if "lights" not in e2e_skip:
+                r.set_lights(lights_host)
             if args.ray_tracing:     # an instance write is followed by the top-level update, src/main.rs:1263-1345
                 f["push_constants"]["acceleration_structure_address"] = r.update_top_level_acceleration_structure()
             r.frame(f)
-            r.read_srgb8_async(out_host[i & 1])
+            if "readback" not in e2e_skip:
+                r.read_srgb8_async(out_host[i & 1])
 
     with torch.cuda.stream(stream):
         for i in range(max(args.warmup, 3)):

@@ -9,6 +9,8 @@
 #include <new>
 #include <vector>
 
+#include <algorithm>
+
 #include "tr_internal.h"
 
 namespace tr {
