@@ -143,6 +143,7 @@ float orc_trace_shadow(const orc_accel* a, v3 origin, v3 direction, float t_max)
 float orc_trace_shadow_brute(const orc_accel* a, v3 origin, v3 direction, float t_max); /* same, no trees */
 void orc_trace_shadow_rays(const orc_accel* a, uint32_t n, const float* origins, const float* directions, const float* t_max,
                            int brute, uint8_t* lit);
+int orc_slab_test(const float origin[3], const float direction[3], float t_min, float t_max, const float lo[3], const float hi[3]);
 
 typedef struct {
     const tr_push_constants* pc;

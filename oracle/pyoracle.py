@@ -362,6 +362,14 @@ class Accel:
         return out
 
 
+def slab_test(origin, direction, t_min, t_max, lo, hi):
+    """The fp32 ray/box interval test of the shadow definition (oracle/shadow.c slab)."""
+    a = [np.ascontiguousarray(x, np.float32) for x in (origin, direction, lo, hi)]
+    L = lib()
+    L.orc_slab_test.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    return bool(L.orc_slab_test(a[0].ctypes.data, a[1].ctypes.data, float(t_min), float(t_max), a[2].ctypes.data, a[3].ctypes.data))
+
+
 def shadow_mask_frame(gbuffer, scene, y0=0, y1=None):
     """(5, h, w) uint32: occluded-ray bits per pixel (planes 0-3: position in the cluster's light list, plane 4: the sun)."""
     pc = scene["push_constants"]

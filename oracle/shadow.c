@@ -348,3 +348,10 @@ void orc_trace_shadow_rays(const orc_accel* a, uint32_t n, const float* origins,
         lit[i] = f != 0.0f;
     }
 }
+
+/* the slab predicate on its own, for the property tests (monotone in the box: tests/test_oracle_shadows.py) */
+int orc_slab_test(const float origin[3], const float direction[3], float t_min, float t_max, const float lo[3], const float hi[3]) {
+    ray r = make_ray(v3_new(origin[0], origin[1], origin[2]), v3_new(direction[0], direction[1], direction[2]), t_min, t_max);
+    box3 b = {{lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}};
+    return slab(&r, &b);
+}

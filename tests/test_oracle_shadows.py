@@ -130,3 +130,31 @@ def test_shadows_darken_the_frame(oracle, ggx_lut):
     t32_lit, _ = oracle.shade_transmission_frame(g1, sc_lit, levels, ggx_lut, sh32, sh16)
     glass = g1["depth"] > 0
     assert glass.sum() > 50 and (np.abs(t32[glass] - t32_lit[glass]).max() > 1e-3)
+
+
+def test_slab_is_monotone_in_the_box(oracle):
+    """What makes the result independent of the trees: a box that contains another one never fails where the inner one
+    passes — including rays with zero and negative-zero direction components and origins on a face (0 * inf)."""
+    from hypothesis import given, settings, strategies as st
+    coord = st.one_of(st.floats(-50, 50, width=32), st.sampled_from([0.0, 1.0, -1.0, 0.5]))
+    comp = st.one_of(st.floats(-1, 1, width=32), st.sampled_from([0.0, -0.0, 1.0, -1.0]))
+    grow = st.one_of(st.floats(0, 10, width=32), st.just(0.0))
+
+    @settings(max_examples=1500, deadline=None)
+    @given(st.tuples(coord, coord, coord), st.tuples(comp, comp, comp), st.tuples(coord, coord, coord), st.tuples(grow, grow, grow),
+           st.tuples(grow, grow, grow), st.tuples(grow, grow, grow), st.floats(0.015625, 100, width=32))
+    def check(o, d, lo, ext, g_lo, g_hi, t_max):
+        if d == (0.0, 0.0, 0.0):
+            return
+        lo = np.array(lo, f32)
+        hi = (lo + np.array(ext, f32)).astype(f32)
+        big_lo = (lo - np.array(g_lo, f32)).astype(f32)
+        big_hi = (hi + np.array(g_hi, f32)).astype(f32)
+        if oracle.slab_test(o, d, 0.001, t_max, lo, hi):
+            assert oracle.slab_test(o, d, 0.001, t_max, big_lo, big_hi)
+
+    check()
+    # known answers of the 0 * inf corner: direction parallel to a face the origin lies on
+    assert oracle.slab_test((0, 0, 0), (1, 0, 0), 0.001, 10, (1, 0, -1), (2, 1, 1))          # origin.y == lo.y, d.y == 0
+    assert not oracle.slab_test((0, -0.5, 0), (1, 0, 0), 0.001, 10, (1, 0, -1), (2, 1, 1))   # below the box, parallel
+    assert oracle.slab_test((0, 0.5, 0), (1, -0.0, 0), 0.001, 10, (1, 0, -1), (2, 1, 1))     # negative zero component
