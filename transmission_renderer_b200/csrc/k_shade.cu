@@ -137,13 +137,16 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
     // the ~5 resident warps per scheduler sat at that barrier).
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem) + warp * STAGES;   // this warp's STAGES barriers (256 B reserved for all)
-    unsigned char* stage_base = smem + 256 + (size_t)warp * STAGES * L::kBytes;
-    LightS* s_lights = reinterpret_cast<LightS*>(smem + 256 + (size_t)WARPS * STAGES * L::kBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem) + warp * STAGES;   // this warp's STAGES barriers (bytes 0-255 for all warps)
+    unsigned char* stage_base = smem + 512 + (size_t)warp * STAGES * L::kBytes;
+    LightS* s_lights = reinterpret_cast<LightS*>(smem + 512 + (size_t)WARPS * STAGES * L::kBytes);
 
     const uint32_t n_px = p.px_end - p.px_begin;
     const uint32_t n_tiles = (n_px + CHUNK - 1) / CHUNK;
-    const uint32_t first_tile = blockIdx.x * WARPS + warp, tile_stride = gridDim.x * WARPS;
+    // runs are handed out dynamically (one atomic per run on p.chunk_counter): a fixed strided assignment leaves the
+    // slowest of the ~3500 resident warps ~15 % behind the average at the end of the kernel (73 runs per warp, cost
+    // proportional to the light count), and the kernel ends with the slowest warp
+    uint32_t* s_claim = reinterpret_cast<uint32_t*>(smem + 256) + warp * STAGES;   // the run each stage of this warp holds (bytes 256-383)
     const bool lights_in_smem = p.n_lights <= MAX_SMEM_LIGHTS;
     uint32_t lights_saddr = smem_u32(s_lights);
     asm volatile("mov.u32 %0, %0;" : "+r"(lights_saddr));  // opaque to the optimiser: keep it in a register instead of re-deriving it per light
@@ -175,11 +178,18 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
     };
 
     if (lane == 0)
-        for (int s = 0; s < STAGES; s++) issue(first_tile + s * tile_stride, s);
+        for (int s = 0; s < STAGES; s++) {
+            const uint32_t t = atomicAdd(p.chunk_counter, 1u);
+            s_claim[s] = t;
+            issue(t, s);
+        }
+    __syncwarp();
 
     uint32_t phase_bits = 0;
     int stage = 0;
-    for (uint32_t t = first_tile; t < n_tiles; t += tile_stride) {
+    while (true) {
+        const uint32_t t = s_claim[stage];
+        if (t >= n_tiles) break;   // claims only grow: nothing valid is left in the other stages either
         const uint32_t start = tile_start(t), n = tile_count(t);
         unsigned char* sb = stage_base + stage * L::kBytes;
         float* s_depth = reinterpret_cast<float*>(sb + L::kDepth);
@@ -336,7 +346,11 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
 
         // the staged planes are only read above: refill the stage right away with the run STAGES turns ahead
         __syncwarp();
-        if (lane == 0) issue(t + STAGES * tile_stride, stage);
+        if (lane == 0) {
+            const uint32_t nt = atomicAdd(p.chunk_counter, 1u);
+            s_claim[stage] = nt;
+            issue(nt, stage);
+        }
 
         // ------------------------------------------------------------ clustered lights
         const uint32_t* const my_list = p.cluster_indices + my_base;
@@ -504,7 +518,7 @@ int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
     if (n_px == 0) return TR_OK;
     const uint32_t n_tiles = (n_px + TILE - 1) / TILE;   // CTAs worth of 32-pixel runs
     const uint32_t n_smem_lights = p.n_lights <= (uint32_t)MAX_SMEM_LIGHTS ? p.n_lights : 0u;
-    const size_t smem = 256 + (size_t)WARPS * STAGES * L::kBytes + (size_t)n_smem_lights * sizeof(LightS);
+    const size_t smem = 512 + (size_t)WARPS * STAGES * L::kBytes + (size_t)n_smem_lights * sizeof(LightS);
     auto kern = shade_kernel<TRANS, HAS_POS, F32OUT, TEX, kShadow>;
     TR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -512,6 +526,7 @@ int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
     if (per_sm < 1) return tr::fail(TR_ERR_CUDA, "shade kernel does not fit on an SM (smem %zu)", smem);
     uint32_t grid = (uint32_t)(sm_count * per_sm);
     if (grid > n_tiles) grid = n_tiles;
+    TR_CUDA(cudaMemsetAsync(p.chunk_counter, 0, sizeof(uint32_t), s));
     kern<<<grid, TILE, smem, s>>>(p);
     tr::count_launches(1);
     TR_CUDA(cudaGetLastError());

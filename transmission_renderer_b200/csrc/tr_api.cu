@@ -265,6 +265,8 @@ static int32_t fill_shade(tr_ctx* c, const tr_push_constants* pc, int layer, Sha
     s->hdr_f32 = (c->flags & TR_FLAG_HDR_F32_DEBUG) ? c->hdr_f32.as<float4>() : nullptr;
     s->pyramid = pyramid_desc(c);
     s->lut = lut_desc(c);
+    TR_TRY(c->shade_counter.ensure(256));
+    s->chunk_counter = c->shade_counter.as<uint32_t>();
     if (pc->acceleration_structure_address != 0) {
         const size_t plane = (size_t)c->width * c->height;
         TR_TRY(c->shadow_mask[layer].ensure(plane * 5 * 4));
@@ -355,7 +357,7 @@ int32_t tr_destroy(tr_ctx* c) {
                       &c->mesh_uv, &c->mesh_idx, &c->visible_ids, &c->cull_scalars, &c->draws[0], &c->draws[1],
                       &c->draws[2], &c->draws[3], &c->work_prefix, &c->slot_z, &c->cluster_aabbs, &c->cluster_counts,
                       &c->cluster_indices, &c->vis[0], &c->vis[1], &c->bin_entries, &c->bin_state, &c->tri_records, &c->dev_status, &c->band_list, &c->hdr, &c->hdr_f32, &c->pyramid,
-                      &c->srgb8, &c->mip_counter, &c->accel_tlas, &c->accel_blas, &c->accel_inst, &c->accel_tris,
+                      &c->srgb8, &c->mip_counter, &c->shade_counter, &c->accel_tlas, &c->accel_blas, &c->accel_inst, &c->accel_tris,
                       &c->shadow_mask[0], &c->shadow_mask[1]};
     for (DevBuf* b : bufs) b->release();
     for (DevBuf& b : c->tex_data) b.release();

@@ -92,7 +92,7 @@ struct tr_ctx {
     // frame targets
     tr::GLayer layer[2];
     tr::DevBuf vis[2], bin_entries, bin_state, tri_records, dev_status, band_list;  // sort-middle rasteriser state (k_visibility.cu)
-    tr::DevBuf hdr, hdr_f32, pyramid, srgb8, mip_counter;
+    tr::DevBuf hdr, hdr_f32, pyramid, srgb8, mip_counter, shade_counter;
     uint32_t levels = 0, level_w[tr::kMaxLevels] = {}, level_h[tr::kMaxLevels] = {}, level_off[tr::kMaxLevels] = {};
     bool opaque_valid = false, mips_valid = false, hdr_valid = false, srgb_valid = false;
 
@@ -158,6 +158,7 @@ struct ShadeLaunch {
     trd::LutDesc lut;
     // ray-queried shadows: occluded-ray bits per pixel, written by the shadow pass and read by the shading kernel.
     // Five planes of `shadow_plane` words: 0-3 = position in the cluster's light list, 4 = the sun.  nullptr: no ray queries.
+    uint32_t* chunk_counter;  // work counter of the shading kernels (zeroed before every launch)
     uint32_t* shadow_mask;
     uint32_t shadow_plane;
     trd::AccelDesc accel;
