@@ -66,6 +66,7 @@ struct VisParams {
     uint32_t rec_capacity;
     uint32_t* rec_count;
     uint32_t* tile_ticket;
+    uint32_t* tile_order;         // [2 * n_tiles] (layer, tile) jobs, heaviest first (tile_order_kernel)
     uint32_t* status;             // bit 0: record overflow, bit 1: bin overflow
     unsigned long long* stats;    // diagnostics: [0] box pixels binned, [1] box pixels after hierarchical Z, [2] exact evaluations
     // resolve outputs
@@ -541,6 +542,31 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
     }
 }
 
+// ---- between A2 and B: the order in which the tile jobs are handed out.  The tile kernel's CTAs take jobs from a ticket
+// counter; a heavy tile taken late is the tail of the kernel, so the jobs are sorted by their triangle count, heaviest first
+// (counting sort on the bit length of the count — longest-processing-time-first needs no finer order), empty tiles last.
+__global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant__ VisParams p) {
+    __shared__ uint32_t s_hist[33], s_base[33];
+    const uint32_t tid = threadIdx.x, n = 2u * p.n_tiles;
+    if (tid < 33) s_hist[tid] = 0;
+    __syncthreads();
+    auto bucket = [&](uint32_t item) {
+        const uint32_t begin = min(p.bin_start[item * DEPTH_BUCKETS], p.bin_capacity), end = min(p.bin_start[(item + 1) * DEPTH_BUCKETS], p.bin_capacity);
+        return 32u - (uint32_t)__clz(end - begin);   // 0 for an empty tile
+    };
+    for (uint32_t i = tid; i < n; i += 1024) atomicAdd(&s_hist[bucket(i)], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int b = 32; b >= 0; b--) {
+            s_base[b] = acc;
+            acc += s_hist[b];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += 1024) p.tile_order[atomicAdd(&s_base[bucket(i)], 1u)] = i;
+}
+
 // ---- pass A3: scatter the surviving triangles into their bin lists
 __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_fill_kernel(const __grid_constant__ VisParams p) {
     const uint32_t n = min(*p.rec_count, p.rec_capacity);
@@ -685,8 +711,8 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
         for (uint32_t i = tid; i < TS * TS; i += TILE_THREADS) keys[i] = 0ull;
         if (tid < (TS / 8) * (TS / 8)) R.zmin_blk[tid] = 0.0f;
         __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= 2u * p.n_tiles) break;
+        if (s_item >= 2u * p.n_tiles) break;
+        const uint32_t item = p.tile_order[s_item];
         const uint32_t layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
         const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         const int tile_x0 = (int)tx * TS, tile_y0 = (int)(ty + p.tile_row0) * TS;
@@ -1110,7 +1136,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     const size_t n_lists = (size_t)2 * p.n_tiles * DEPTH_BUCKETS;
     p.n_lists = (uint32_t)n_lists;
     const size_t zero_bytes = (n_lists + 4 + 32) * 4;  // bin_count, rec_count/ticket, scan totals
-    TR_TRY(c->bin_state.ensure(zero_bytes + (2 * n_lists + 4) * 4));
+    TR_TRY(c->bin_state.ensure(zero_bytes + (2 * n_lists + 4) * 4 + (size_t)2 * p.n_tiles * 4));
     if (!c->dev_status.p) {
         TR_TRY(c->dev_status.ensure(64));
         TR_CUDA(cudaMemsetAsync(c->dev_status.p, 0, 64, c->stream));
@@ -1123,6 +1149,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.scan_totals = st + n_lists + 4;
     p.bin_start = st + n_lists + 4 + 32;
     p.bin_cursor = p.bin_start + n_lists + 4;  // keeps 16-byte alignment (n_lists is a multiple of 16)
+    p.tile_order = p.bin_cursor + n_lists;
     p.bin_entries = c->bin_entries.as<uint2>();
     p.records = c->tri_records.as<uint4>();
     p.status = c->dev_status.as<uint32_t>();
@@ -1198,11 +1225,12 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     bin_count_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     bin_scan_kernel<<<SCAN_CTAS, 1024, 0, c->stream>>>(p);
     bin_fill_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
+    tile_order_kernel<<<1, 1024, 0, c->stream>>>(p);
     tile_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
     const dim3 res_grid((c->width + RES_W - 1) / RES_W, (c->band_y1 - c->band_y0 + RES_H - 1) / RES_H, 1);
     if (c->materials_textured) resolve_kernel<true><<<res_grid, RES_W * RES_H, 0, c->stream>>>(p);
     else resolve_kernel<false><<<res_grid, RES_W * RES_H, 0, c->stream>>>(p);
-    count_launches(5 + extra_launch);
+    count_launches(6 + extra_launch);
     TR_CUDA(cudaGetLastError());
     for (int l = 0; l < 2; l++) {
         c->layer[l].valid = true;
