@@ -25,7 +25,7 @@ using namespace trd;
 
 namespace {
 
-constexpr int TS_MAX = 64;           // tile edge in pixels: 64, or 32 when a small band would give too few tiles to fill the GPU
+// tile edge in pixels: 64, or 32 when a small band would give too few tiles to fill the GPU (launch_visibility)
 constexpr int TILE_THREADS = 256;    // 8 warps per tile CTA
 constexpr uint32_t BIN_CAPACITY = 1u << 24;  // (triangle, tile) pairs per frame
 constexpr int DEPTH_BUCKETS = 16;    // bin lists per (layer, tile), nearest instances first
