@@ -226,13 +226,44 @@ def test_interleaved_views_short_indices_and_data_uris(tmp_path):
     assert m["mesh"]["indices"].dtype == np.uint32 and np.array_equal(m["mesh"]["indices"], idx)
     np.testing.assert_allclose(m["mesh"]["uvs"], np.clip(uv, 0, 1), atol=1.0 / 65535)
     assert len(m["materials"]) == 1 and m["materials"]["index_of_refraction"][0] == 1.5        # the default material
-    # sparse accessors are refused, not misread
-    doc["accessors"][0]["sparse"] = dict(count=1, indices=dict(bufferView=2, componentType=5123), values=dict(bufferView=0))
-    p.write_text(json.dumps(doc))
+    # a sparse accessor (glTF 3.6.2.3; the gltf crate's iterators resolve it): two positions replaced on top of the base view
+    repl = np.array([[5.0, 6.0, 7.0], [-1.0, -2.0, -3.0]], f32)
+    extra = np.array([1, 3], np.uint16).tobytes() + repl.tobytes()
+    blob2 = blob + extra
+    doc2 = json.loads(json.dumps(doc))
+    doc2["buffers"][0] = dict(byteLength=len(blob2), uri="data:application/octet-stream;base64," + base64.b64encode(blob2).decode())
+    doc2["bufferViews"] += [dict(buffer=0, byteOffset=len(blob), byteLength=4), dict(buffer=0, byteOffset=len(blob) + 4, byteLength=24)]
+    doc2["accessors"][0]["sparse"] = dict(count=2, indices=dict(bufferView=3, componentType=5123), values=dict(bufferView=4))
+    doc2["accessors"][0]["min"], doc2["accessors"][0]["max"] = [-1.0, -2.0, -3.0], [5.0, 6.0, 7.0]
+    p.write_text(json.dumps(doc2))
+    sp = gltf_ingest.finish(gltf_ingest.load_gltf(str(p)))
+    want = pos.astype(f32).copy()
+    want[[1, 3]] = repl
+    assert sp["mesh"]["positions"].tobytes() == want.tobytes()
+    # ... and one without a base view starts from zeros
+    del doc2["accessors"][1]["bufferView"]
+    doc2["accessors"][1].pop("byteOffset", None)
+    doc2["accessors"][1]["sparse"] = dict(count=2, indices=dict(bufferView=3, componentType=5123), values=dict(bufferView=4))
+    p.write_text(json.dumps(doc2))
+    sp = gltf_ingest.finish(gltf_ingest.load_gltf(str(p)))
+    want_n = np.zeros_like(nrm, f32)
+    want_n[[1, 3]] = repl
+    assert sp["mesh"]["normals"].tobytes() == want_n.tobytes()
+    # sparse indices out of range are refused, not misread
+    blob3 = blob2 + np.array([3, 1], np.uint16).tobytes()                                    # not increasing
+    doc2["buffers"][0] = dict(byteLength=len(blob3), uri="data:application/octet-stream;base64," + base64.b64encode(blob3).decode())
+    doc2["bufferViews"].append(dict(buffer=0, byteOffset=len(blob2), byteLength=4))
+    doc2["accessors"][0]["sparse"]["indices"] = dict(bufferView=5, componentType=5123)
+    p.write_text(json.dumps(doc2))
+    with pytest.raises(ValueError):
+        gltf_ingest.load_gltf(str(p))
+    # a primitive without indices is what the reference's loader panics on (model_loading.rs:100)
+    doc3 = json.loads(json.dumps(doc))
+    del doc3["meshes"][0]["primitives"][0]["indices"]
+    p.write_text(json.dumps(doc3))
     with pytest.raises(ValueError):
         gltf_ingest.load_gltf(str(p))
     # and so is a node with non-uniform scale (model_loading.rs:449-458)
-    del doc["accessors"][0]["sparse"]
     doc["nodes"][0]["scale"] = [1.0, 2.0, 1.0]
     p.write_text(json.dumps(doc))
     with pytest.raises(ValueError):

@@ -118,18 +118,34 @@ class _Buffers:
 
     def read(self, accessor_index):
         a = self.doc["accessors"][accessor_index]
-        if "sparse" in a or "bufferView" not in a:
-            raise ValueError(f"accessor {accessor_index}: sparse / view-less accessors are not supported")
         dt, width, count = np.dtype(_COMPONENT[a["componentType"]]), _WIDTH[a["type"]], a["count"]
-        data, stride = self.view_bytes(a["bufferView"])
-        off = a.get("byteOffset", 0)
         elem = dt.itemsize * width
-        if stride in (None, 0, elem):
-            out = np.frombuffer(data, dtype=dt, count=count * width, offset=off).reshape(count, width)
-        else:
+
+        def dense(view_index, byte_offset, n, dtype, w):
+            data, stride = self.view_bytes(view_index)
+            e = dtype.itemsize * w
+            if stride in (None, 0, e):
+                return np.frombuffer(data, dtype=dtype, count=n * w, offset=byte_offset).reshape(n, w)
             raw = np.frombuffer(data, dtype=np.uint8)
-            idx = off + np.arange(count)[:, None] * stride + np.arange(elem)[None, :]
-            out = raw[idx].view(dt).reshape(count, width)
+            idx = byte_offset + np.arange(n)[:, None] * stride + np.arange(e)[None, :]
+            return raw[idx].view(dtype).reshape(n, w)
+
+        # the gltf crate's accessor iterators (what model_loading.rs reads through) resolve sparse accessors: zeros or the
+        # base view, then `count` elements replaced at the given indices (glTF 2.0, 5.1.4 / 3.6.2.3)
+        if "bufferView" in a:
+            out = dense(a["bufferView"], a.get("byteOffset", 0), count, dt, width)
+        else:
+            out = np.zeros((count, width), dt)
+        if "sparse" in a:
+            sp = a["sparse"]
+            n = sp["count"]
+            si, sv = sp["indices"], sp["values"]
+            where = dense(si["bufferView"], si.get("byteOffset", 0), n, np.dtype(_COMPONENT[si["componentType"]]), 1).reshape(-1).astype(np.int64)
+            if n and (where.max() >= count or (np.diff(where) <= 0).any()):
+                raise ValueError(f"accessor {accessor_index}: sparse indices must be strictly increasing and below {count}")
+            vals = dense(sv["bufferView"], sv.get("byteOffset", 0), n, dt, width)
+            out = np.array(out, copy=True)
+            out[where] = vals
         if a.get("normalized") and dt.kind in "iu":
             out = out.astype(np.float32) / float(np.iinfo(dt).max)
             if dt.kind == "i":
@@ -194,6 +210,10 @@ def load_gltf(path, base_transform=None, roughness_override=None, into=None):
             uv_scale = np.asarray(tinfo.get("extensions", {}).get("KHR_texture_transform", {}).get("scale", (1, 1)), f32)
             material_id = prim.get("material", 0) + n_existing_materials
             attrs = prim["attributes"]
+            if "indices" not in prim:   # `reader.read_indices().unwrap()`, model_loading.rs:100: the reference panics here
+                raise ValueError(f"node {node_index}: primitive without indices (the reference's loader requires indexed primitives)")
+            if prim.get("mode", 4) != 4:
+                raise ValueError(f"node {node_index}: primitive mode {prim.get('mode')} (only triangle lists are drawn)")
             idx = bufs.read(prim["indices"]).reshape(-1).astype(np.uint32)
             pos = bufs.read(attrs["POSITION"]).astype(f32)
             nrm = bufs.read(attrs["NORMAL"]).astype(f32)
