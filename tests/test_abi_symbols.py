@@ -49,3 +49,19 @@ def test_product_does_not_import_the_oracle():
                     code = "\n".join(l.split("//")[0].split("#")[0] if not l.lstrip().startswith("#include") else l
                                      for l in text.splitlines())
                     assert b not in code, (f, b)
+
+
+def test_plain_c_host_compiles_and_fails_loudly_without_a_device(tmp_path):
+    """examples/frame.c is a C11 host of the ABI: the header compiles as C, the library links, and without a CUDA device
+    the first call fails with a message instead of falling back to anything."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(root, "transmission_renderer_b200")
+    exe = str(tmp_path / "frame")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "frame.c"),
+                           "-L", libdir, "-ltr", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe])
+    p = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), timeout=120)
+    assert p.returncode == 3 and "tr_create" in p.stderr and "no CPU path" in p.stderr
