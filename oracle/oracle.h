@@ -181,6 +181,13 @@ void orc_shade_opaque_frame(const orc_gbuffer* g, const orc_scene* s, uint32_t y
                             uint16_t* hdr_f16, uint16_t* opaque_f16);
 void orc_shade_transmission_frame(const orc_gbuffer* g, const orc_scene* s, const orc_pyramid* fb, const orc_lut* lut,
                                   uint32_t y0, uint32_t y1, float* hdr_f32, uint16_t* hdr_f16);
+/* The same frame loop with the per-fragment function supplied by the caller (oracle/spv_harness.c runs the reference's
+ * shipped SPIR-V through it): identical G-buffer decode, derivative decode and stores. transmissive = 0: `fragment`
+ * semantics (clear + two targets), 1: `fragment_transmission` semantics (LOAD, covered pixels only). */
+typedef v4 (*orc_fragment_fn)(v3 position, v3 normal, v2 uv, uint32_t material_id, float model_scale, v4 frag_coord,
+                              const orc_frag_derivatives* d, void* user);
+void orc_shade_frame_with(const orc_gbuffer* g, const tr_push_constants* pc, int transmissive, uint32_t y0, uint32_t y1,
+                          orc_fragment_fn fn, void* user, float* hdr_f32, uint16_t* hdr_f16, uint16_t* opaque_f16);
 /* occluded-ray bits of a layer: [5][h*w], planes 0-3 = cluster-list position, plane 4 bit 0 = sun */
 void orc_shadow_mask_frame(const orc_gbuffer* g, const orc_scene* s, uint32_t y0, uint32_t y1, uint32_t* mask);
 
@@ -212,6 +219,11 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
                     float* duv0, float* ddepth0, float* duv1, float* ddepth1 /* derivative planes, any may be NULL */,
                     const tr_material_info* materials /* NULL: no alpha clipping */, const orc_texture* textures,
                     uint32_t n_textures);
+
+void orc_vertex_instanced_with_scale(v3 position, v3 normal, const tr_instance* instance, const tr_push_constants* pc,
+                                     v4* clip, v3* out_position, v3* out_normal, uint32_t* out_material_id, float* out_scale);
+int orc_alpha_clip_kills(const tr_material_info* m, const orc_texture* textures, uint32_t n_textures, v2 uv, v2 duv_dx,
+                         v2 duv_dy);
 
 int orc_num_threads(void);
 void orc_set_num_threads(int n);

@@ -499,3 +499,51 @@ class ShadePathRunner:
     def tonemap(self, y0, y1):
         lib().orc_tonemap_frame(_p(self.hdr16), C.c_uint32(self.w), C.c_uint32(self.h), C.c_uint32(y0), C.c_uint32(y1),
                                 _p(self._tm), _p(self.srgb8))
+
+
+# ---- vertex stage / alpha clip, exposed for the comparison with the reference's shipped modules --------------------
+class _V2(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float)]
+
+
+class _V3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class _V4(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("w", C.c_float)]
+
+
+def vertex_instanced_with_scale(positions, normals, uvs, instance_index, instances, push_constants):
+    positions, normals = _c(positions, np.float32).reshape(-1, 3), _c(normals, np.float32).reshape(-1, 3)
+    instances = _c(instances, abi.instance)
+    pc = _c(push_constants, abi.push_constants)
+    n = len(positions)
+    out = dict(clip=np.zeros((n, 4), np.float32), position=np.zeros((n, 3), np.float32), normal=np.zeros((n, 3), np.float32),
+               uv=_c(uvs, np.float32).reshape(-1, 2).copy(), material_id=np.zeros(n, np.uint32), scale=np.zeros(n, np.float32))
+    L = lib()
+    L.orc_vertex_instanced_with_scale.argtypes = [_V3, _V3, C.c_void_p, C.c_void_p] + [C.c_void_p] * 5
+    L.orc_vertex_instanced_with_scale.restype = None
+    isz = abi.instance.itemsize
+    for i in range(n):
+        L.orc_vertex_instanced_with_scale(_V3(*positions[i]), _V3(*normals[i]), instances.ctypes.data + isz * int(instance_index[i]),
+                                          pc.ctypes.data, out["clip"].ctypes.data + 16 * i, out["position"].ctypes.data + 12 * i,
+                                          out["normal"].ctypes.data + 12 * i, out["material_id"].ctypes.data + 4 * i,
+                                          out["scale"].ctypes.data + 4 * i)
+    return out
+
+
+def alpha_clip(uvs, duv, material_id, scene):
+    """depth_pre_pass_alpha_clip per fragment: 1 = discarded."""
+    uvs = _c(uvs, np.float32).reshape(-1, 2)
+    duv = _c(duv, np.float32).reshape(-1, 4) if duv is not None else np.zeros((len(uvs), 4), np.float32)
+    s, ks = _scene_struct(scene)
+    L = lib()
+    L.orc_alpha_clip_kills.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, _V2, _V2, _V2]
+    L.orc_alpha_clip_kills.restype = C.c_int
+    msz = abi.material_info.itemsize
+    out = np.zeros(len(uvs), np.uint8)
+    for i in range(len(uvs)):
+        out[i] = L.orc_alpha_clip_kills(ks.m.ctypes.data + msz * int(material_id[i]), s.textures, s.n_textures, _V2(*uvs[i]),
+                                        _V2(*duv[i, :2]), _V2(*duv[i, 2:]))
+    return out

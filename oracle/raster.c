@@ -34,6 +34,34 @@ static v3 sim_mul(const tr_packed_similarity* t, v3 p) {
     return v3_add(translation, v3_scale(quat_mul_v3(rot, p), t->translation_and_scale.w));
 }
 
+/* vertex_instanced_with_scale, shader/src/lib.rs:364-391 (vertex_instanced :336-362 is the same without the scale) */
+void orc_vertex_instanced_with_scale(v3 position, v3 normal, const tr_instance* instance, const tr_push_constants* pc,
+                                     v4* clip, v3* out_position, v3* out_normal, uint32_t* out_material_id, float* out_scale) {
+    m4 pv;
+    memcpy(&pv, &pc->proj_view, sizeof pv);
+    v3 wp = sim_mul(&instance->transform, position);
+    v4 rot = v4_new(instance->transform.rotation.x, instance->transform.rotation.y, instance->transform.rotation.z,
+                    instance->transform.rotation.w);
+    *out_position = wp;
+    *out_normal = quat_mul_v3(rot, normal);
+    *out_material_id = instance->material_id;
+    *out_scale = instance->transform.translation_and_scale.w;
+    *clip = m4_mul_v4(&pv, v4_new(wp.x, wp.y, wp.z, 1.0f));
+}
+
+/* depth_pre_pass_alpha_clip, shader/src/lib.rs:269-293: 1 = the fragment is discarded */
+int orc_alpha_clip_kills(const tr_material_info* m, const orc_texture* textures, uint32_t n_textures, v2 uv, v2 duv_dx,
+                         v2 duv_dy) {
+    float alpha = m->diffuse_factor.w;
+    if (m->textures.diffuse != -1) {
+        float a = 0.0f;
+        if (textures && (uint32_t)m->textures.diffuse < n_textures)
+            a = orc_sample_texture(&textures[m->textures.diffuse], uv, duv_dx, duv_dy).w;
+        alpha *= a;
+    }
+    return alpha < m->alpha_clipping_cutoff;
+}
+
 /* returns 0 if the triangle is culled / off-band */
 static int setup_triangle(const orc_mesh* mesh, const tr_instance* inst, const tr_primitive_info* prim, uint32_t tri,
                           const m4* pv, uint32_t width, uint32_t height, uint32_t y0, uint32_t y1, tri_setup* s) {
@@ -226,7 +254,6 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
                         if (!eval_pixel(&s, px, py, l, &d)) continue;
                         if (alpha_clip && materials) { /* depth_pre_pass_alpha_clip, shader/src/lib.rs:269-293 */
                             const tr_material_info* m = &materials[inst[ii].material_id];
-                            float alpha = m->diffuse_factor.w;
                             if (m->textures.diffuse != -1) {
                                 const float *u0 = &mesh->uvs[s.vid[0] * 2], *u1 = &mesh->uvs[s.vid[1] * 2], *u2 = &mesh->uvs[s.vid[2] * 2];
                                 v2 uv = {(l[0] * u0[0] + l[1] * u1[0]) + l[2] * u2[0], (l[0] * u0[1] + l[1] * u1[1]) + l[2] * u2[1]};
@@ -238,12 +265,11 @@ void orc_visibility(const orc_mesh* mesh, const tr_instance* inst, uint32_t n_in
                                         dq[k].y = ((ln[0] * u0[1] + ln[1] * u1[1]) + ln[2] * u2[1]) - uv.y;
                                     }
                                 }
-                                float a = 0.0f;
-                                if (textures && (uint32_t)m->textures.diffuse < n_textures)
-                                    a = orc_sample_texture(&textures[m->textures.diffuse], uv, dq[0], dq[1]).w;
-                                alpha *= a;
+                                if (orc_alpha_clip_kills(m, textures, n_textures, uv, dq[0], dq[1])) continue;
+                            } else {
+                                v2 zero = {0.0f, 0.0f};
+                                if (orc_alpha_clip_kills(m, textures, n_textures, zero, zero, zero)) continue;
                             }
-                            if (alpha < m->alpha_clipping_cutoff) continue; /* kill */
                         }
                         size_t i = (size_t)py * width + px;
                         if (layer == 1) { /* GREATER against the opaque depth already in the shared depth buffer */

@@ -538,6 +538,34 @@ void orc_shade_transmission_frame(const orc_gbuffer* g, const orc_scene* s, cons
     }
 }
 
+void orc_shade_frame_with(const orc_gbuffer* g, const tr_push_constants* pc, int transmissive, uint32_t y0, uint32_t y1,
+                          orc_fragment_fn fn, void* user, float* hdr_f32, uint16_t* hdr_f16, uint16_t* opaque_f16) {
+    tr_mat4 inv;
+    orc_mat4_inverse(&pc->proj_view, &inv);
+    m4 inv_pv;
+    memcpy(&inv_pv, &inv, sizeof(m4));
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t yy = (int64_t)y0; yy < (int64_t)y1; yy++) {
+        uint32_t y = (uint32_t)yy;
+        for (uint32_t x = 0; x < g->width; x++) {
+            size_t i = (size_t)y * g->width + x;
+            float depth = g->depth[i];
+            v4 c = v4_new(0.0f, 0.0f, 0.0f, 1.0f);
+            if (depth == 0.0f && transmissive) continue;
+            if (depth != 0.0f) {
+                v3 pos = decode_position(g, &inv_pv, x, y, depth);
+                v3 n = v3_new(g->normal[i * 3], g->normal[i * 3 + 1], g->normal[i * 3 + 2]);
+                v2 uv = {g->uv ? g->uv[i * 2] : 0.0f, g->uv ? g->uv[i * 2 + 1] : 0.0f};
+                v4 fc = v4_new((float)x + 0.5f, (float)y + 0.5f, depth, 1.0f);
+                float scale = g->scale ? g->scale[i] : 1.0f;
+                orc_frag_derivatives d = decode_derivatives(g, &inv_pv, x, y, depth, pos);
+                c = fn(pos, n, uv, g->material_id[i], scale, fc, &d, user);
+            }
+            store_px(hdr_f32, hdr_f16, transmissive ? NULL : opaque_f16, i, c);
+        }
+    }
+}
+
 /* Which shadow rays of a layer are occluded, as the product's shadow pass stores them: plane 0..3 = bit i set when the
  * ray towards the i-th light of the pixel's cluster list is occluded, plane 4 bit 0 = the sun ray.  mask: [5][h*w]. */
 void orc_shadow_mask_frame(const orc_gbuffer* g, const orc_scene* s, uint32_t y0, uint32_t y1, uint32_t* mask) {

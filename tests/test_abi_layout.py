@@ -55,3 +55,85 @@ def test_default_material_matches_loader_defaults():
     assert np.isinf(m["attenuation_distance"][0])               # model_loading.rs:318
     assert m["alpha_clipping_cutoff"][0] == np.float32(0.5)     # model_loading.rs:295
     assert (m["textures"] == -1).all()
+
+
+# ---- against the layouts the reference's own compiled shaders declare -----------------------------------------------
+# tests/golden/spv_layouts.json = OpMemberDecorate Offset / OpDecorate ArrayStride of every buffer and push-constant
+# block in /root/reference/compiled-shaders/normal/*.spv (tests/golden/make_spv_layouts.py).  (module, set, binding) ->
+# the struct of include/tr_abi.h bound there (shader/src/lib.rs entry-point signatures); None = push constants.
+SPV_BINDINGS = {
+    ("frustum_culling", 0, 0): "primitive_info", ("frustum_culling", 1, 0): "instance",
+    ("frustum_culling", None, None): "culling_push_constants",
+    ("demultiplex_draws", 0, 0): "primitive_info", ("demultiplex_draws", 0, 3): "draw_indexed_indirect_command",
+    ("demultiplex_draws", 0, 4): "draw_indexed_indirect_command", ("demultiplex_draws", 0, 5): "draw_indexed_indirect_command",
+    ("demultiplex_draws", 0, 6): "draw_indexed_indirect_command",
+    ("write_cluster_data", 0, 3): "uniforms", ("write_cluster_data", 1, 0): "cluster_aabb",
+    ("write_cluster_data", None, None): "write_cluster_data_push_constants",
+    ("assign_lights_to_clusters", 0, 0): "light", ("assign_lights_to_clusters", 1, 0): "cluster_aabb",
+    ("assign_lights_to_clusters", None, None): "assign_lights_push_constants",
+    ("fragment", 0, 2): "material_info", ("fragment", 0, 3): "uniforms", ("fragment", 2, 0): "light",
+    ("fragment", None, None): "push_constants",
+    ("fragment_transmission", 0, 2): "material_info", ("fragment_transmission", 0, 3): "uniforms",
+    ("fragment_transmission", 2, 0): "light", ("fragment_transmission", None, None): "push_constants",
+    ("fragment_tonemap", None, None): "baked_lottes_tonemapper_params",
+    ("vertex_instanced", 1, 0): "instance", ("vertex_instanced", None, None): "push_constants",
+    ("vertex_instanced_with_scale", 1, 0): "instance", ("vertex_instanced_with_scale", None, None): "push_constants",
+    ("depth_pre_pass_instanced", 1, 0): "instance", ("depth_pre_pass_alpha_clip", 0, 2): "material_info",
+}
+
+
+def _spv_leaves(t, base=0):
+    """[(offset, kind)] of every 32-bit scalar a SPIR-V type description lays out."""
+    if isinstance(t, str):
+        kind, _, n = t.partition("x")
+        return [(base + 4 * k, kind[0]) for k in range(int(n) if n else 1)]
+    if "struct" in t:
+        out = []
+        for m in t["struct"]:
+            out += _spv_leaves(m["type"], base + m["offset"])
+        return out
+    if "array" in t:
+        out = []
+        for k in range(t["len"]):
+            out += _spv_leaves(t["array"], base + k * t["stride"])
+        return out
+    raise AssertionError(t)
+
+
+def _np_leaves(dt, base=0):
+    """{offset of each 4-byte word: kind} of a numpy struct dtype (u8 covers two words)."""
+    out = {}
+    if dt.fields is None:
+        sub, shape = (dt.subdtype if dt.subdtype else (dt, ()))
+        count = int(np.prod(shape)) if shape else 1
+        for k in range(count):
+            for wd in range(sub.itemsize // 4):
+                out[base + k * sub.itemsize + wd * 4] = sub.kind
+        return out
+    for name in dt.names:
+        fdt, off = dt.fields[name][:2]
+        out.update(_np_leaves(fdt, base + off))
+    return out
+
+
+def test_layouts_match_the_shipped_spirv():
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spv = json.load(open(os.path.join(root, "tests", "golden", "spv_layouts.json")))
+    checked = 0
+    for (module, s, b), name in SPV_BINDINGS.items():
+        dt = getattr(abi, name)
+        block = next(i for i in spv[module]["interface"] if i["set"] == s and i["binding"] == b)["type"]
+        inner = block["struct"][0]["type"]           # rust-gpu wraps every binding in a one-member Block struct
+        if isinstance(inner, dict) and "rtarray" in inner:
+            assert inner["stride"] == dt.itemsize, (module, name, "ArrayStride")
+            inner = inner["rtarray"]
+        have = _np_leaves(dt)
+        kinds = {"f": "f", "u": "u", "i": "i"}
+        for off, kind in _spv_leaves(inner):
+            assert off in have, (module, name, off)
+            assert have[off] == kinds[kind], (module, name, off, kind, have[off])
+            checked += 1
+        assert max(o for o, _ in _spv_leaves(inner)) + 4 <= dt.itemsize
+    assert checked > 300
