@@ -272,7 +272,30 @@ typedef struct {
     tr_vec3 attenuation_colour;
 } tr_ibl_volume_refraction_params;
 
+/* One iteration of the clustered-light loops for a point light — shader/src/lighting.rs:179-216 (`evaluate_lights`) and
+ * :58-92 (`evaluate_lights_transmission`): light_direction_and_attenuation(position, light_position) (glam-pbr
+ * lib.rs:12-23), then basic_brdf(normal, direction, colour * attenuation, view, material) and
+ * transmission_btdf(material, normal, view, direction) * colour * attenuation.  `normal` and `view` are unit vectors
+ * (the shaders normalise them before the loop).  tr_eval_point_light runs the SAME device code as the frame kernels'
+ * light loop (fast regime + adaptive exactness), so the hot loop has a per-element contract test of its own. */
+typedef struct {
+    tr_vec3 normal;
+    tr_vec3 view;
+    tr_vec3 position;       /* fragment, world space */
+    tr_vec3 light_position;
+    tr_vec3 light_colour;   /* Light::colour_emission (rgb = colour * intensity) */
+    tr_material_params material_params;
+} tr_point_light_params;
+
+typedef struct {
+    tr_vec3 diffuse;        /* BrdfResult.diffuse */
+    tr_vec3 specular;       /* BrdfResult.specular */
+    tr_vec3 transmission;   /* transmission_btdf(..) * light */
+} tr_point_light_result;
+
 TR_STATIC_ASSERT(sizeof(tr_material_params) == 40, "MaterialParams (C form)");
+TR_STATIC_ASSERT(sizeof(tr_point_light_params) == 100, "point-light loop iteration params");
+TR_STATIC_ASSERT(sizeof(tr_point_light_result) == 36, "point-light loop iteration result");
 TR_STATIC_ASSERT(sizeof(tr_basic_brdf_params) == 88, "BasicBrdfParams (C form)");
 TR_STATIC_ASSERT(sizeof(tr_transmission_btdf_params) == 76, "transmission_btdf params (C form)");
 TR_STATIC_ASSERT(sizeof(tr_ibl_volume_refraction_params) == 104, "IblVolumeRefractionParams (C form)");
@@ -442,6 +465,9 @@ TR_STATIC_ASSERT(offsetof(tr_frame_params, push_constants) == 176, "tr_frame_par
 TR_STATIC_ASSERT(offsetof(tr_frame_params, tonemap) == 272, "tr_frame_params.tonemap");
 TR_STATIC_ASSERT(offsetof(tr_frame_params, flags) == 300, "tr_frame_params.flags");
 TR_API int32_t tr_frame(tr_ctx* ctx, const tr_frame_params* params);
+/* Marks the start of a frame for the per-pass timers when the passes are called one by one instead of through tr_frame
+ * (the reference collects its per-pass timestamp queries once per frame, src/profiling.rs:101-131). */
+TR_API int32_t tr_begin_frame(tr_ctx* ctx);
 
 /* ------------------------------------------------------------------ */
 /* Parity hooks: inject / read back every intermediate                  */
@@ -486,6 +512,8 @@ TR_API int32_t tr_read_pass_totals(tr_ctx* ctx, tr_frame_times* sum, uint32_t* n
 /* ------------------------------------------------------------------ */
 TR_API int32_t tr_eval_basic_brdf(tr_ctx* ctx, uint32_t n, const tr_basic_brdf_params* params, tr_brdf_result* out);
 TR_API int32_t tr_eval_transmission_btdf(tr_ctx* ctx, uint32_t n, const tr_transmission_btdf_params* params, tr_vec3* out);
+/* the light loop of the frame kernels, one (pixel, point light) pair per element (see tr_point_light_params) */
+TR_API int32_t tr_eval_point_light(tr_ctx* ctx, uint32_t n, const tr_point_light_params* params, tr_point_light_result* out);
 /* samples the context's current opaque pyramid + LUT (Appendix E rules). */
 TR_API int32_t tr_eval_ibl_volume_refraction(tr_ctx* ctx, uint32_t n, const tr_mat4* proj_view,
                                              const tr_ibl_volume_refraction_params* params, tr_vec3* out);

@@ -80,6 +80,7 @@ v3 orc_ibl_volume_refraction(const orc_ibl_params* p, const orc_pyramid* fb, con
 /* batch forms mirroring tr_eval_* in include/tr_abi.h */
 void orc_eval_basic_brdf(uint32_t n, const tr_basic_brdf_params* p, tr_brdf_result* out);
 void orc_eval_transmission_btdf(uint32_t n, const tr_transmission_btdf_params* p, tr_vec3* out);
+void orc_eval_point_light(uint32_t n, const tr_point_light_params* p, tr_point_light_result* out);
 void orc_eval_ibl_volume_refraction(uint32_t n, const tr_mat4* proj_view, const tr_ibl_volume_refraction_params* p,
                                     const orc_pyramid* fb, const orc_lut* lut, tr_vec3* out);
 

@@ -208,6 +208,22 @@ void orc_eval_transmission_btdf(uint32_t n, const tr_transmission_btdf_params* p
                                               from_tr3(p[i].view), from_tr3(p[i].light)));
 }
 
+/* one iteration of evaluate_lights (lighting.rs:179-216) + evaluate_lights_transmission (:58-92) for a point light */
+void orc_eval_point_light(uint32_t n, const tr_point_light_params* p, tr_point_light_result* out) {
+    for (uint32_t i = 0; i < n; i++) {
+        v3 direction;
+        float distance, attenuation;
+        orc_light_direction_and_attenuation(from_tr3(p[i].position), from_tr3(p[i].light_position), &direction, &distance,
+                                            &attenuation);
+        orc_material_params m = from_tr_mat(&p[i].material_params);
+        v3 light = v3_scale(from_tr3(p[i].light_colour), attenuation);   /* light_emission = colour_emission * factor * attenuation */
+        orc_brdf_result r = orc_basic_brdf(from_tr3(p[i].normal), direction, light, from_tr3(p[i].view), m);
+        out[i].diffuse = to_tr3(r.diffuse);
+        out[i].specular = to_tr3(r.specular);
+        out[i].transmission = to_tr3(v3_mul(orc_transmission_btdf(m, from_tr3(p[i].normal), from_tr3(p[i].view), direction), light));
+    }
+}
+
 void orc_eval_ibl_volume_refraction(uint32_t n, const tr_mat4* proj_view, const tr_ibl_volume_refraction_params* p,
                                     const orc_pyramid* fb, const orc_lut* lut, tr_vec3* out) {
     for (uint32_t i = 0; i < n; i++) {

@@ -14,15 +14,25 @@ from transmission_renderer_b200 import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_VARIANT = "parity"   # "parity": -O2 -ffp-contract=off (the checker); "o3": -O3 -march=native, a timing variant only
 
 
-def build(force=False):
-    so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+def build(force=False, variant="parity"):
+    name = "liboracle.so" if variant == "parity" else "liboracle_o3.so"
+    so = os.path.join(_HERE, name)
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) and not f.startswith("spv_")]
     srcs.append(os.path.join(_HERE, "..", "include", "tr_abi.h"))
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", name])
     return so
+
+
+def select_variant(variant):
+    """Swap the library behind this module (bench.py times the -O3 -march=native build next to the parity build)."""
+    global _LIB, _VARIANT
+    if variant != _VARIANT:
+        build(variant=variant)
+        _VARIANT, _LIB = variant, None
 
 
 class Pyramid(C.Structure):
@@ -60,7 +70,7 @@ class Mesh(C.Structure):
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
+        _LIB = C.CDLL(build(variant=_VARIANT))
         _LIB.orc_log2_spec.restype = C.c_float
         _LIB.orc_log2_spec.argtypes = [C.c_float]
         _LIB.orc_linear_depth.restype = C.c_float
@@ -119,6 +129,13 @@ def eval_transmission_btdf(params):
     params = _c(params, abi.transmission_btdf_params)
     out = np.zeros((params.shape[0], 3), dtype=np.float32)
     lib().orc_eval_transmission_btdf(C.c_uint32(params.shape[0]), _p(params), _p(out))
+    return out
+
+
+def eval_point_light(params):
+    params = _c(params, abi.point_light_params)
+    out = np.zeros(params.shape[0], dtype=abi.point_light_result)
+    lib().orc_eval_point_light(C.c_uint32(params.shape[0]), _p(params), _p(out))
     return out
 
 

@@ -79,6 +79,12 @@ brdf_result = _dt([("diffuse", VEC3, 0), ("specular", VEC3, 12)], 24)
 transmission_btdf_params = _dt(
     [("material_params", material_params, 0), ("normal", VEC3, 40), ("view", VEC3, 52), ("light", VEC3, 64)], 76)
 
+point_light_params = _dt(
+    [("normal", VEC3, 0), ("view", VEC3, 12), ("position", VEC3, 24), ("light_position", VEC3, 36),
+     ("light_colour", VEC3, 48), ("material_params", material_params, 60)], 100)
+
+point_light_result = _dt([("diffuse", VEC3, 0), ("specular", VEC3, 12), ("transmission", VEC3, 24)], 36)
+
 ibl_volume_refraction_params = _dt(
     [("material_params", material_params, 0), ("framebuffer_size_x", "<u4", 40), ("normal", VEC3, 44),
      ("view", VEC3, 56), ("position", VEC3, 68), ("thickness", "<f4", 80), ("model_scale", "<f4", 84),

@@ -206,6 +206,7 @@ namespace tr {
 
 int32_t launch_cull(tr_ctx* c, const tr_culling_push_constants& pc) {
     if (!c->n_instances || !c->n_primitives) return fail(TR_ERR_STATE, "tr_cull: instances and primitives must be set");
+    TR_TRY(validate_scene(c, "tr_cull"));  // the kernel indexes prims[] and instance_counts[] by instance.primitive_id
     const uint32_t n_blocks = (c->n_instances + CULL_THREADS - 1) / CULL_THREADS;
     // state block: [ticket | pad][desc x n_blocks][instance_counts x n_prims][scalars x 8] -> one memset per frame
     const size_t desc_off = 16, counts_off = desc_off + (size_t)n_blocks * 8;

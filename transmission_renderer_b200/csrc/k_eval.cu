@@ -41,6 +41,24 @@ __global__ void eval_btdf_kernel(uint32_t n, const tr_transmission_btdf_params* 
     out[i].x = r.x; out[i].y = r.y; out[i].z = r.z;
 }
 
+// the frame kernels' light loop for one (pixel, point light) pair: make_pixel_shading -> make_loop_pixel ->
+// point_light_lean -> finish_sums, exactly the sequence of shade_kernel (k_shade.cu)
+__global__ void eval_point_light_kernel(uint32_t n, const tr_point_light_params* in, tr_point_light_result* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const MaterialParams m = ldm(in[i].material_params);
+    const PixelShading ps = make_pixel_shading(m, ld3(in[i].normal), ld3(in[i].view), true);
+    const LoopPixel lp = make_loop_pixel(ps, ld3(in[i].position));
+    LoopSums sums;
+    sums.clear();
+    point_light_lean<true>(lp, ld3(in[i].light_position), dup_colour(ld3(in[i].light_colour)), [](const f3&, float&) {}, sums);
+    f3 diff, spec, trans;
+    finish_sums(sums, ps.f0, ps.df, ps.c_diff_pi, ps.base, lp.a2, lp.at2, true, diff, spec, trans);
+    out[i].diffuse.x = diff.x; out[i].diffuse.y = diff.y; out[i].diffuse.z = diff.z;
+    out[i].specular.x = spec.x; out[i].specular.y = spec.y; out[i].specular.z = spec.z;
+    out[i].transmission.x = trans.x; out[i].transmission.y = trans.y; out[i].transmission.z = trans.z;
+}
+
 __global__ void eval_ibl_kernel(uint32_t n, const __grid_constant__ mat4 pv, const tr_ibl_volume_refraction_params* in,
                                 tr_vec3* out, const __grid_constant__ PyramidDesc pyr, const __grid_constant__ LutDesc lut) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,6 +90,13 @@ int32_t launch_eval_basic_brdf(uint32_t n, const tr_basic_brdf_params* in, tr_br
 int32_t launch_eval_transmission_btdf(uint32_t n, const tr_transmission_btdf_params* in, tr_vec3* out, cudaStream_t s) {
     if (!n) return TR_OK;
     eval_btdf_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, in, out);
+    count_launches(1);
+    TR_CUDA(cudaGetLastError());
+    return TR_OK;
+}
+int32_t launch_eval_point_light(uint32_t n, const tr_point_light_params* in, tr_point_light_result* out, cudaStream_t s) {
+    if (!n) return TR_OK;
+    eval_point_light_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, in, out);
     count_launches(1);
     TR_CUDA(cudaGetLastError());
     return TR_OK;

@@ -41,15 +41,17 @@ constexpr int TILE = 256;   // threads per CTA
 constexpr int CHUNK = 32;   // pixels per work item: one warp, one pixel per lane
 constexpr int WARPS = TILE / 32;
 constexpr int STAGES = 4;
-constexpr int MAX_SMEM_LIGHTS = 1024;
+constexpr int MAX_SMEM_LIGHTS = 768;
+constexpr int kHeaderBytes = 512 + WARPS * TR_MAX_LIGHTS_PER_CLUSTER * 4;   // barriers + claims, then one light list per warp
 
-struct LightS {  // 48 B, shared-memory form of shared_structs::Light
+struct LightS {  // 64 B, shared-memory form of shared_structs::Light: a point light is the first 40 bytes
     float px, py, pz;
-    float er, eg, eb;
-    float sx, sy, sz;
-    float cos_outer, inv_eps;
     uint32_t is_spot;
+    float er, er2, eg, eg2;        // every colour channel twice: the packed accumulators take (c, c) pairs (tr_device_pbr.cuh)
+    float eb, eb2, sx, sy;         // spotlight: direction, cos(outer angle), 1 / epsilon — only read for spotlights
+    float sz, cos_outer, inv_eps, pad;
 };
+static_assert(sizeof(LightS) == 64, "LightS layout");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -92,8 +94,9 @@ __device__ __forceinline__ LightS make_light_s(const tr_light* lights, uint32_t 
     const float4* q = reinterpret_cast<const float4*>(lights + i);
     float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
     LightS l;
+    l.pad = 0.0f;
     l.px = a.x; l.py = a.y; l.pz = a.z;
-    l.er = b.x; l.eg = b.y; l.eb = b.z;
+    l.er = l.er2 = b.x; l.eg = l.eg2 = b.y; l.eb = l.eb2 = b.z;
     l.sx = c.x; l.sy = c.y; l.sz = c.z;
     l.is_spot = c.w != 0.0f;                       // Light::is_a_spotlight, shared-structs lib.rs:125-127
     l.cos_outer = l.is_spot ? (float)cos((double)c.w) : 0.0f;
@@ -138,8 +141,9 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem) + warp * STAGES;   // this warp's STAGES barriers (bytes 0-255 for all warps)
-    unsigned char* stage_base = smem + 512 + (size_t)warp * STAGES * L::kBytes;
-    LightS* s_lights = reinterpret_cast<LightS*>(smem + 512 + (size_t)WARPS * STAGES * L::kBytes);
+    uint32_t* s_refs = reinterpret_cast<uint32_t*>(smem + 512) + warp * TR_MAX_LIGHTS_PER_CLUSTER;   // this warp's light list of the run
+    unsigned char* stage_base = smem + kHeaderBytes + (size_t)warp * STAGES * L::kBytes;
+    LightS* s_lights = reinterpret_cast<LightS*>(smem + kHeaderBytes + (size_t)WARPS * STAGES * L::kBytes);
 
     const uint32_t n_px = p.px_end - p.px_begin;
     const uint32_t n_tiles = (n_px + CHUNK - 1) / CHUNK;
@@ -220,10 +224,11 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
         const float depth = active ? s_depth[lane] : 0.0f;
         const bool covered = active && depth != 0.0f;
 
-        PixelShading ps;
+        PixelShading ps;   // TEX: kept for the epilogue; otherwise dead after the prologue (the epilogue re-derives the colour factors)
+        LoopPixel lp;
+        LoopSums sums;
+        sums.clear();
         f3 pos = mk3(0.f, 0.f, 0.f), emission = mk3(0.f, 0.f, 0.f);
-        f3 diff = mk3(0.f, 0.f, 0.f), spec = mk3(0.f, 0.f, 0.f), trans = mk3(0.f, 0.f, 0.f);
-        f3 sum_d = mk3(0.f, 0.f, 0.f), sum_t = mk3(0.f, 0.f, 0.f);  // clustered lights: sums before the per-pixel colour factors
         const tr_material_info* mat = nullptr;
         uint32_t my_count = 0, my_base = 0;
         float model_scale = 1.0f;
@@ -315,6 +320,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             mp.diffuse_colour = mk3(dfac.x, dfac.y, dfac.z);
             roughness_px = mp.perceptual_roughness;
             ps = make_pixel_shading(mp, nrm, v, TRANS);
+            lp = make_loop_pixel(ps, pos);
             if (TRANS) model_scale = s_scale[lane];
 
             const uint32_t cluster = cluster_index(fx, fy, depth, p.uniforms);
@@ -338,9 +344,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             }
             if (!SHADOW || sun_factor != 0.0f) {
                 auto exact_sun = [&]() { return sun_dir; };
-                const float nol_raw = dot3(ps.n, sun_dir), vol = dot3(ps.v, sun_dir);
-                brdf_light_fast(ps, exact_sun, nol_raw, vol, sun_int, sun_factor, sum_d, spec);
-                if (TRANS) btdf_light_fast(ps, exact_sun, nol_raw, vol, sun_int, sun_factor, sum_t);
+                light_lean<TRANS>(lp, exact_sun, dot3(lp.n, sun_dir), dot3(lp.v, sun_dir), dup_colour(sun_int), sun_factor, sums);
             }
         }
 
@@ -358,73 +362,95 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
         // the global fallback for > MAX_SMEM_LIGHTS lights costs nothing per light
         auto light_loop = [&](auto in_smem_tag) {
             constexpr bool IN_SMEM = decltype(in_smem_tag)::value;
-            auto load_light = [&](uint32_t m) {
-                LightS l;
+            // a light record by its shared-memory byte address (IN_SMEM) or its id (global fallback)
+            auto shade_light = [&](uint32_t ref) {
+                float4 q0;
+                Colour2 col;
                 if (IN_SMEM) {
-                    // explicit shared-window loads: 3 x 128 bit, address formed from a 32-bit base hoisted out of the loop
-                    const uint32_t a = lights_saddr + m * (uint32_t)sizeof(LightS);
-                    float4 q0, q1, q2;
-                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a));
-                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(a));
-                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a));
-                    l.px = q0.x; l.py = q0.y; l.pz = q0.z; l.er = q0.w;
-                    l.eg = q1.x; l.eb = q1.y; l.sx = q1.z; l.sy = q1.w;
-                    l.sz = q2.x; l.cos_outer = q2.y; l.inv_eps = q2.z; l.is_spot = __float_as_uint(q2.w);
+                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(ref));
+                    asm("ld.shared.v2.b64 {%0,%1}, [%2+16];" : "=l"(col.r), "=l"(col.g) : "r"(ref));
+                    asm("ld.shared.b64 %0, [%1+32];" : "=l"(col.b) : "r"(ref));
                 } else {
-                    l = make_light_s(p.lights, m);
+                    const float4* g4 = reinterpret_cast<const float4*>(p.lights + ref);
+                    const float4 a = __ldg(g4), b = __ldg(g4 + 1), c = __ldg(g4 + 2);
+                    q0 = make_float4(a.x, a.y, a.z, __uint_as_float(c.w != 0.0f ? 1u : 0u));
+                    col = dup_colour(mk3(b.x, b.y, b.z));
                 }
-                return l;
+                point_light_lean<TRANS>(lp, mk3(q0.x, q0.y, q0.z), col, [&](const f3& dir, float& factor) {
+                    if (!TRANS && __float_as_uint(q0.w) != 0u) {  // lighting.rs:201-203; the transmissive loop has no spotlight factor (:58-92)
+                        float sx, sy, sz, cos_outer, inv_eps;
+                        if (IN_SMEM) {
+                            asm("ld.shared.v2.f32 {%0,%1}, [%2+40];" : "=f"(sx), "=f"(sy) : "r"(ref));
+                            asm("ld.shared.v2.f32 {%0,%1}, [%2+48];" : "=f"(sz), "=f"(cos_outer) : "r"(ref));
+                            asm("ld.shared.f32 %0, [%1+56];" : "=f"(inv_eps) : "r"(ref));
+                        } else {
+                            const LightS l = make_light_s(p.lights, ref);
+                            sx = l.sx; sy = l.sy; sz = l.sz; cos_outer = l.cos_outer; inv_eps = l.inv_eps;
+                        }
+                        const float theta = -dot3(dir, mk3(sx, sy, sz));
+                        factor *= fmaxf((theta - cos_outer) * inv_eps, 0.0f);
+                    }
+                }, sums);
             };
-            auto shade_light = [&](const LightS& l) {
-                // light_direction_and_attenuation (glam-pbr lib.rs:12-23), fast regime; the exact chain is re-derived
-                // from `vec` inside the BRDF only where it matters (tr_device_pbr.cuh "adaptive exactness")
-                const f3 vec = sub3(mk3(l.px, l.py, l.pz), pos);
-                const float inv_d = frsqrt(dot3(vec, vec));
-                const f3 dir = scale3(vec, inv_d);
-                const float nol_raw = dot3(ps.n, dir), vol = dot3(ps.v, dir);
-                float factor = inv_d * inv_d;
-                if (!TRANS && l.is_spot) {  // lighting.rs:201-203; the transmissive loop has no spotlight factor (:58-92)
-                    float theta = -dot3(dir, mk3(l.sx, l.sy, l.sz));
-                    factor *= fmaxf((theta - l.cos_outer) * l.inv_eps, 0.0f);
-                }
-                auto exact_dir = [&]() { return exact_light_dir(vec); };
-                brdf_light_fast(ps, exact_dir, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_d, spec);
-                if (TRANS) btdf_light_fast(ps, exact_dir, nol_raw, vol, mk3(l.er, l.eg, l.eb), factor, sum_t);
-            };
+            auto light_ref = [&](uint32_t id) { return IN_SMEM ? lights_saddr + id * (uint32_t)sizeof(LightS) : id; };
             auto occluded_word = [&](uint32_t i) { return i < 64u ? (i < 32u ? occl0 : occl1) : (i < 96u ? occl2 : occl3); };
             // 93-96 % of the warps of the 4K workload have all their covered pixels in ONE cluster: the list is then walked
-            // with warp-uniform indices (no merge, no per-lane cursor); uncovered lanes just compute along
+            // with warp-uniform indices (no merge, no per-lane cursor); uncovered lanes just compute along.  The lanes fetch
+            // 32 list entries at once (one coalesced load) and hand them round by shuffle: one issue slot per light.
             const uint32_t key = covered ? my_base : 0xffffffffu;
             const uint32_t first = __reduce_min_sync(0xffffffffu, key);
             if (__all_sync(0xffffffffu, key == first || key == 0xffffffffu)) {
                 if (first != 0xffffffffu) {
-                    const uint32_t count = __reduce_max_sync(0xffffffffu, covered ? my_count : 0u);
+                    const uint32_t count = min(__reduce_max_sync(0xffffffffu, covered ? my_count : 0u), (uint32_t)TR_MAX_LIGHTS_PER_CLUSTER);
                     const uint32_t* list = p.cluster_indices + first;
+                    // the lanes fetch the list (coalesced) and park it in the warp's shared-memory slot as light-record references
+                    for (uint32_t k = lane; k < count; k += 32u) s_refs[k] = light_ref(__ldg(list + k));
+                    __syncwarp();
+                    // the list is walked through one shared-memory address register (index + base would be re-derived per
+                    // light), one entry ahead, so the entry -> light record -> arithmetic chain starts a light early.  One light
+                    // per trip: unrolled by two, the transmissive kernel's loop (with its exact-regime patches) no longer fits
+                    // the instruction cache (ncu: no_instruction stalls 0.2 -> 1.9 per issue).
+                    uint32_t a = smem_u32(s_refs);
+                    const uint32_t a_end = a + count * 4u;
+                    auto entry = [&]() {   // reads one entry past the list on the last trip: still this CTA's shared memory
+                        uint32_t ref;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ref) : "r"(a));
+                        return ref;
+                    };
+                    uint32_t ref = entry();
                     if (SHADOW) {
-                        for (uint32_t i = 0; i < count; i++) {
-                            const LightS l = load_light(__ldg(list + i));
-                            if (!((occluded_word(i) >> (i & 31u)) & 1u)) shade_light(l);  // an occluded light adds nothing
+                        for (uint32_t i = 0; a != a_end; i++) {
+                            a += 4u;
+                            const uint32_t nxt = entry();
+                            if (!((occluded_word(i) >> (i & 31u)) & 1u)) shade_light(ref);  // an occluded light adds nothing
+                            ref = nxt;
                         }
                     } else {
-#pragma unroll kLightUnroll
-                        for (uint32_t i = 0; i < count; i++) shade_light(load_light(__ldg(list + i)));
+#pragma unroll 1
+                        while (a != a_end) {
+                            a += 4u;
+                            const uint32_t nxt = entry();
+                            shade_light(ref);
+                            ref = nxt;
+                        }
                     }
+                    __syncwarp();
                 }
                 return;
             }
             // mixed warp: every lane walks its own cluster's list (ascending light ids) through a private cursor; the warp
             // takes the smallest pending id each turn, so all lanes stay converged and each pixel still sums in ascending id order
             uint32_t my_i = 0;
-            uint32_t next = my_count ? __ldg(my_list) : 0xffffffffu;
+            const uint32_t my_n = min(my_count, (uint32_t)TR_MAX_LIGHTS_PER_CLUSTER);
+            uint32_t next = my_n ? __ldg(my_list) : 0xffffffffu;
             while (true) {
                 const uint32_t m = __reduce_min_sync(0xffffffffu, next);
                 if (m == 0xffffffffu) break;
-                const LightS l = load_light(m);
                 if (next == m) {
                     const bool occluded = SHADOW && ((occluded_word(my_i) >> (my_i & 31u)) & 1u);
                     my_i++;
-                    const uint32_t upcoming = my_i < my_count ? __ldg(my_list + my_i) : 0xffffffffu;  // issued early: hidden behind the BRDF
-                    if (!occluded) shade_light(l);
+                    const uint32_t upcoming = my_i < my_n ? __ldg(my_list + my_i) : 0xffffffffu;  // issued early: hidden behind the BRDF
+                    if (!occluded) shade_light(light_ref(m));
                     next = upcoming;
                 }
             }
@@ -435,19 +461,26 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
         // ------------------------------------------------------------ epilogue
         float4 out = make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // clear colour, main.rs:1592-1602
         if (covered) {
-            f3 base = ps.base, c_diff_pi = ps.c_diff_pi;
+            f3 base = ps.base, c_diff_pi = ps.c_diff_pi, f0 = ps.f0, df = ps.df;
             if (!TEX) {
-                // untextured materials: re-read the few factors that are only needed after the light loop instead of
-                // keeping them in registers across it (nine registers the loop can use)
+                // untextured materials: re-derive the colour factors, which are only needed after the light loop, instead of
+                // keeping them in registers across it (registers the loop can use)
                 const float4 dfac = __ldg(reinterpret_cast<const float4*>(&mat->diffuse_factor));
                 const float4 emis = __ldg(reinterpret_cast<const float4*>(&mat->emissive_factor));
-                const float metallic = __ldg(&mat->metallic_factor);
-                base = mk3(dfac.x, dfac.y, dfac.z);
-                c_diff_pi = scale3(lerp3(base, splat3(0.0f), metallic), TR_FRAC_1_PI);
+                const float4 scol = __ldg(reinterpret_cast<const float4*>(&mat->specular_colour_factor));
+                MaterialParams mp;
+                mp.diffuse_colour = mk3(dfac.x, dfac.y, dfac.z);
+                mp.metallic = __ldg(&mat->metallic_factor);
+                mp.perceptual_roughness = 0.0f;
+                mp.index_of_refraction = __ldg(&mat->index_of_refraction);
+                mp.specular_colour = mk3(scol.x, scol.y, scol.z);
+                mp.specular_factor = __ldg(&mat->specular_factor);
+                base = mp.diffuse_colour;
+                colour_factors(mp, f0, df, c_diff_pi);
                 emission = mk3(emis.x, emis.y, emis.z);
             }
-            diff = add3(diff, mul3(sum_d, c_diff_pi));   // diffuse_brdf's c_diff / pi, once for all clustered lights
-            if (TRANS) trans = add3(trans, mul3(sum_t, base));
+            f3 diff, spec, trans;
+            finish_sums(sums, f0, df, c_diff_pi, base, lp.a2, lp.at2, TRANS, diff, spec, trans);
             if (TRANS) {
                 const float4 acol = __ldg(reinterpret_cast<const float4*>(&mat->attenuation_colour));
                 IblVolumeRefractionParams ip;
@@ -457,14 +490,14 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
                 ip.material_params.index_of_refraction = __ldg(&mat->index_of_refraction);
                 ip.material_params.specular_colour = mk3(0.f, 0.f, 0.f);
                 ip.material_params.specular_factor = 0.0f;
-                ip.normal = ps.n;
-                ip.view = ps.v;
+                ip.normal = lp.n;
+                ip.view = lp.v;
                 ip.position = pos;
                 ip.thickness = thickness_px;                                // lib.rs:120-124
                 ip.model_scale = model_scale;
                 ip.attenuation_distance = __ldg(&mat->attenuation_distance);
                 ip.attenuation_colour = mk3(acol.x, acol.y, acol.z);
-                trans = add3(trans, ibl_volume_refraction(ip, p.proj_view, p.log2_size_x, p.pyramid, p.lut, ps.f0, ps.df));
+                trans = add3(trans, ibl_volume_refraction(ip, p.proj_view, p.log2_size_x, p.pyramid, p.lut, f0, df));
                 const float tf = transmission_px;
                 f3 real_t = scale3(trans, tf);                              // lib.rs:157
                 diff = lerp3(diff, real_t, tf);                             // lib.rs:159
@@ -518,7 +551,7 @@ int32_t launch_variant(const tr::ShadeLaunch& p, int sm_count, cudaStream_t s) {
     if (n_px == 0) return TR_OK;
     const uint32_t n_tiles = (n_px + TILE - 1) / TILE;   // CTAs worth of 32-pixel runs
     const uint32_t n_smem_lights = p.n_lights <= (uint32_t)MAX_SMEM_LIGHTS ? p.n_lights : 0u;
-    const size_t smem = 512 + (size_t)WARPS * STAGES * L::kBytes + (size_t)n_smem_lights * sizeof(LightS);
+    const size_t smem = kHeaderBytes + (size_t)WARPS * STAGES * L::kBytes + (size_t)n_smem_lights * sizeof(LightS);
     auto kern = shade_kernel<TRANS, HAS_POS, F32OUT, TEX, kShadow>;
     TR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

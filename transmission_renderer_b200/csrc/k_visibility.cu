@@ -19,6 +19,8 @@
 //           next frame.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "tr_internal.h"
 
 using namespace trd;
@@ -1128,7 +1130,9 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.tiles_y = (c->band_y1 - 1) / p.ts - p.tile_row0 + 1;
     p.n_tiles = p.tiles_x * p.tiles_y;
     if (p.tiles_x > 256 || p.tiles_y > 256) return fail(TR_ERR_UNSUPPORTED, "tr_visibility: frame or band larger than 256 tiles on a side");
-    p.bin_capacity = BIN_CAPACITY;
+    // (triangle, tile) pairs: a fixed floor, more for big scenes; an overflow is still detected (status bit 1) and reported
+    // by every read-back entry point, never silently accepted
+    p.bin_capacity = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(BIN_CAPACITY, 6 * c->max_triangles + 64ull * p.n_tiles), 1ull << 27);
     p.rec_capacity = (uint32_t)(c->max_triangles ? c->max_triangles : 1);
     TR_TRY(c->bin_entries.ensure((size_t)p.bin_capacity * sizeof(uint2)));
     TR_TRY(c->tri_records.ensure((size_t)p.rec_capacity * sizeof(uint4)));

@@ -224,6 +224,7 @@ static int32_t fill_shade(tr_ctx* c, const tr_push_constants* pc, int layer, Sha
     if (!c->have_uniforms) return fail(TR_ERR_STATE, "%s: uniforms not set", who);
     if (!c->n_materials) return fail(TR_ERR_STATE, "%s: materials not set", who);
     if (!c->layer[layer].valid) return fail(TR_ERR_STATE, "%s: no G-buffer for layer %d (tr_visibility / tr_set_gbuffer)", who, layer);
+    TR_TRY(validate_scene(c, who));
     TR_TRY(ensure_cluster_lists(c, who));
     const GLayer& g = c->layer[layer];
     memset(s, 0, sizeof(*s));
@@ -274,6 +275,26 @@ static int32_t fill_shade(tr_ctx* c, const tr_push_constants* pc, int layer, Sha
         s->shadow_plane = (uint32_t)plane;
         s->accel = accel_desc(c);
     }
+    return TR_OK;
+}
+
+// The kernels index primitives[instance.primitive_id], materials[instance.material_id] and the index buffer at
+// first_index .. first_index + index_count without bounds checks of their own (neither do the reference's shaders —
+// shader/src/lib.rs:393-399 `index_unchecked`); the ids are checked here, once per upload, on the host copies.
+int32_t validate_scene(tr_ctx* c, const char* who) {
+    if (c->scene_checked) return TR_OK;
+    for (uint32_t i = 0; i < c->n_instances; i++) {
+        if (c->h_inst_prim[i] >= c->n_primitives)
+            return fail(TR_ERR_INVALID_ARG, "%s: instance %u names primitive %u of %u", who, i, c->h_inst_prim[i], c->n_primitives);
+        if (c->n_materials && c->h_inst_mat[i] >= c->n_materials)
+            return fail(TR_ERR_INVALID_ARG, "%s: instance %u names material %u of %u", who, i, c->h_inst_mat[i], c->n_materials);
+    }
+    if (c->n_indices)
+        for (uint32_t p = 0; p < c->n_primitives; p++)
+            if ((uint64_t)c->h_prim_first[p] + c->h_prim_count[p] > c->n_indices)
+                return fail(TR_ERR_INVALID_ARG, "%s: primitive %u reads indices [%u, %u + %u) of %u", who, p, c->h_prim_first[p],
+                            c->h_prim_first[p], c->h_prim_count[p], c->n_indices);
+    c->scene_checked = true;
     return TR_OK;
 }
 
@@ -397,6 +418,10 @@ int32_t tr_resize(tr_ctx* c, uint32_t width, uint32_t height) {
     c->height = height;
     c->band_y0 = 0;
     c->band_y1 = height;
+    if (c->n_ranks > 1) {  // a rank of a band-sharded frame keeps its share of the new frame
+        c->band_y0 = (uint32_t)(((uint64_t)c->rank * height) / c->n_ranks);
+        c->band_y1 = (uint32_t)(((uint64_t)(c->rank + 1) * height) / c->n_ranks);
+    }
     c->clusters_valid = false;  // main.rs:1113-1121 reruns write_cluster_data on resize
     return alloc_frame(c);
 }
@@ -436,7 +461,12 @@ int32_t tr_set_instances(tr_ctx* c, const tr_instance* instances, uint32_t n) {
     TR_TRY(upload(c, c->instances, instances, (size_t)n * sizeof(tr_instance)));
     c->n_instances = n;
     c->h_inst_prim.resize(n);
-    for (uint32_t i = 0; i < n; i++) c->h_inst_prim[i] = instances[i].primitive_id;
+    c->h_inst_mat.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        c->h_inst_prim[i] = instances[i].primitive_id;
+        c->h_inst_mat[i] = instances[i].material_id;
+    }
+    c->scene_checked = false;
     c->tri_bound_valid = false;
     c->cull_valid = false;
     c->accel_tlas_valid = false;  // src/main.rs:1263-1345: an instance write is followed by a top-level update
@@ -456,7 +486,14 @@ int32_t tr_set_primitives(tr_ctx* c, const tr_primitive_info* prims, uint32_t n)
     TR_TRY(upload(c, c->primitives, prims, (size_t)n * sizeof(tr_primitive_info)));
     c->n_primitives = n;
     c->h_prim_tris.resize(n);
-    for (uint32_t i = 0; i < n; i++) c->h_prim_tris[i] = prims[i].index_count / 3u;
+    c->h_prim_first.resize(n);
+    c->h_prim_count.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        c->h_prim_tris[i] = prims[i].index_count / 3u;
+        c->h_prim_first[i] = prims[i].first_index;
+        c->h_prim_count[i] = prims[i].index_count;
+    }
+    c->scene_checked = false;
     c->tri_bound_valid = false;
     c->cull_valid = false;
     c->accel_blas_valid = c->accel_tlas_valid = false;
@@ -478,6 +515,7 @@ int32_t tr_set_materials(tr_ctx* c, const tr_material_info* materials, uint32_t 
     c->materials_textured = textured;
     TR_TRY(upload(c, c->materials, materials, (size_t)n * sizeof(tr_material_info)));
     c->n_materials = n;
+    c->scene_checked = false;
     return TR_OK;
 }
 
@@ -511,8 +549,10 @@ int32_t tr_set_ggx_lut(tr_ctx* c, const uint8_t* rgba8, uint32_t width, uint32_t
         rg[i * 2] = rgba8[i * 4];
         rg[i * 2 + 1] = rgba8[i * 4 + 1];
     }
+    TR_CUDA(cudaStreamSynchronize(c->stream));  // a frame in flight may still sample the old table (as tr_set_texture does)
     TR_TRY(c->lut.ensure(rg.size()));
-    TR_CUDA(cudaMemcpy(c->lut.p, rg.data(), rg.size(), cudaMemcpyHostToDevice));
+    TR_CUDA(cudaMemcpyAsync(c->lut.p, rg.data(), rg.size(), cudaMemcpyHostToDevice, c->stream));
+    TR_CUDA(cudaStreamSynchronize(c->stream));  // `rg` is a local
     c->lut_w = width;
     c->lut_h = height;
     return TR_OK;
@@ -580,6 +620,7 @@ int32_t tr_set_mesh(tr_ctx* c, const float* positions, const float* normals, con
     TR_TRY(upload(c, c->mesh_idx, indices, (size_t)n_indices * 4));
     c->n_vertices = n_vertices;
     c->n_indices = n_indices;
+    c->scene_checked = false;
     c->accel_blas_valid = c->accel_tlas_valid = false;
     return TR_OK;
 }
@@ -757,6 +798,12 @@ int32_t tr_tonemap(tr_ctx* c, const tr_baked_lottes_tonemapper_params* params) {
     return TR_OK;
 }
 
+int32_t tr_begin_frame(tr_ctx* c) {
+    TR_CHECK_CTX(c);
+    timing_next_frame(c);
+    return TR_OK;
+}
+
 int32_t tr_frame(tr_ctx* c, const tr_frame_params* f) {
     TR_CHECK_CTX(c);
     if (!f) return fail(TR_ERR_INVALID_ARG, "tr_frame: null");
@@ -834,7 +881,8 @@ int32_t tr_set_gbuffer(tr_ctx* c, int32_t layer, const tr_gbuffer_planes* g) {
     if (g->scale) TR_CUDA(cudaMemcpyAsync(L.scale.p, g->scale, npx * 4, cudaMemcpyHostToDevice, c->stream));
     else {  // model_scale 1.0 everywhere
         std::vector<float> ones(npx, 1.0f);
-        TR_CUDA(cudaMemcpy(L.scale.p, ones.data(), npx * 4, cudaMemcpyHostToDevice));
+        TR_CUDA(cudaMemcpyAsync(L.scale.p, ones.data(), npx * 4, cudaMemcpyHostToDevice, c->stream));  // ordered after a frame in flight
+        TR_CUDA(cudaStreamSynchronize(c->stream));  // `ones` is a local
     }
     if (g->position) TR_CUDA(cudaMemcpyAsync(L.position.p, g->position, npx * 12, cudaMemcpyHostToDevice, c->stream));
     if (c->materials_textured) {
@@ -889,6 +937,14 @@ int32_t tr_set_cluster_lights(tr_ctx* c, const uint32_t* counts, const uint32_t*
     TR_CHECK_CTX(c);
     if (!c->have_uniforms) return fail(TR_ERR_STATE, "tr_set_cluster_lights: uniforms not set");
     if (!counts || !indices) return fail(TR_ERR_INVALID_ARG, "tr_set_cluster_lights: null");
+    for (uint32_t k = 0; k < c->n_clusters; k++) {
+        if (counts[k] > TR_MAX_LIGHTS_PER_CLUSTER)
+            return fail(TR_ERR_INVALID_ARG, "tr_set_cluster_lights: cluster %u lists %u lights (at most %u)", k, counts[k], TR_MAX_LIGHTS_PER_CLUSTER);
+        for (uint32_t i = 0; i < counts[k]; i++)
+            if (indices[(size_t)k * TR_MAX_LIGHTS_PER_CLUSTER + i] >= c->n_lights)
+                return fail(TR_ERR_INVALID_ARG, "tr_set_cluster_lights: cluster %u names light %u of %u", k,
+                            indices[(size_t)k * TR_MAX_LIGHTS_PER_CLUSTER + i], c->n_lights);
+    }
     TR_TRY(upload(c, c->cluster_counts, counts, (size_t)c->n_clusters * 4));
     TR_TRY(upload(c, c->cluster_indices, indices, (size_t)c->n_clusters * TR_MAX_LIGHTS_PER_CLUSTER * 4));
     c->cluster_lights_valid = true;
@@ -957,7 +1013,7 @@ int32_t tr_read_hdr(tr_ctx* c, uint16_t* rgba16f) {
     if (!c->hdr_valid) return fail(TR_ERR_STATE, "tr_read_hdr: nothing rendered");
     TR_CUDA(cudaStreamSynchronize(c->stream));
     TR_CUDA(cudaMemcpy(rgba16f, c->hdr.p, (size_t)c->width * c->height * 8, cudaMemcpyDeviceToHost));
-    return TR_OK;
+    return check_device_status(c, "tr_read_hdr");
 }
 
 int32_t tr_read_hdr_f32(tr_ctx* c, float* rgba32f) {
@@ -967,7 +1023,7 @@ int32_t tr_read_hdr_f32(tr_ctx* c, float* rgba32f) {
     if (!c->hdr_valid) return fail(TR_ERR_STATE, "tr_read_hdr_f32: nothing rendered");
     TR_CUDA(cudaStreamSynchronize(c->stream));
     TR_CUDA(cudaMemcpy(rgba32f, c->hdr_f32.p, (size_t)c->width * c->height * 16, cudaMemcpyDeviceToHost));
-    return TR_OK;
+    return check_device_status(c, "tr_read_hdr_f32");
 }
 
 int32_t tr_read_pyramid_level(tr_ctx* c, uint32_t level, uint16_t* rgba16f, uint32_t* w, uint32_t* h) {
@@ -991,7 +1047,7 @@ int32_t tr_read_srgb8(tr_ctx* c, uint8_t* rgba8) {
     const size_t off = (size_t)c->band_y0 * c->width * 4, bytes = (size_t)(c->band_y1 - c->band_y0) * c->width * 4;
     TR_CUDA(cudaMemcpyAsync(rgba8 + off, c->srgb8.as<uint8_t>() + off, bytes, cudaMemcpyDeviceToHost, c->stream));
     TR_CUDA(cudaStreamSynchronize(c->stream));
-    return TR_OK;
+    return check_device_status(c, "tr_read_srgb8");
 }
 
 int32_t tr_read_srgb8_async(tr_ctx* c, uint8_t* rgba8) {
@@ -1015,7 +1071,7 @@ int32_t tr_read_srgb8_async(tr_ctx* c, uint8_t* rgba8) {
 int32_t tr_wait_readback(tr_ctx* c) {
     TR_CHECK_CTX(c);
     if (c->copy_pending) TR_CUDA(cudaEventSynchronize(c->ev_copy_done));
-    return TR_OK;
+    return check_device_status(c, "tr_wait_readback");  // an overflowed visibility pass must not pass for a good frame
 }
 
 int32_t tr_mip_levels(tr_ctx* c, uint32_t* levels) {
@@ -1059,6 +1115,13 @@ int32_t tr_eval_transmission_btdf(tr_ctx* c, uint32_t n, const tr_transmission_b
     TR_CHECK_CTX(c);
     return eval_batch(c, n, params, out, [&](const tr_transmission_btdf_params* i, tr_vec3* o) {
         return launch_eval_transmission_btdf(n, i, o, c->stream);
+    });
+}
+
+int32_t tr_eval_point_light(tr_ctx* c, uint32_t n, const tr_point_light_params* params, tr_point_light_result* out) {
+    TR_CHECK_CTX(c);
+    return eval_batch(c, n, params, out, [&](const tr_point_light_params* i, tr_point_light_result* o) {
+        return launch_eval_point_light(n, i, o, c->stream);
     });
 }
 

@@ -57,19 +57,24 @@ struct PixelShading {
     float s_nov, s_nov_t, a2_2pi, at2_2pi;
 };
 
+// calculate_combined_f0 / f90 (lib.rs:425-435) and c_diff / pi (lib.rs:404, 359): the colour factors of a pixel
+TRD void colour_factors(const MaterialParams& m, f3& f0, f3& df, f3& c_diff_pi) {
+    float d0 = to_dielectric_f0(m.index_of_refraction);
+    f3 dielectric = scale3(scale3(m.specular_colour, d0), m.specular_factor);
+    f0 = lerp3(dielectric, m.diffuse_colour, m.metallic);
+    f3 f90 = lerp3(splat3(m.specular_factor), splat3(1.0f), m.metallic);
+    df = sub3(f90, f0);
+    c_diff_pi = scale3(lerp3(m.diffuse_colour, splat3(0.0f), m.metallic), TR_FRAC_1_PI);
+}
+
 TRD PixelShading make_pixel_shading(const MaterialParams& m, f3 n, f3 v, bool with_transmission) {
     PixelShading s;
     s.n = n;
     s.v = v;
     s.nov_raw = xdot3(n, v);
     s.nov = fmaxf(s.nov_raw, TR_F32_EPSILON);
-    float d0 = to_dielectric_f0(m.index_of_refraction);
-    f3 dielectric = scale3(scale3(m.specular_colour, d0), m.specular_factor);
-    s.f0 = lerp3(dielectric, m.diffuse_colour, m.metallic);
-    f3 f90 = lerp3(splat3(m.specular_factor), splat3(1.0f), m.metallic);
-    s.df = sub3(f90, s.f0);
+    colour_factors(m, s.f0, s.df, s.c_diff_pi);
     s.base = m.diffuse_colour;
-    s.c_diff_pi = scale3(lerp3(m.diffuse_colour, splat3(0.0f), m.metallic), TR_FRAC_1_PI);
     float alpha = xmul(m.perceptual_roughness, m.perceptual_roughness);
     s.a2 = xmul(alpha, alpha);
     s.a2m1 = xsub(s.a2, 1.0f);
@@ -157,9 +162,8 @@ TRD f3 btdf_light(const PixelShading& s, f3 l) {
 #endif
 
 TRD f3 exact_light_dir(f3 vec) {  // light_direction_and_attenuation, lib.rs:12-23, exact regime
-    return xdivs3(vec, xsqrt(xdot3(vec, vec)));
+    return xunit3_mid(vec);
 }
-TRD float exact_noh(const struct PixelShading& s, f3 l);
 
 // light_direction_and_attenuation, lib.rs:12-23 (direction exact, attenuation fast)
 TRD void light_direction_and_attenuation(f3 fragment_position, f3 light_position, f3& direction, float& attenuation) {
@@ -170,72 +174,172 @@ TRD void light_direction_and_attenuation(f3 fragment_position, f3 light_position
     attenuation = frcp(d2);
 }
 
-TRD float exact_noh(const PixelShading& s, f3 l) {
-    f3 h = xnormalize3(xadd3(s.v, l));
-    return fmaxf(xdot3(s.n, h), TR_F32_EPSILON);
+TRD float exact_noh(f3 n, f3 v, f3 l) {
+    f3 h = xnormalize3_mid(xadd3(v, l));                             // Halfway::new, lib.rs:64-68
+    return fmaxf(xdot3(n, h), TR_F32_EPSILON);
 }
 
-// One GGX lobe of the fast light loop.  For unit v and l': |v + l'|^2 = 2 (1 + v.l'), so with opv = 1 + v.l'
-//   n.h = (n.v + n.l') / sqrt(2 opv),   v.h = opv / sqrt(2 opv)
-// and the halfway vector is never formed.  Returns d_ggx * v_smith_ggx_correlated = (a^2 / 2 pi) / (f^2 ggx)
-// (lib.rs:101-133 merged into one reciprocal; ggx > 0 always because n.v and n.l' are clamped to EPSILON).
-// `exact()` returns (n.h, n.l') of the exact chain.  It replaces the fast n.h inside highlights (f < TR_EXACT_F) and — for
-// the transmission lobe only (GGX_GUARD), whose value has no n.l' factor and therefore grows like 1/ggx — also the fast
-// n.l' where the Smith denominator is so small that 1e-7 of n.l' matters (grazing light on a pixel whose n.v is clamped).
+// ---- the light loop's fast regime ("lean" form) -----------------------------------------------------------
+// Everything the loop needs of a pixel, and nothing else (registers are what bounds the kernels' occupancy):
+struct LoopPixel {
+    f3 pos, n, v;                           // world position, unit normal, unit view vector
+    float nov_raw, nov;                     // n.v, and Dot::new's clamp of it (lib.rs:92-99)
+    float a2, a2m1h, one_m_a2, s_nov;       // reflection lobe: alpha^2, (alpha^2 - 1) / 2, 1 - alpha^2, sqrt(nov^2 (1 - a2) + a2)
+    float omf0m, ndfm;                      // 1 - f0[m] and -(f90 - f0)[m] 2^-5/2, m = the channel with the largest f0 (see below)
+    // transmission lobe (alpha_t = alpha clamp(2 ior - 2, 0, 1), lib.rs:144-148,209) and -2 n.v for the mirrored light
+    float at2, at2m1h, one_m_at2, s_nov_t, m2nov;
+};
+// Sums over the lights of a pixel.  The per-pixel colour factors are applied once, after the loop (finish_sums):
+//   d  = sum li * (1 - max F)                  diffuse  = c_diff / pi * d                  (lib.rs:356-360, 404)
+//   s0 = sum li * D V, s1 = sum li * D V * p   specular = f0 * s0 + (f90 - f0) * s1        (F = f0 + (f90 - f0) p, lib.rs:137-139)
+//   t0 = sum l * D' V', t1 = sum l * D' V' p'  transmission = base * ((1 - f0) t0 - (f90 - f0) t1)   (lib.rs:226-232)
+// with li = light intensity * n.l, p = (1 - v.h)^5 (carried as p 2^5/2, see light_lean), and D V without its
+// alpha^2 / (2 pi) (a per-pixel constant too).
+// max_element(F) (lib.rs:359): f90 = lerp(splat(specular_factor), 1, metallic) has three equal channels (lib.rs:432-435), so
+// the three lines f0_c + (f90 - f0_c) p meet at p = 1 and the channel with the largest f0 is the largest on all of [0, 1].
+// sm_100a retires two fp32 FMAs per issue slot as one packed instruction (PTX fma.rn.f32x2, SASS FFMA2) when both halves
+// live in an aligned register pair.  The accumulators are kept as such pairs — (d, s0) and (s1, t1) per colour channel —
+// and the light table stores every colour channel twice, so one FFMA2 adds (colour, colour) * (w_a, w_b) to both sums.
+typedef unsigned long long f32x2;
+TRD f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+TRD void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+TRD void ffma2(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+struct Colour2 { f32x2 r, g, b; };   // (r, r), (g, g), (b, b)
+TRD Colour2 dup_colour(f3 c) { Colour2 k; k.r = pack2(c.x, c.x); k.g = pack2(c.y, c.y); k.b = pack2(c.z, c.z); return k; }
+TRD float lo2(f32x2 v) { float a, b; unpack2(v, a, b); return a; }
+
+struct LoopSums {
+    f32x2 ds_r, ds_g, ds_b;   // (d, s0) per channel
+    f32x2 st_r, st_g, st_b;   // (s1, t1) per channel (transmissive pass)
+    f3 s1;                    // s1 alone (opaque pass: no t1 to pair it with)
+    f3 t0;
+    TRD void clear() { ds_r = ds_g = ds_b = st_r = st_g = st_b = 0ull; t0.x = t0.y = t0.z = 0.0f; s1 = t0; }
+};
+#define TR_SQRT2 1.41421356237309504880f
+#define TR_2_POW_M2_5 0.17677669529663688110f   // 2^-5/2
+
+TRD uint32_t argmax3(f3 a) { return a.x >= a.y ? (a.x >= a.z ? 0u : 2u) : (a.y >= a.z ? 1u : 2u); }
+TRD float pick3(f3 a, uint32_t i) { return i == 0u ? a.x : (i == 1u ? a.y : a.z); }
+
+TRD LoopPixel make_loop_pixel(const PixelShading& s, f3 pos) {
+    LoopPixel q;
+    q.pos = pos; q.n = s.n; q.v = s.v;
+    q.nov_raw = s.nov_raw; q.nov = s.nov;
+    q.a2 = s.a2; q.a2m1h = s.a2m1 * 0.5f; q.one_m_a2 = s.one_m_a2; q.s_nov = s.s_nov;
+    const uint32_t m = argmax3(s.f0);
+    q.omf0m = 1.0f - pick3(s.f0, m);
+    q.ndfm = -pick3(s.df, m) * TR_2_POW_M2_5;
+    q.at2 = s.at2; q.at2m1h = s.at2m1 * 0.5f; q.one_m_at2 = s.one_m_at2; q.s_nov_t = s.s_nov_t;
+    q.m2nov = -2.0f * s.nov_raw;
+    return q;
+}
+
+// One light: basic_brdf (lib.rs:377-423) and, with TRANS, transmission_btdf (lib.rs:200-233) for the same light.
+//   nol_raw = n.l, vol = v.l for the unit light direction l; colour * factor = the light's intensity at the fragment
+//   (emission x attenuation x spotlight factor); exact_dir() = l of the exact chain (only evaluated inside highlights).
+// For unit v and l: |v + l|^2 = 2 (1 + v.l), so with r = 1 / sqrt(1 + v.l):  sqrt2 n.h = (n.v + n.l) r  and
+// sqrt2 v.h = (1 + v.l) r — the halfway vector is never formed, and the sqrt2 is carried along instead of multiplied out:
+// f = noh^2 (a^2 - 1) + 1 = (sqrt2 noh)^2 ((a^2 - 1) / 2) + 1, and y = sqrt2 - sqrt2 v.h gives y^5 = 2^5/2 (1 - v.h)^5.
+// The mirrored light of the BTDF, l' = l - 2 (n.l) n, is a reflection: n.l' = -n.l, v.l' = v.l - 2 (n.l)(n.v).
+// D V = (a^2 / 2 pi) / (f^2 ggx) (lib.rs:101-133 in one reciprocal; ggx > 0 because n.v and n.l are clamped to EPSILON).
+// f is ill-conditioned inside a highlight: below TR_EXACT_F it is re-derived through the exact chain.  The transmission
+// lobe has no n.l' factor and grows like 1 / ggx, so where ggx is below TR_EXACT_GGX (grazing light on a pixel whose n.v is
+// clamped) n.l' comes from the exact chain too.  Both lobes share one (rarely taken) branch.
 #ifndef TR_EXACT_GGX
 #define TR_EXACT_GGX 0.005f
 #endif
-template <bool GGX_GUARD, typename Exact>
-TRD float ggx_lobe(float noh_num, float opv, float nol, float nov, float a2, float a2m1, float one_m_a2, float s_nov,
-                   float a2_2pi, Exact exact, float& voh) {
-    float inv_h = frsqrt(opv + opv);
-    float noh = fmaxf(noh_num * inv_h, TR_F32_EPSILON);
-    voh = fmaxf(opv * inv_h, TR_F32_EPSILON);
-    float f = fmaf(noh * noh, a2m1, 1.0f);
-    float ggx = fmaf(nol, s_nov, nov * fsqrt(fmaf(nol * nol, one_m_a2, a2)));
-    if (f < TR_EXACT_F || (GGX_GUARD && ggx < TR_EXACT_GGX)) {
-        const float2 e = exact();
-        f = xadd(xmul(xmul(e.x, e.x), a2m1), 1.0f);
-        if (GGX_GUARD) ggx = fmaf(e.y, s_nov, nov * fsqrt(fmaf(e.y * e.y, one_m_a2, a2)));
+template <bool TRANS, typename ExactDir>
+TRD void light_lean(const LoopPixel& s, ExactDir exact_dir, float nol_raw, float vol, const Colour2& colour, float factor, LoopSums& a) {
+    const float nol = fmaxf(nol_raw, TR_F32_EPSILON);
+    const float opv = fmaxf(vol + 1.0f, 1e-30f);
+    const float r = frsqrt(opv);
+    const float nohs = fmaxf((s.nov_raw + nol_raw) * r, TR_F32_EPSILON);
+    float f = fmaf(nohs * nohs, s.a2m1h, 1.0f);
+    const float y = TR_SQRT2 - opv * r;
+    const float ggx = fmaf(nol, s.s_nov, s.nov * fsqrt(fmaf(nol * nol, s.one_m_a2, s.a2)));
+    bool slow = f < TR_EXACT_F;
+    // transmission lobe
+    float nolt = 0.0f, ft = 1.0f, yt = 0.0f, ggxt = 1.0f;
+    if (TRANS) {
+        nolt = fmaxf(-nol_raw, TR_F32_EPSILON);
+        const float opvt = fmaxf(fmaf(nol_raw, s.m2nov, vol) + 1.0f, 1e-30f);
+        const float rt = frsqrt(opvt);
+        const float nohst = fmaxf((s.nov_raw - nol_raw) * rt, TR_F32_EPSILON);
+        ft = fmaf(nohst * nohst, s.at2m1h, 1.0f);
+        yt = TR_SQRT2 - opvt * rt;
+        ggxt = fmaf(nolt, s.s_nov_t, s.nov * fsqrt(fmaf(nolt * nolt, s.one_m_at2, s.at2)));
+        slow = slow || ft < TR_EXACT_F || ggxt < TR_EXACT_GGX;
     }
-    return a2_2pi * frcp(f * f * ggx);
+    if (slow) {
+        const f3 lx = exact_dir();
+        if (f < TR_EXACT_F) {
+            const float e = exact_noh(s.n, s.v, lx);
+            f = xadd(xmul(xmul(e, e), xadd(s.a2m1h, s.a2m1h)), 1.0f);
+        }
+        if (TRANS && (ft < TR_EXACT_F || ggxt < TR_EXACT_GGX)) {
+            const f3 lmx = xnormalize3_mid(xadd3(lx, xscale3(xscale3(s.n, 2.0f), -xdot3(lx, s.n))));   // lib.rs:211
+            const float e = exact_noh(s.n, s.v, lmx);
+            const float nolx = fmaxf(xdot3(s.n, lmx), TR_F32_EPSILON);
+            ft = xadd(xmul(xmul(e, e), xadd(s.at2m1h, s.at2m1h)), 1.0f);
+            ggxt = fmaf(nolx, s.s_nov_t, s.nov * fsqrt(fmaf(nolx * nolx, s.one_m_at2, s.at2)));
+        }
+    }
+    const float y2 = y * y;
+    const float p = y2 * y2 * y;                                            // 2^5/2 x fresnel_schlick's powf(1 - v.h, 5)
+    const float w = factor * nol;
+    const float wdv = w * frcp(f * f * ggx);
+    const f32x2 w_ds = pack2(w * fmaf(s.ndfm, p, s.omf0m), wdv);
+    ffma2(a.ds_r, colour.r, w_ds);
+    ffma2(a.ds_g, colour.g, w_ds);
+    ffma2(a.ds_b, colour.b, w_ds);
+    const f3 c1 = mk3(lo2(colour.r), lo2(colour.g), lo2(colour.b));
+    if (TRANS) {
+        const float yt2 = yt * yt;
+        const float pt = yt2 * yt2 * yt;
+        const float wt = factor * frcp(ft * ft * ggxt);
+        a.t0 = fma3(c1, wt, a.t0);
+        const f32x2 w_st = pack2(wdv * p, wt * pt);
+        ffma2(a.st_r, colour.r, w_st);
+        ffma2(a.st_g, colour.g, w_st);
+        ffma2(a.st_b, colour.b, w_st);
+    } else {
+        a.s1 = fma3(c1, wdv * p, a.s1);
+    }
 }
 
-// basic_brdf (lib.rs:377-423) for a point light at offset `vec`; `l` = vec / |vec| (fast), nol_raw = n.l, vol = v.l.
-// Accumulates sum(li * kd) (to be multiplied by c_diff / pi once, after the loop) and sum(li * F * D * V).
-// `colour` * `factor` is the light's intensity at the fragment (emission x attenuation x spotlight factor).
-// `exact_dir()` returns the unit light direction of the exact chain (only evaluated inside highlights).
-template <typename ExactDir>
-TRD void brdf_light_fast(const PixelShading& s, ExactDir exact_dir, float nol_raw, float vol, f3 colour, float factor, f3& diffuse_sum,
-                         f3& specular_acc) {
-    float voh;
-    float nol = fmaxf(nol_raw, TR_F32_EPSILON);
-    float dv = ggx_lobe<false>(s.nov_raw + nol_raw, 1.0f + vol, nol, s.nov, s.a2, s.a2m1, s.one_m_a2, s.s_nov, s.a2_2pi,
-                               [&]() { return make_float2(exact_noh(s, exact_dir()), 0.0f); }, voh);
-    f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
-    float w = factor * nol;                                   // light_intensity * n.l, per channel below
-    float kd = 1.0f - max_element3(fresnel);
-    diffuse_sum = fma3(colour, w * kd, diffuse_sum);
-    specular_acc = fma3(mul3(colour, fresnel), w * dv, specular_acc);
+// A point light of the clustered loops (lighting.rs:58-92, 179-216): light_direction_and_attenuation (lib.rs:12-23) in the
+// fast regime, then light_lean.  The direction is formed first and the dot products taken with it, as the exact chain does:
+// for a grazing light n.l cancels, and only then does its rounding follow the reference's operation order.
+// `spot(dir, factor)` may scale the factor (Light::spotlight_factor, opaque loop only).
+template <bool TRANS, typename Spot>
+TRD void point_light_lean(const LoopPixel& lp, f3 light_position, const Colour2& colour, Spot spot, LoopSums& sums) {
+    const f3 vec = sub3(light_position, lp.pos);
+    const float inv_d = frsqrt(dot3(vec, vec));
+    const f3 dir = scale3(vec, inv_d);
+    const float nol_raw = dot3(lp.n, dir), vol = dot3(lp.v, dir);
+    float factor = inv_d * inv_d;
+    spot(dir, factor);
+    light_lean<TRANS>(lp, [&]() { return exact_light_dir(vec); }, nol_raw, vol, colour, factor, sums);
 }
 
-// transmission_btdf (lib.rs:200-233) for the same light: l' = l - 2 (n.l) n is a reflection, so it is unit,
-// n.l' = -n.l and v.l' = v.l - 2 (n.l)(n.v).  Accumulates sum(light * (1 - F) * D * V) (times base colour after the loop).
-template <typename ExactDir>
-TRD void btdf_light_fast(const PixelShading& s, ExactDir exact_dir, float nol_raw, float vol, f3 colour, float factor, f3& transmission_sum) {
-    float voh;
-    float nolm = fmaxf(-nol_raw, TR_F32_EPSILON);
-    float vlm = fmaf(-2.0f * nol_raw, s.nov_raw, vol);
-    float dv = ggx_lobe<true>(s.nov_raw - nol_raw, 1.0f + vlm, nolm, s.nov, s.at2, s.at2m1, s.one_m_at2, s.s_nov_t, s.at2_2pi,
-                              [&]() {
-                                  f3 lx = exact_dir();
-                                  f3 lmx = xnormalize3(xadd3(lx, xscale3(xscale3(s.n, 2.0f), -xdot3(lx, s.n))));
-                                  return make_float2(exact_noh(s, lmx), fmaxf(xdot3(s.n, lmx), TR_F32_EPSILON));
-                              }, voh);
-    f3 fresnel = fresnel_schlick(voh, s.f0, s.df);
-    float w = factor * dv;
-    f3 t = mk3(fmaf(-fresnel.x, w, w), fmaf(-fresnel.y, w, w), fmaf(-fresnel.z, w, w));   // (1 - F) * w
-    transmission_sum = fma3v(colour, t, transmission_sum);
+// The per-pixel colour factors, once for all lights of the pixel (see LoopSums).
+TRD void finish_sums(const LoopSums& a, f3 f0, f3 df, f3 c_diff_pi, f3 base, float a2, float at2, bool with_transmission,
+                     f3& diffuse, f3& specular, f3& transmission) {
+    const float k = a2 * (0.5f * TR_FRAC_1_PI);
+    const f3 dfs = scale3(df, TR_2_POW_M2_5);   // s1 / t1 carry p 2^5/2
+    f3 d, s0, s1, t1;
+    unpack2(a.ds_r, d.x, s0.x); unpack2(a.ds_g, d.y, s0.y); unpack2(a.ds_b, d.z, s0.z);
+    unpack2(a.st_r, s1.x, t1.x); unpack2(a.st_g, s1.y, t1.y); unpack2(a.st_b, s1.z, t1.z);
+    if (!with_transmission) s1 = a.s1;
+    diffuse = mul3(d, c_diff_pi);
+    specular = scale3(fma3v(f0, s0, mul3(dfs, s1)), k);
+    transmission = splat3(0.0f);
+    if (with_transmission) {
+        const float kt = at2 * (0.5f * TR_FRAC_1_PI);
+        const f3 omf0 = mk3(1.0f - f0.x, 1.0f - f0.y, 1.0f - f0.z);
+        const f3 t = sub3(mul3(omf0, a.t0), mul3(dfs, t1));
+        transmission = scale3(mul3(t, base), kt);
+    }
 }
 
 // ---- contract-shaped wrappers (used by the tr_eval_* batch evaluators) ----

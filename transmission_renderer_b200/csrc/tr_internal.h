@@ -80,6 +80,8 @@ struct tr_ctx {
     uint32_t* d_instance_counts = nullptr;  // views into cull_scalars (state block of K1)
     uint32_t* d_cull_scalars = nullptr;     // [0] n_visible [1] visible triangles [2..5] draw_counts [6,7] ~min/max bits of slot_z
     std::vector<uint32_t> h_prim_tris, h_inst_prim;  // host copies: triangles per primitive, primitive of each instance
+    std::vector<uint32_t> h_inst_mat, h_prim_first, h_prim_count;  // material of each instance; index range of each primitive
+    bool scene_checked = false;  // ids / index ranges validated since the last upload (validate_scene)
     uint64_t max_triangles = 0;                      // upper bound of the visibility work list
     bool tri_bound_valid = false;
     bool cull_valid = false;
@@ -184,10 +186,12 @@ int32_t launch_assign_lights(tr_ctx* c, const tr_assign_lights_push_constants& p
 int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc);
 int32_t launch_eval_basic_brdf(uint32_t n, const tr_basic_brdf_params* in, tr_brdf_result* out, cudaStream_t s);
 int32_t launch_eval_transmission_btdf(uint32_t n, const tr_transmission_btdf_params* in, tr_vec3* out, cudaStream_t s);
+int32_t launch_eval_point_light(uint32_t n, const tr_point_light_params* in, tr_point_light_result* out, cudaStream_t s);
 int32_t launch_eval_ibl(uint32_t n, const trd::mat4& pv, const tr_ibl_volume_refraction_params* in, tr_vec3* out,
                         const trd::PyramidDesc& pyr, const trd::LutDesc& lut, cudaStream_t s);
 
-int32_t check_device_status(tr_ctx* c, const char* who);  // sticky device-side error bits -> TR_ERR_STATE
+int32_t check_device_status(tr_ctx* c, const char* who);
+int32_t validate_scene(tr_ctx* c, const char* who);  // instance -> primitive / material ids, primitive index ranges  // sticky device-side error bits -> TR_ERR_STATE
 void mat4_inverse_f64(const tr_mat4& m, tr_mat4* out);
 int32_t ensure_layer(tr_ctx* c, int layer, bool with_position);
 int32_t upload_texture_table(tr_ctx* c);  // descriptor table of the bound images -> device (if it changed)

@@ -182,6 +182,10 @@ class Renderer:
     def frame(self, frame_params):
         _check(_lib().tr_frame(self._ctx, _p(_c(frame_params, abi.frame_params))))
 
+    def begin_frame(self):
+        """Start of a frame for the per-pass timers when the passes are called one by one (tr_frame does it itself)."""
+        _check(_lib().tr_begin_frame(self._ctx))
+
     def enable_timing(self, on=True):
         _check(_lib().tr_enable_timing(self._ctx, C.c_int32(1 if on else 0)))
 
@@ -316,6 +320,13 @@ class Renderer:
         a = _c(params, abi.transmission_btdf_params)
         out = np.zeros((len(a), 3), dtype=np.float32)
         _check(_lib().tr_eval_transmission_btdf(self._ctx, C.c_uint32(len(a)), _p(a), _p(out)))
+        return out
+
+    def eval_point_light(self, params):
+        """The frame kernels' light loop for one (pixel, point light) pair per element."""
+        a = _c(params, abi.point_light_params)
+        out = np.zeros(len(a), dtype=abi.point_light_result)
+        _check(_lib().tr_eval_point_light(self._ctx, C.c_uint32(len(a)), _p(a), _p(out)))
         return out
 
     def eval_ibl_volume_refraction(self, proj_view, params):
