@@ -76,13 +76,33 @@ def _conditioning(p):
     return nol, nov, 1.0 + vol, 1.0 + vol - 2.0 * nol * nov
 
 
-# Per element: |got - ref| <= RTOL |ref| + ATOL x (light colour x attenuation).  The absolute term is the fp32 resolution of
-# the unit-vector dot products the lobes start from (n.l = 1e-4 is known to 1e-3 relative in ANY fp32 evaluation, the
-# reference's included): 1e-6 is ~8 ulp of 1.0.  Where the problem itself is singular the reference's value is rounding
-# noise and no tolerance is meaningful, so those elements are only counted: the halfway vector v + l (or v + l' of the
-# mirrored light) vanishes — `Halfway::new` normalises a zero vector (glam-pbr lib.rs:64-68) — or n.v is clamped to EPSILON
-# and 1 / (n.l n.v) amplifies every ulp by 1e7 (`Dot::new`, lib.rs:92-99).
-RTOL, ATOL = 1e-4, 1e-6
+def _ulp_sensitivity(oracle, p, ref):
+    """max |reference(inputs nudged by one ulp) - reference(inputs)| per element and lobe: how far the REFERENCE's own result
+    moves when one input component moves by one unit in the last place.  Nudged: each light-position component, one
+    component of the normal and of the view vector (six re-evaluations)."""
+    dev = {k: np.zeros(ref[k].shape, np.float64) for k in ("diffuse", "specular", "transmission")}
+    for field, comp in (("light_position", 0), ("light_position", 1), ("light_position", 2), ("normal", 0), ("view", 1), ("position", 2)):
+        q = p.copy()
+        x = q[field][:, comp]
+        q[field][:, comp] = np.nextafter(x, np.where(x > 0, np.float32(np.inf), np.float32(-np.inf)).astype(np.float32))
+        r = oracle.eval_point_light(q)
+        for k in dev:
+            d = np.abs(r[k].astype(np.float64) - ref[k].astype(np.float64))
+            dev[k] = np.maximum(dev[k], np.where(np.isfinite(d), d, np.inf))
+    return dev
+
+
+# Per element and channel:  |got - ref| <= RTOL |ref| + ATOL x (light colour x attenuation + the lobe's largest channel) + 4 x S,
+# where S is the reference's own sensitivity to a one-ulp nudge of its inputs (_ulp_sensitivity).  Where the lobes are regular S is ~1e-7 |ref|
+# and the bound is the relative tolerance; where the reference's value is rounding noise — the halfway vector v + l (or
+# v + l' of the mirrored light) vanishes and `Halfway::new` normalises a zero vector (glam-pbr lib.rs:64-68), or n.v / n.l are
+# clamped to EPSILON and 1 / (n.l n.v) amplifies every ulp by 1e7 (`Dot::new`, lib.rs:92-99) — the bound widens by exactly
+# as much as the reference itself is undetermined.  ATOL: the fp32 resolution of the unit-vector dot products (8 ulp of 1);
+# the three channels of a lobe share D V, so a channel that (1 - F) cancels to a millionth of the others is held to
+# their scale.  Not judged at all (only counted): elements whose halfway vector is shorter than 0.015 (1 + v.l < 1e-4 for the
+# reflection lobe, 1 + v.l' < 1e-4 for the transmission lobe) — there the reference's n.h and v.h are quotients of two
+# rounding residues, and nudging the inputs by an ulp does not reveal it.
+RTOL, ATOL, DEGENERATE = 1e-4, 1e-6, 1e-4
 
 
 @pytest.mark.parametrize("kind", ["random", "highlight", "highlight_t", "grazing", "rim", "backfacing"])
@@ -93,22 +113,32 @@ def test_point_light_per_element(oracle, kind):
     with Renderer(64, 64) as r:
         got = r.eval_point_light(p)
     ref = oracle.eval_point_light(p)
+    sens = _ulp_sensitivity(oracle, p, ref)
     d2 = np.sum((p["light_position"].astype(np.float64) - p["position"]) ** 2, axis=1, keepdims=True)
     scale = p["light_colour"].astype(np.float64) / d2          # colour x attenuation
-    nol, nov, opv, opvt = _conditioning(p)
-    regular = {"diffuse": nov > 1e-3, "specular": (opv > 1e-3) & (nov > 1e-3), "transmission": (opvt > 1e-3) & (nov > 1e-3)}
     report = []
+    _, _, opv, opvt = _conditioning(p)
+    judged = {"diffuse": np.ones(n, bool), "specular": opv >= DEGENERATE, "transmission": opvt >= DEGENERATE}
     for k in ("diffuse", "specular", "transmission"):
         g, f = got[k].astype(np.float64), ref[k].astype(np.float64)
-        finite = np.isfinite(f).all(axis=1) & np.isfinite(g).all(axis=1)
-        ok = finite & regular[k]
-        excess = np.abs(g - f) / (RTOL * np.abs(f) + ATOL * scale)      # <= 1 passes
-        worst = float(excess[ok].max())
-        share_bad = float((excess[ok] > 1.0).any(axis=1).mean())
-        l2 = rel_l2(got[k][ok], ref[k][ok])
-        report.append(f"{k}: {ok.mean():.3f} of the elements regular, worst {worst:.2f} x tolerance, rel-L2 {l2:.1e}; "
-                      f"singular ones: rel-L2 {rel_l2(got[k][finite & ~ok], ref[k][finite & ~ok]) if (finite & ~ok).any() else 0.0:.1e}")
+        finite = np.isfinite(f).all(axis=1) & np.isfinite(g).all(axis=1) & np.isfinite(sens[k]).all(axis=1)
         assert finite.mean() > 0.99, (kind, k, finite.mean())
-        assert ok.sum() > 1000 and share_bad == 0.0, (kind, k, worst, share_bad)
-        assert l2 < 2e-5, (kind, k, l2)
+        finite &= judged[k]
+        assert finite.sum() > 2000, (kind, k, int(finite.sum()))
+        tol = RTOL * np.abs(f) + ATOL * (scale + np.abs(f).max(axis=1, keepdims=True)) + 4.0 * sens[k]
+        excess = (np.abs(g - f) / tol)[finite]
+        regular = (4.0 * sens[k] <= RTOL * np.abs(f) + ATOL * scale).all(axis=1)[finite]   # bound not widened by the sensitivity term
+        bad = (excess > 1.0).any(axis=1)
+        l2 = rel_l2(got[k][finite][regular], ref[k][finite][regular])
+        report.append(f"{k}: worst {excess.max():.2f} x tolerance, {bad.sum()} of {len(bad)} judged elements over ({n - len(bad)} degenerate / non-finite); "
+                      f"{regular.mean():.3f} regular (rel-L2 there {l2:.1e})")
+        if bad.sum():   # show what the offending elements look like before failing
+            idx = np.nonzero(finite)[0][np.argsort(-excess.max(axis=1))[:4]]
+            nol, nov, opv, opvt = _conditioning(p[idx])
+            for j, i in enumerate(idx):
+                print(f"  worst[{k}] #{i}: got {got[k][i]} ref {ref[k][i]} sens {sens[k][i]} n.l {nol[j]:.3e} n.v {nov[j]:.3e} 1+v.l {opv[j]:.3e} "
+                      f"1+v.l' {opvt[j]:.3e} rough {p['material_params']['perceptual_roughness'][i]:.3f} ior {p['material_params']['index_of_refraction'][i]:.3f} "
+                      f"metallic {p['material_params']['metallic'][i]:.1f} dist {np.sqrt(d2[i, 0]):.3f}")
+        assert bad.sum() == 0, (kind, k, float(excess.max()), int(bad.sum()))
+        assert l2 < 1e-4, (kind, k, l2)   # the north-star tolerance, on the regular elements of the population
     print(f"point light [{kind}] " + " | ".join(report))

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(TILE, TEX ? 2 : (TRANS ? TR_SHADE_CTAS_TRANS :
             }
             if (!SHADOW || sun_factor != 0.0f) {
                 auto exact_sun = [&]() { return sun_dir; };
-                light_lean<TRANS>(lp, exact_sun, dot3(lp.n, sun_dir), dot3(lp.v, sun_dir), dup_colour(sun_int), sun_factor, sums);
+                light_lean<TRANS>(lp, exact_sun, sun_dir, dot3(lp.n, sun_dir), dup_colour(sun_int), sun_factor, sums);
             }
         }
 

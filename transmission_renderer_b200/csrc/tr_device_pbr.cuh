@@ -158,7 +158,7 @@ TRD f3 btdf_light(const PixelShading& s, f3 l) {
 // residual is fp32 rounding of the sums, not the MUFU approximation), so the threshold is the only knob: 0.08 keeps 8x margin
 // to the 1e-4 tolerance for ~3 % of the shading time.  There the result is bit-identical to the all-exact evaluation; elsewhere it is within ~1e-6 of it.
 #ifndef TR_EXACT_F
-#define TR_EXACT_F 0.08f
+#define TR_EXACT_F 0.04f
 #endif
 
 TRD f3 exact_light_dir(f3 vec) {  // light_direction_and_attenuation, lib.rs:12-23, exact regime
@@ -184,19 +184,36 @@ TRD float exact_noh(f3 n, f3 v, f3 l) {
 struct LoopPixel {
     f3 pos, n, v;                           // world position, unit normal, unit view vector
     float nov_raw, nov;                     // n.v, and Dot::new's clamp of it (lib.rs:92-99)
-    float a2, a2m1h, one_m_a2, s_nov;       // reflection lobe: alpha^2, (alpha^2 - 1) / 2, 1 - alpha^2, sqrt(nov^2 (1 - a2) + a2)
-    float omf0m, ndfm;                      // 1 - f0[m] and -(f90 - f0)[m] 2^-5/2, m = the channel with the largest f0 (see below)
-    // transmission lobe (alpha_t = alpha clamp(2 ior - 2, 0, 1), lib.rs:144-148,209) and -2 n.v for the mirrored light
-    float at2, at2m1h, one_m_at2, s_nov_t, m2nov;
+    float a2, a2m1, one_m_a2, s_nov;        // reflection lobe: alpha^2, alpha^2 - 1, 1 - alpha^2, sqrt(nov^2 (1 - a2) + a2)
+    float omf0m, ndfm;                      // 1 - f0[m] and -(f90 - f0)[m] / 32, m = the channel with the largest f0 (see below)
+    // transmission lobe (alpha_t = alpha clamp(2 ior - 2, 0, 1), lib.rs:144-148,209)
+    float at2, at2m1, one_m_at2, s_nov_t;
 };
 // Sums over the lights of a pixel.  The per-pixel colour factors are applied once, after the loop (finish_sums):
 //   d  = sum li * (1 - max F)                  diffuse  = c_diff / pi * d                  (lib.rs:356-360, 404)
 //   s0 = sum li * D V, s1 = sum li * D V * p   specular = f0 * s0 + (f90 - f0) * s1        (F = f0 + (f90 - f0) p, lib.rs:137-139)
 //   t0 = sum l * D' V', t1 = sum l * D' V' p'  transmission = base * ((1 - f0) t0 - (f90 - f0) t1)   (lib.rs:226-232)
-// with li = light intensity * n.l, p = (1 - v.h)^5 (carried as p 2^5/2, see light_lean), and D V without its
+// with li = light intensity * n.l, p = (1 - v.h)^5 (carried as 32 p, see light_lean), and D V without its
 // alpha^2 / (2 pi) (a per-pixel constant too).
 // max_element(F) (lib.rs:359): f90 = lerp(splat(specular_factor), 1, metallic) has three equal channels (lib.rs:432-435), so
 // the three lines f0_c + (f90 - f0_c) p meet at p = 1 and the channel with the largest f0 is the largest on all of [0, 1].
+#define TR_2_POW_M5 0.03125f
+
+TRD uint32_t argmax3(f3 a) { return a.x >= a.y ? (a.x >= a.z ? 0u : 2u) : (a.y >= a.z ? 1u : 2u); }
+TRD float pick3(f3 a, uint32_t i) { return i == 0u ? a.x : (i == 1u ? a.y : a.z); }
+
+TRD LoopPixel make_loop_pixel(const PixelShading& s, f3 pos) {
+    LoopPixel q;
+    q.pos = pos; q.n = s.n; q.v = s.v;
+    q.nov_raw = s.nov_raw; q.nov = s.nov;
+    q.a2 = s.a2; q.a2m1 = s.a2m1; q.one_m_a2 = s.one_m_a2; q.s_nov = s.s_nov;
+    const uint32_t m = argmax3(s.f0);
+    q.omf0m = 1.0f - pick3(s.f0, m);
+    q.ndfm = -pick3(s.df, m) * TR_2_POW_M5;
+    q.at2 = s.at2; q.at2m1 = s.at2m1; q.one_m_at2 = s.one_m_at2; q.s_nov_t = s.s_nov_t;
+    return q;
+}
+
 // sm_100a retires two fp32 FMAs per issue slot as one packed instruction (PTX fma.rn.f32x2, SASS FFMA2) when both halves
 // live in an aligned register pair.  The accumulators are kept as such pairs — (d, s0) and (s1, t1) per colour channel —
 // and the light table stores every colour channel twice, so one FFMA2 adds (colour, colour) * (w_a, w_b) to both sums.
@@ -215,58 +232,42 @@ struct LoopSums {
     f3 t0;
     TRD void clear() { ds_r = ds_g = ds_b = st_r = st_g = st_b = 0ull; t0.x = t0.y = t0.z = 0.0f; s1 = t0; }
 };
-#define TR_SQRT2 1.41421356237309504880f
-#define TR_2_POW_M2_5 0.17677669529663688110f   // 2^-5/2
-
-TRD uint32_t argmax3(f3 a) { return a.x >= a.y ? (a.x >= a.z ? 0u : 2u) : (a.y >= a.z ? 1u : 2u); }
-TRD float pick3(f3 a, uint32_t i) { return i == 0u ? a.x : (i == 1u ? a.y : a.z); }
-
-TRD LoopPixel make_loop_pixel(const PixelShading& s, f3 pos) {
-    LoopPixel q;
-    q.pos = pos; q.n = s.n; q.v = s.v;
-    q.nov_raw = s.nov_raw; q.nov = s.nov;
-    q.a2 = s.a2; q.a2m1h = s.a2m1 * 0.5f; q.one_m_a2 = s.one_m_a2; q.s_nov = s.s_nov;
-    const uint32_t m = argmax3(s.f0);
-    q.omf0m = 1.0f - pick3(s.f0, m);
-    q.ndfm = -pick3(s.df, m) * TR_2_POW_M2_5;
-    q.at2 = s.at2; q.at2m1h = s.at2m1 * 0.5f; q.one_m_at2 = s.one_m_at2; q.s_nov_t = s.s_nov_t;
-    q.m2nov = -2.0f * s.nov_raw;
-    return q;
-}
-
 // One light: basic_brdf (lib.rs:377-423) and, with TRANS, transmission_btdf (lib.rs:200-233) for the same light.
-//   nol_raw = n.l, vol = v.l for the unit light direction l; colour * factor = the light's intensity at the fragment
-//   (emission x attenuation x spotlight factor); exact_dir() = l of the exact chain (only evaluated inside highlights).
-// For unit v and l: |v + l|^2 = 2 (1 + v.l), so with r = 1 / sqrt(1 + v.l):  sqrt2 n.h = (n.v + n.l) r  and
-// sqrt2 v.h = (1 + v.l) r — the halfway vector is never formed, and the sqrt2 is carried along instead of multiplied out:
-// f = noh^2 (a^2 - 1) + 1 = (sqrt2 noh)^2 ((a^2 - 1) / 2) + 1, and y = sqrt2 - sqrt2 v.h gives y^5 = 2^5/2 (1 - v.h)^5.
-// The mirrored light of the BTDF, l' = l - 2 (n.l) n, is a reflection: n.l' = -n.l, v.l' = v.l - 2 (n.l)(n.v).
-// D V = (a^2 / 2 pi) / (f^2 ggx) (lib.rs:101-133 in one reciprocal; ggx > 0 because n.v and n.l are clamped to EPSILON).
-// f is ill-conditioned inside a highlight: below TR_EXACT_F it is re-derived through the exact chain.  The transmission
-// lobe has no n.l' factor and grows like 1 / ggx, so where ggx is below TR_EXACT_GGX (grazing light on a pixel whose n.v is
-// clamped) n.l' comes from the exact chain too.  Both lobes share one (rarely taken) branch.
+//   l = the unit light direction, nol_raw = n.l; colour * factor = the light's intensity at the fragment (emission x
+//   attenuation x spotlight factor); exact_dir() = l of the exact chain (only evaluated inside highlights).
+// The halfway vector is formed un-normalised, h = v + l, and only its squared length is used: n.h = (n.v + n.l) / |h| and,
+// for unit v and l, v.h = |h| / 2 — so y = 2 - |h| = 2 (1 - v.h) and y^5 = 32 (1 - v.h)^5.  (|h|^2 = 2 (1 + v.l) would save
+// three instructions, but 1 + v.l cancels when the light is almost behind the viewer, the grazing forward-scatter
+// configuration: tests/test_gpu_hot_loop.py.)  The mirrored light of the BTDF, l' = l - 2 (n.l) n, is a reflection:
+// h' = v + l' = h - 2 (n.l) n and n.l' = -n.l.  D V = (a^2 / 2 pi) / (f^2 ggx) with f = noh^2 (a^2 - 1) + 1 (lib.rs:101-133 in
+// one reciprocal; ggx > 0 because n.v and n.l are clamped to EPSILON).  f is ill-conditioned inside a highlight: below
+// TR_EXACT_F it is re-derived through the exact chain.  The transmission lobe has no n.l' factor and grows like 1 / ggx, so
+// where ggx is below TR_EXACT_GGX (grazing light on a pixel whose n.v is clamped) n.l' comes from the exact chain too.
+// Both lobes share one (rarely taken) branch.
 #ifndef TR_EXACT_GGX
 #define TR_EXACT_GGX 0.005f
 #endif
 template <bool TRANS, typename ExactDir>
-TRD void light_lean(const LoopPixel& s, ExactDir exact_dir, float nol_raw, float vol, const Colour2& colour, float factor, LoopSums& a) {
+TRD void light_lean(const LoopPixel& s, ExactDir exact_dir, f3 l, float nol_raw, const Colour2& colour, float factor, LoopSums& a) {
     const float nol = fmaxf(nol_raw, TR_F32_EPSILON);
-    const float opv = fmaxf(vol + 1.0f, 1e-30f);
-    const float r = frsqrt(opv);
-    const float nohs = fmaxf((s.nov_raw + nol_raw) * r, TR_F32_EPSILON);
-    float f = fmaf(nohs * nohs, s.a2m1h, 1.0f);
-    const float y = TR_SQRT2 - opv * r;
+    const f3 h = add3(s.v, l);
+    const float h2 = fmaxf(dot3(h, h), 1e-30f);
+    const float r = frsqrt(h2);
+    const float noh = fmaxf((s.nov_raw + nol_raw) * r, TR_F32_EPSILON);
+    float f = fmaf(noh * noh, s.a2m1, 1.0f);
+    const float y = 2.0f - h2 * r;
     const float ggx = fmaf(nol, s.s_nov, s.nov * fsqrt(fmaf(nol * nol, s.one_m_a2, s.a2)));
     bool slow = f < TR_EXACT_F;
     // transmission lobe
     float nolt = 0.0f, ft = 1.0f, yt = 0.0f, ggxt = 1.0f;
     if (TRANS) {
         nolt = fmaxf(-nol_raw, TR_F32_EPSILON);
-        const float opvt = fmaxf(fmaf(nol_raw, s.m2nov, vol) + 1.0f, 1e-30f);
-        const float rt = frsqrt(opvt);
-        const float nohst = fmaxf((s.nov_raw - nol_raw) * rt, TR_F32_EPSILON);
-        ft = fmaf(nohst * nohst, s.at2m1h, 1.0f);
-        yt = TR_SQRT2 - opvt * rt;
+        const f3 ht = fma3(s.n, -2.0f * nol_raw, h);
+        const float ht2 = fmaxf(dot3(ht, ht), 1e-30f);
+        const float rt = frsqrt(ht2);
+        const float noht = fmaxf((s.nov_raw - nol_raw) * rt, TR_F32_EPSILON);
+        ft = fmaf(noht * noht, s.at2m1, 1.0f);
+        yt = 2.0f - ht2 * rt;
         ggxt = fmaf(nolt, s.s_nov_t, s.nov * fsqrt(fmaf(nolt * nolt, s.one_m_at2, s.at2)));
         slow = slow || ft < TR_EXACT_F || ggxt < TR_EXACT_GGX;
     }
@@ -274,18 +275,18 @@ TRD void light_lean(const LoopPixel& s, ExactDir exact_dir, float nol_raw, float
         const f3 lx = exact_dir();
         if (f < TR_EXACT_F) {
             const float e = exact_noh(s.n, s.v, lx);
-            f = xadd(xmul(xmul(e, e), xadd(s.a2m1h, s.a2m1h)), 1.0f);
+            f = xadd(xmul(xmul(e, e), s.a2m1), 1.0f);
         }
         if (TRANS && (ft < TR_EXACT_F || ggxt < TR_EXACT_GGX)) {
             const f3 lmx = xnormalize3_mid(xadd3(lx, xscale3(xscale3(s.n, 2.0f), -xdot3(lx, s.n))));   // lib.rs:211
             const float e = exact_noh(s.n, s.v, lmx);
             const float nolx = fmaxf(xdot3(s.n, lmx), TR_F32_EPSILON);
-            ft = xadd(xmul(xmul(e, e), xadd(s.at2m1h, s.at2m1h)), 1.0f);
+            ft = xadd(xmul(xmul(e, e), s.at2m1), 1.0f);
             ggxt = fmaf(nolx, s.s_nov_t, s.nov * fsqrt(fmaf(nolx * nolx, s.one_m_at2, s.at2)));
         }
     }
     const float y2 = y * y;
-    const float p = y2 * y2 * y;                                            // 2^5/2 x fresnel_schlick's powf(1 - v.h, 5)
+    const float p = y2 * y2 * y;                                            // 32 x fresnel_schlick's powf(1 - v.h, 5)
     const float w = factor * nol;
     const float wdv = w * frcp(f * f * ggx);
     const f32x2 w_ds = pack2(w * fmaf(s.ndfm, p, s.omf0m), wdv);
@@ -316,17 +317,16 @@ TRD void point_light_lean(const LoopPixel& lp, f3 light_position, const Colour2&
     const f3 vec = sub3(light_position, lp.pos);
     const float inv_d = frsqrt(dot3(vec, vec));
     const f3 dir = scale3(vec, inv_d);
-    const float nol_raw = dot3(lp.n, dir), vol = dot3(lp.v, dir);
     float factor = inv_d * inv_d;
     spot(dir, factor);
-    light_lean<TRANS>(lp, [&]() { return exact_light_dir(vec); }, nol_raw, vol, colour, factor, sums);
+    light_lean<TRANS>(lp, [&]() { return exact_light_dir(vec); }, dir, dot3(lp.n, dir), colour, factor, sums);
 }
 
 // The per-pixel colour factors, once for all lights of the pixel (see LoopSums).
 TRD void finish_sums(const LoopSums& a, f3 f0, f3 df, f3 c_diff_pi, f3 base, float a2, float at2, bool with_transmission,
                      f3& diffuse, f3& specular, f3& transmission) {
     const float k = a2 * (0.5f * TR_FRAC_1_PI);
-    const f3 dfs = scale3(df, TR_2_POW_M2_5);   // s1 / t1 carry p 2^5/2
+    const f3 dfs = scale3(df, TR_2_POW_M5);   // s1 / t1 carry 32 p
     f3 d, s0, s1, t1;
     unpack2(a.ds_r, d.x, s0.x); unpack2(a.ds_g, d.y, s0.y); unpack2(a.ds_b, d.z, s0.z);
     unpack2(a.st_r, s1.x, t1.x); unpack2(a.st_g, s1.y, t1.y); unpack2(a.st_b, s1.z, t1.z);
