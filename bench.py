@@ -19,8 +19,10 @@ the frame is fixed), with the opaque bands exchanged before the mip chain.
 `--workload`  4k = BASELINE.json configs[3] (the headline, default); config1/2/3/5 = configs[0]/[1]/[2]/[4] at their
          stated sizes (config5: 8K x 64 orbit views; combine with --view-groups for the 8x1/4x2/2x4/1x8 sweep).
 `sustained`  the same frames back to back for >= --min-seconds (default 2 s) with its own clock summary, next to the K-step burst.
-`band_hashes`  SHA-256 of every rank's HDR (RGBA16F) and sRGB8 band; the N = 1 line carries the hashes of the same row
-         ranges for 2, 4 and 8 bands, so that N-GPU output == 1-GPU output can be checked from the JSON lines alone.
+`frame_sha256`  SHA-256 of the whole HDR (RGBA16F) and sRGB8 frame, at N > 1 stitched from the ranks' bands: equal at every N
+         <=> N-GPU output == 1-GPU output bitwise, checkable from the JSON lines alone.  `band_hashes` are the per-band
+         digests (the N = 1 line carries those of the equal-row splits into 2, 4 and 8); `band_rows` the boundaries used —
+         at N > 1 they are balanced by measured cost before the timed region (--equal-bands keeps tr_comm_init's).
 `--impl reference`  the reference's per-pixel code (shader + glam-pbr) as the CPU oracle port, all host
          threads (OpenMP), on a bounded band of the same 4K frame.  The reference is Rust -> SPIR-V and
          cannot be built here (no cargo/rustc), so the port under oracle/ is the only runnable form.
@@ -451,6 +453,18 @@ def run_b200(args, wl):
     if sampler:
         sampler.start()
 
+    # N > 1: equal-row bands leave the ranks unequal work (coverage, triangle density and light counts vary down the frame);
+    # a few untimed frames with the per-pass timers on move the boundaries until every band costs about the same. The frame
+    # is bitwise the same for any boundaries (frame_sha256 below).
+    band_bounds = [host.band_rows(H, b, bands)[0] for b in range(bands)] + [H]
+    if bands > 1 and not args.equal_bands and not args.emulate_band:
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                one_step()
+            sync()
+            band_bounds = parallel.balance_bands(r, lambda: [one_step() for _ in range(3)], band_rank, bands, group=band_group)
+        y0, y1 = band_bounds[band_rank], band_bounds[band_rank + 1]
+
     # the 512^2 case fits L2: a 256 MB buffer is overwritten between timed steps, each step under its own event pair
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if W * H < 1920 * 1080 else None
 
@@ -582,7 +596,7 @@ def run_b200(args, wl):
         sampler.stop()
 
     # ------------------------------------------------------------------ band hashes: N-GPU output == 1-GPU output, from the lines
-    band_hashes = None
+    band_hashes, frame_sha = None, None
     if args.views == 1 and not args.emulate_band:
         hdr_bits, srgb = r.read_hdr(), r.read_srgb8()
         mine = {"rows": [int(y0), int(y1)], "hdr_rgba16f": sha256_rows(hdr_bits, y0, y1), "srgb8": sha256_rows(srgb, y0, y1)}
@@ -590,7 +604,15 @@ def run_b200(args, wl):
             every = [None] * world
             dist.all_gather_object(every, mine, group=cpu_group)
             band_hashes = {str(bands): every[:bands]}
+            if groups == 1:   # the whole frame, stitched from the ranks' bands on rank 0 (outside every timed region)
+                parts = [None] * world
+                dist.all_gather_object(parts, (hdr_bits[y0:y1].copy(), srgb[y0:y1].copy()), group=cpu_group)
+                if rank == 0:
+                    import hashlib
+                    frame_sha = {"hdr_rgba16f": hashlib.sha256(b"".join(p[0].tobytes() for p in parts)).hexdigest(),
+                                 "srgb8": hashlib.sha256(b"".join(p[1].tobytes() for p in parts)).hexdigest()}
         else:
+            frame_sha = {"hdr_rgba16f": sha256_rows(hdr_bits, 0, H), "srgb8": sha256_rows(srgb, 0, H)}
             band_hashes = {}
             for n in (1, 2, 4, 8):
                 rows = [host.band_rows(H, b, n) for b in range(n)]
@@ -657,6 +679,8 @@ def run_b200(args, wl):
             "shade_path": {"ms": shade_path_ms, "Mpx/s": W * H / (shade_path_ms * 1e-3) / 1e6},
             "fp32_peak_tflops_measured": fp32_peak,
             "raster_stats_per_frame": {k: v / (args.steps + max(args.warmup, 3)) for k, v in rstats.items()},
+            "band_rows": [int(v) for v in band_bounds],
+            "frame_sha256": frame_sha,
             "band_hashes": band_hashes,
         }
         # ---- CPU baseline: the oracle port on the box's host cores, bounded sample, N=1 only; doubles as a live parity check
@@ -710,6 +734,8 @@ def main():
                     help="camera views per step (BASELINE configs[4]: 64 orbit views, the default of --workload config5); a step renders all of them")
     ap.add_argument("--view-groups", type=int, default=1,
                     help="N ranks = view-groups x bands: each group of N/view-groups ranks renders its share of the views band-parallel")
+    ap.add_argument("--equal-bands", action="store_true",
+                    help="N>1: keep the equal-row bands of tr_comm_init instead of balancing the band boundaries by measured cost")
     ap.add_argument("--emulate-band", default=None, metavar="R/N",
                     help="profiling aid (1 GPU): render only band R of N without any exchange, e.g. 3/8")
     args = ap.parse_args()

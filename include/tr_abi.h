@@ -525,6 +525,11 @@ TR_API int32_t tr_eval_ibl_volume_refraction(tr_ctx* ctx, uint32_t n, const tr_m
 TR_API int32_t tr_comm_unique_id(uint8_t id[TR_NCCL_UNIQUE_ID_BYTES]);
 TR_API int32_t tr_comm_init(tr_ctx* ctx, const uint8_t id[TR_NCCL_UNIQUE_ID_BYTES], int32_t rank, int32_t n_ranks);
 TR_API int32_t tr_comm_destroy(tr_ctx* ctx);
+/* Caller-balanced bands: `bounds` = n_ranks + 1 ascending row boundaries, the same on every rank (0 ... height); rank r
+ * renders rows [bounds[r], bounds[r+1]).  Equal rows (tr_comm_init's default) leave the ranks unequal work where
+ * coverage and light counts vary down the frame; the frame is bitwise the same for any boundaries.  Call between
+ * frames, on all ranks alike. */
+TR_API int32_t tr_set_bands(tr_ctx* ctx, const uint32_t* bounds, uint32_t n_bounds);
 /* Peer-store path: K4 writes its band into every peer's frame directly over NVLink. */
 #define TR_IPC_HANDLE_BYTES 64
 TR_API int32_t tr_peer_export(tr_ctx* ctx, uint8_t handle[TR_IPC_HANDLE_BYTES]);

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from transmission_renderer_b200 import Renderer, host, parallel, scenes  # noqa: E402
 
 
-def render(s, lut, w, h, rank, world, group, exchange, frames=3, ray_tracing=False):
+def render(s, lut, w, h, rank, world, group, exchange, frames=3, ray_tracing=False, bounds=None):
     cam = s["camera"]
     with Renderer(w, h, device=int(os.environ.get("LOCAL_RANK", "0"))) as r:
         r.set_uniforms(s["uniforms"]); r.set_materials(s["materials"]); r.set_lights(s["lights"]); r.set_ggx_lut(lut)
@@ -22,6 +22,9 @@ def render(s, lut, w, h, rank, world, group, exchange, frames=3, ray_tracing=Fal
         r.set_mesh(m["positions"], m["normals"], m["uvs"], m["indices"])
         r.build_clusters(cam.write_cluster_data())
         y0, y1 = parallel.init_bands(r, rank, world, group=group, exchange=exchange) if world > 1 else (0, h)
+        if bounds is not None:   # caller-balanced (ragged) bands, tr_set_bands
+            r.set_bands(bounds)
+            y0, y1 = bounds[rank], bounds[rank + 1]
         handle = r.build_acceleration_structures() if ray_tracing else 0   # every rank builds the same structures
         fp = cam.frame_params(host.default_tonemap_params(), acceleration_structure_address=handle)
         for _ in range(frames):   # several frames back to back: the exchange buffers are reused
@@ -53,6 +56,16 @@ def main():
         assert mip0.tobytes() == mip0_1.tobytes(), f"{exchange}: exchanged opaque frame differs"
         assert mip3.tobytes() == mip3_1.tobytes(), f"{exchange}: mip 3 differs"
         dist.barrier(group=group)
+    # caller-balanced bands (tr_set_bands): ragged boundaries, both exchanges
+    cuts = sorted({int(round(h * f / 8.0)) * 8 for f in (0.17, 0.49, 0.8)})[: world - 1]
+    bounds = [0] + cuts + [h]
+    assert len(bounds) == world + 1
+    for exchange in ("nccl", "peer"):
+        (y0, y1), hdr, srgb, mip0, mip3 = render(s, lut, w, h, rank, world, group, exchange, bounds=bounds)
+        assert (y0, y1) == (bounds[rank], bounds[rank + 1])
+        assert hdr.tobytes() == hdr1[y0:y1].tobytes(), f"{exchange}, balanced bands {bounds}: HDR band differs from the single-GPU frame"
+        assert srgb.tobytes() == srgb1[y0:y1].tobytes() and mip0.tobytes() == mip0_1.tobytes() and mip3.tobytes() == mip3_1.tobytes()
+        dist.barrier(group=group)
     # ray-queried shadows: every rank traces the rays of its own rows against the whole scene
     _, hdr1, srgb1, mip0_1, _ = render(s, lut, w, h, 0, 1, None, "nccl", frames=1, ray_tracing=True)
     (y0, y1), hdr, srgb, mip0, _ = render(s, lut, w, h, rank, world, group, "peer", frames=2, ray_tracing=True)
@@ -60,7 +73,7 @@ def main():
     assert srgb.tobytes() == srgb1[y0:y1].tobytes() and mip0.tobytes() == mip0_1.tobytes(), "ray queries: band / exchanged frame differs"
     dist.barrier(group=group)
     if rank == 0:
-        print(f"multi-GPU OK: {world} ranks, nccl + peer exchange, bands == single-GPU frame bitwise")
+        print(f"multi-GPU OK: {world} ranks, nccl + peer exchange, equal and balanced bands == single-GPU frame bitwise")
     dist.destroy_process_group()
 
 

@@ -90,3 +90,90 @@ def test_two_rank_bands_equal_full_frame():
         assert p.exitcode == 0
     got = sorted(out.get(timeout=5) for _ in range(2))
     assert got == [(0, 0, H // 2), (1, H // 2, H)]
+
+
+# ---- cost-balanced bands (tr_set_bands / parallel.balance_bands) ---------------------------------------------------------
+def test_balanced_bounds_properties():
+    rng = np.random.default_rng(0)
+    for n in (2, 4, 8):
+        for h in (1080, 2160, 4320):
+            bounds = [parallel.band_rows(h, r, n)[0] for r in range(n)] + [h]
+            ms = rng.uniform(0.2, 1.0, n)
+            new = parallel.balanced_bounds(bounds, ms)
+            assert new[0] == 0 and new[-1] == h and all(b > a for a, b in zip(new, new[1:]))
+            assert all(v % 8 == 0 for v in new[1:-1])
+            # the slowest band gets fewer rows, the fastest more
+            rows_old, rows_new = np.diff(bounds), np.diff(new)
+            assert rows_new[np.argmax(ms)] <= rows_old[np.argmax(ms)] and rows_new[np.argmin(ms)] >= rows_old[np.argmin(ms)]
+            # equal cost -> nothing moves (up to the alignment)
+            same = parallel.balanced_bounds(bounds, np.ones(n))
+            assert max(abs(a - b) for a, b in zip(same, bounds)) <= 4
+
+
+def test_balanced_bounds_converge_on_a_known_cost_profile():
+    """Cost per row 1 + 3 y / H: repeated balancing against the exact band costs ends with equal-cost bands."""
+    h, n = 2160, 8
+    cost = 1.0 + 3.0 * np.arange(h) / h
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    bounds = [parallel.band_rows(h, r, n)[0] for r in range(n)] + [h]
+    for _ in range(6):
+        bounds = parallel.balanced_bounds(bounds, [cum[b] - cum[a] for a, b in zip(bounds, bounds[1:])])
+    ms = np.array([cum[b] - cum[a] for a, b in zip(bounds, bounds[1:])])
+    assert ms.max() / ms.mean() < 1.03
+
+
+class TimedFakeRenderer(FakeRenderer):
+    """A band's cost grows with its rows and with how far down the frame it lies."""
+
+    def __init__(self, rank, world):
+        super().__init__(rank)
+        self.y0, self.y1 = parallel.band_rows(H * 40, rank, world)
+        self.height = H * 40
+        self.frames = 0
+
+    def enable_timing(self, on):
+        self.frames = 0
+
+    def sync(self):
+        pass
+
+    def render(self):
+        self.frames += 1
+
+    def pass_totals(self):
+        ys = np.arange(self.y0, self.y1)
+        ms = float((1.0 + 3.0 * ys / self.height).sum()) * 1e-3
+        return {"visibility_ms": ms * self.frames, "shade_opaque_ms": 0.0, "shade_transmission_ms": 0.0, "tonemap_ms": 0.0}, self.frames
+
+    def set_bands(self, bounds):
+        self.calls.append(("set_bands", tuple(bounds)))
+        self.y0, self.y1 = bounds[self.rank], bounds[self.rank + 1]
+
+
+def _balance_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r = TimedFakeRenderer(rank, world)
+        bounds = parallel.balance_bands(r, lambda: [r.render() for _ in range(3)], rank, world, iterations=5)
+        r.frames = 1
+        out.put((rank, tuple(bounds), r.pass_totals()[0]["visibility_ms"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_balance_bands_agree_and_equalise():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_balance_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(150)
+        assert p.exitcode == 0
+    got = sorted(out.get(timeout=5) for _ in range(2))
+    assert got[0][1] == got[1][1]                      # every rank computed the same boundaries
+    assert got[0][1][1] > (H * 40) // 2                # the cheaper top band grew
+    assert abs(got[0][2] - got[1][2]) / max(got[0][2], got[1][2]) < 0.05

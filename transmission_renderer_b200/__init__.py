@@ -28,7 +28,7 @@ EXPORTS = [
     "tr_read_instance_counts", "tr_read_draws", "tr_read_cluster_aabbs", "tr_read_cluster_lights", "tr_read_hdr",
     "tr_read_hdr_f32", "tr_read_pyramid_level", "tr_read_srgb8", "tr_read_srgb8_async", "tr_wait_readback", "tr_mip_levels", "tr_enable_timing",
     "tr_begin_frame", "tr_read_frame_times", "tr_read_pass_totals", "tr_eval_basic_brdf", "tr_eval_transmission_btdf", "tr_eval_point_light", "tr_eval_ibl_volume_refraction",
-    "tr_comm_unique_id", "tr_comm_init", "tr_comm_destroy", "tr_peer_export", "tr_peer_attach", "tr_device_buffer",
+    "tr_set_bands", "tr_comm_unique_id", "tr_comm_init", "tr_comm_destroy", "tr_peer_export", "tr_peer_attach", "tr_device_buffer",
     "tr_launch_count", "tr_raster_stats", "tr_measure_fp32_peak", "tr_measure_hbm_copy",
 ]
 

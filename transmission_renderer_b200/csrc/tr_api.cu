@@ -418,7 +418,8 @@ int32_t tr_resize(tr_ctx* c, uint32_t width, uint32_t height) {
     c->height = height;
     c->band_y0 = 0;
     c->band_y1 = height;
-    if (c->n_ranks > 1) {  // a rank of a band-sharded frame keeps its share of the new frame
+    c->band_bounds.clear();
+    if (c->n_ranks > 1) {  // a rank of a band-sharded frame keeps its (equal-rows) share of the new frame
         c->band_y0 = (uint32_t)(((uint64_t)c->rank * height) / c->n_ranks);
         c->band_y1 = (uint32_t)(((uint64_t)(c->rank + 1) * height) / c->n_ranks);
     }

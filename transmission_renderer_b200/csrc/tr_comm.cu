@@ -71,6 +71,11 @@ int32_t nccl_fail(const char* what, int rc) {
 }  // namespace
 
 static void band_of(const tr_ctx* c, int r, uint32_t* y0, uint32_t* y1) {
+    if (c->band_bounds.size() == (size_t)c->n_ranks + 1) {  // caller-balanced bands (tr_set_bands)
+        *y0 = c->band_bounds[r];
+        *y1 = c->band_bounds[r + 1];
+        return;
+    }
     *y0 = (uint32_t)(((uint64_t)r * c->height) / c->n_ranks);
     *y1 = (uint32_t)(((uint64_t)(r + 1) * c->height) / c->n_ranks);
 }
@@ -120,7 +125,7 @@ int32_t comm_allgather_opaque(tr_ctx* c) {
     if (c->peers_attached) return comm_barrier(c);
     uint8_t* mip0 = reinterpret_cast<uint8_t*>(c->pyramid.as<uint2>() + c->level_off[0]);
     const size_t row = (size_t)c->width * 8;
-    if (c->height % c->n_ranks == 0) {
+    if (c->band_bounds.empty() && c->height % c->n_ranks == 0) {
         const size_t count = (size_t)(c->height / c->n_ranks) * row;
         int rc = g_nccl.all_gather(mip0 + (size_t)c->rank * count, mip0, count, kNcclUint8, c->nccl_comm, c->stream);
         if (rc) return nccl_fail("ncclAllGather", rc);
@@ -173,6 +178,7 @@ int32_t tr_comm_init(tr_ctx* c, const uint8_t id[TR_NCCL_UNIQUE_ID_BYTES], int32
     TR_CUDA(cudaSetDevice(c->device));
     c->rank = rank;
     c->n_ranks = n_ranks;
+    c->band_bounds.clear();
     uint32_t y0, y1;
     band_of(c, rank, &y0, &y1);
     c->band_y0 = y0;
@@ -193,8 +199,21 @@ int32_t tr_comm_destroy(tr_ctx* c) {
     comm_release(c);
     c->rank = 0;
     c->n_ranks = 1;
+    c->band_bounds.clear();
     c->band_y0 = 0;
     c->band_y1 = c->height;
+    return TR_OK;
+}
+
+int32_t tr_set_bands(tr_ctx* c, const uint32_t* bounds, uint32_t n_bounds) {
+    if (!c || !bounds) return fail(TR_ERR_INVALID_ARG, "tr_set_bands: null");
+    if (n_bounds != (uint32_t)c->n_ranks + 1) return fail(TR_ERR_INVALID_ARG, "tr_set_bands: %u boundaries for %d ranks", n_bounds, c->n_ranks);
+    if (bounds[0] != 0 || bounds[c->n_ranks] != c->height) return fail(TR_ERR_INVALID_ARG, "tr_set_bands: the bands must cover rows [0, %u)", c->height);
+    for (int r = 0; r < c->n_ranks; r++)
+        if (bounds[r] >= bounds[r + 1]) return fail(TR_ERR_INVALID_ARG, "tr_set_bands: band %d is empty", r);
+    c->band_bounds.assign(bounds, bounds + n_bounds);
+    c->band_y0 = bounds[c->rank];
+    c->band_y1 = bounds[c->rank + 1];
     return TR_OK;
 }
 

@@ -81,6 +81,7 @@ struct tr_ctx {
     uint32_t* d_cull_scalars = nullptr;     // [0] n_visible [1] visible triangles [2..5] draw_counts [6,7] ~min/max bits of slot_z
     std::vector<uint32_t> h_prim_tris, h_inst_prim;  // host copies: triangles per primitive, primitive of each instance
     std::vector<uint32_t> h_inst_mat, h_prim_first, h_prim_count;  // material of each instance; index range of each primitive
+    std::vector<uint32_t> band_bounds;  // n_ranks + 1 row boundaries when the caller balances the bands itself (tr_set_bands)
     bool scene_checked = false;  // ids / index ranges validated since the last upload (validate_scene)
     uint64_t max_triangles = 0;                      // upper bound of the visibility work list
     bool tri_bound_valid = false;

@@ -46,3 +46,49 @@ def gather_bands(band, height, rank, world_size, group=None):
         if p.shape[0] != y1 - y0:
             raise ValueError(f"rank {r} sent {p.shape[0]} rows for band [{y0},{y1})")
     return np.concatenate(parts, axis=0)
+
+
+def balanced_bounds(bounds, band_ms, align=8, damping=0.7):
+    """New band boundaries from the measured time of every band.
+
+    `bounds`: the n + 1 current row boundaries, `band_ms`: what each band cost.  The cost is taken as uniform inside a band,
+    which makes the cumulative cost piecewise linear in the row; the new boundaries cut it into n equal parts, moved only
+    `damping` of the way (the cost inside a band is not really uniform) and rounded to `align` rows.  Pure function of its
+    arguments, so every rank computes the same boundaries from the gathered times."""
+    b = np.asarray(bounds, np.float64)
+    t = np.maximum(np.asarray(band_ms, np.float64), 1e-9)
+    n = len(t)
+    cum = np.concatenate([[0.0], np.cumsum(t)])
+    target = cum[-1] * np.arange(1, n) / n
+    new = np.interp(target, cum, b)                       # rows at which the cumulative cost reaches k / n of the total
+    new = b[1:-1] + damping * (new - b[1:-1])
+    new = np.round(new / align) * align
+    out = np.concatenate([[b[0]], new, [b[-1]]]).astype(np.int64)
+    for k in range(1, n):                                 # keep every band at least `align` rows high
+        out[k] = min(max(out[k], out[k - 1] + align), int(b[-1]) - (n - k) * align)
+    return [int(v) for v in out]
+
+
+def balance_bands(renderer, run_frames, rank, world_size, group=None, iterations=4):
+    """Move the band boundaries until every rank's band costs about the same (tr_set_bands).
+
+    Equal-row bands leave the ranks unequal work where coverage, triangle density and light counts vary down the frame — the
+    frame time is the slowest band's.  `run_frames()` renders a few frames with the per-pass timers on; the band-local passes
+    (visibility, both shading passes, tonemap) are the band's cost.  Returns the final boundaries."""
+    import torch.distributed as dist
+    h = renderer.height
+    bounds = [band_rows(h, r, world_size)[0] for r in range(world_size)] + [h]
+    if world_size == 1:
+        return bounds
+    for _ in range(iterations):
+        renderer.enable_timing(True)
+        run_frames()
+        renderer.sync()
+        totals, n = renderer.pass_totals()
+        renderer.enable_timing(False)
+        mine = sum(totals[k] for k in ("visibility_ms", "shade_opaque_ms", "shade_transmission_ms", "tonemap_ms")) / max(n, 1)
+        every = [None] * world_size
+        dist.all_gather_object(every, float(mine), group=group)
+        bounds = balanced_bounds(bounds, every)
+        renderer.set_bands(bounds)
+    return bounds

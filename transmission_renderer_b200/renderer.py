@@ -347,6 +347,11 @@ class Renderer:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         _check(_lib().tr_comm_init(self._ctx, buf, C.c_int32(rank), C.c_int32(n_ranks)))
 
+    def set_bands(self, bounds):
+        """n_ranks + 1 ascending row boundaries, the same on every rank (tr_set_bands)."""
+        a = _c(bounds, np.uint32)
+        _check(_lib().tr_set_bands(self._ctx, _p(a), C.c_uint32(len(a))))
+
     def comm_destroy(self):
         _check(_lib().tr_comm_destroy(self._ctx))
 
