@@ -374,6 +374,9 @@ def run_b200(args, wl):
     if synthetic and (world > 1 or args.views > 1 or args.ray_tracing):
         raise SystemExit("--workload config1 is the single-GPU, single-view synthetic-G-buffer case")
     scene = make_scene(wl)
+    if "instances" in scene:   # the exact #[repr(C)] layout (48-byte Instance), whatever dtype the scene builder concatenated
+        scene["instances"] = np.ascontiguousarray(scene["instances"]).astype(abi.instance)
+        scene["lights"] = np.ascontiguousarray(scene["lights"]).astype(abi.light)
     lut = load_lut()
     cam = scene["camera"]
     stream = torch.cuda.Stream()

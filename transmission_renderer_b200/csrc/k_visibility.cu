@@ -11,12 +11,18 @@
 // tie rule, nearest fragment wins through a 64-bit atomicMax on (depth bits << 32 | ~triangle id)
 // — order independent, hence deterministic —, transmissive layer tested GREATER against the final
 // opaque depth.  Work list = the visible instances' triangles from K1's scan (no host round trip).
-//   pass 1  one thread per triangle; small bounding boxes are rasterised in place, large ones are
-//           cut into 64x64-pixel tiles (conservatively culled against the edges) and queued
-//   pass 2  one warp per queued tile
-//   pass 3  per pixel: re-evaluate the winning triangle, interpolate perspective-correct varyings,
-//           write the SoA G-buffer planes of both layers, and clear the visibility words for the
-//           next frame.
+// Sort-middle, front to back, with a hierarchical Z:
+//   A1 bin_count   one thread per triangle: exact set-up, cull (back face, off band, w <= 0), count into the 64x64-pixel
+//                  tile bins (16 depth buckets per tile and layer), compact the survivors into records
+//   A2 bin_scan    exclusive scan of the bin counts;  tile_order: the tile jobs heaviest first
+//   A3 bin_fill    scatter the survivors into their bins
+//   B  raster_tiles  persistent CTAs, one tile job at a time with the tile's depth/id words in shared memory: rounds of 64
+//                  triangles (fp32 coarse form with proven bounds + exact double form), all threads walk all box pixels,
+//                  survivors evaluated exactly, winners by shared-memory atomicMax, 8x8 block minima refreshed per round
+//   C  resolve     per pixel: the winning triangle's plane, perspective-correct varyings, the SoA G-buffer planes of both
+//                  layers
+// (Tried and dropped, round 2: cutting a long tile list into parts that merge by global atomicMax — every part loses the
+// others' occluders to the hierarchical Z, the pass got 40 % slower.)
 #include <stdlib.h>
 
 #include <algorithm>
@@ -43,6 +49,7 @@ struct VisParams {
     const uint32_t* work_prefix;  // [n_visible + 1]
     const uint32_t* scalars;      // [0] n_visible, [1] total triangles, [6] ~min / [7] max bits of slot_z
     const float* slot_z;          // [n_visible] nearest view depth of the instance in each slot
+    const uint32_t* slot_first;   // [n_visible] first_index of the slot's primitive
     mat4 proj_view;
     float row_y_norm, row_w_norm;  // |rows 1 and 3 of proj_view (xyz)|: how far a unit world offset moves clip y / w
     uint32_t band_cull;            // the band is a strict part of the frame: the work list holds only instances that can reach it
@@ -97,11 +104,16 @@ __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a,
 
 // oracle/raster.c setup_triangle
 template <bool WITH_BOX = true>
+__device__ __forceinline__ bool setup_triangle_at(const VisParams& p, const tr_instance* inst, uint32_t first_index, uint32_t tri, TriSetup& s);
+template <bool WITH_BOX = true>
 __device__ __forceinline__ bool setup_triangle(const VisParams& p, const tr_instance* inst, const tr_primitive_info* prim,
                                                uint32_t tri, TriSetup& s) {
+    return setup_triangle_at<WITH_BOX>(p, inst, __ldg(&prim->first_index), tri, s);
+}
+template <bool WITH_BOX>
+__device__ __forceinline__ bool setup_triangle_at(const VisParams& p, const tr_instance* inst, uint32_t first_index, uint32_t tri, TriSetup& s) {
     const float4* iq = reinterpret_cast<const float4*>(inst);
     const float4 ts = __ldg(iq), rot = __ldg(iq + 1);
-    const uint32_t first_index = __ldg(&prim->first_index);
     uint32_t vid[3];
     float sx[3], sy[3], Z[3], W[3];
     const float half_w = xmul((float)p.width, 0.5f), half_h = xmul((float)p.height, 0.5f);
@@ -935,13 +947,34 @@ struct ResolveRec {
     float scale;
 };
 
-__device__ __forceinline__ void resolve_setup(const VisParams& p, uint32_t gtid, uint32_t n_visible, ResolveRec& r) {
-    const uint32_t slot = find_slot(p, gtid, n_visible);
-    const uint32_t tri = gtid - __ldg(p.work_prefix + slot);
+// The slot of a triangle id: largest slot with work_prefix[slot] <= w.  The CTA keeps every `stride`-th entry of work_prefix
+// in shared memory (RES_COARSE entries), so the search is shared-memory steps plus log2(stride) dependent global loads
+// instead of log2(n_visible) of them.
+constexpr int RES_COARSE = 512;
+__device__ __forceinline__ uint32_t find_slot_coarse(const VisParams& p, const uint32_t* coarse, uint32_t stride, uint32_t n_coarse,
+                                                     uint32_t w, uint32_t n_visible, uint32_t& prefix) {
+    uint32_t lo = 0, hi = n_coarse;   // largest k with coarse[k] <= w (coarse[0] = work_prefix[0] = 0)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (coarse[mid] <= w) lo = mid; else hi = mid;
+    }
+    prefix = coarse[lo];
+    lo *= stride;
+    hi = min(lo + stride, n_visible);
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t v = __ldg(p.work_prefix + mid);
+        if (v <= w) { lo = mid; prefix = v; } else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void resolve_setup(const VisParams& p, uint32_t gtid, uint32_t slot, uint32_t prefix, ResolveRec& r) {
+    const uint32_t tri = gtid - prefix;
+    const uint32_t first_index = __ldg(p.slot_first + slot);   // from K1: no instance -> primitive -> first_index hop
     const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
-    const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
     TriSetup s;
-    setup_triangle<false>(p, inst, prim, tri, s);
+    setup_triangle_at<false>(p, inst, first_index, tri, s);
     const float4 rot = __ldg(reinterpret_cast<const float4*>(inst) + 1);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -1014,8 +1047,11 @@ __global__ void __launch_bounds__(RES_W * RES_H, TR_RESOLVE_CTAS) resolve_kernel
     __shared__ uint32_t s_list[2 * RES_W * RES_H];
     __shared__ uint32_t s_count;
     __shared__ ResolveRec s_rec[RES_CAP];
+    __shared__ uint32_t s_coarse[RES_COARSE];
     const uint32_t n_visible = p.scalars[0];
     const uint32_t tid = threadIdx.x;
+    const uint32_t stride = (n_visible + RES_COARSE - 1) / RES_COARSE, n_coarse = stride ? (n_visible + stride - 1) / stride : 0;
+    for (uint32_t k = tid; k < n_coarse; k += RES_W * RES_H) s_coarse[k] = __ldg(p.work_prefix + k * stride);
     const int px = (int)(blockIdx.x * RES_W + (tid & (RES_W - 1)));
     const int py = (int)(p.y0 + blockIdx.y * RES_H + tid / RES_W);
     const bool inside = px < (int)p.width && py < (int)p.y1;
@@ -1064,7 +1100,11 @@ __global__ void __launch_bounds__(RES_W * RES_H, TR_RESOLVE_CTAS) resolve_kernel
 
     // phase 2: one thread per distinct triangle sets it up (packed into the first warps)
     const uint32_t n_tri = s_count;
-    for (uint32_t t = tid; t < min(n_tri, (uint32_t)RES_CAP); t += RES_W * RES_H) resolve_setup(p, s_list[t], n_visible, s_rec[t]);
+    for (uint32_t t = tid; t < min(n_tri, (uint32_t)RES_CAP); t += RES_W * RES_H) {
+        uint32_t prefix;
+        const uint32_t slot = find_slot_coarse(p, s_coarse, stride, n_coarse, s_list[t], n_visible, prefix);
+        resolve_setup(p, s_list[t], slot, prefix, s_rec[t]);
+    }
     __syncthreads();
 
     // phase 3: per pixel
@@ -1088,7 +1128,9 @@ __global__ void __launch_bounds__(RES_W * RES_H, TR_RESOLVE_CTAS) resolve_kernel
             resolve_write<DERIV>(p, s_rec[idx], layer, i, px, py);
         } else {  // more distinct triangles in this block than records: set this one up privately
             ResolveRec r;
-            resolve_setup(p, gtid[layer], n_visible, r);
+            uint32_t prefix;
+            const uint32_t slot_ = find_slot_coarse(p, s_coarse, stride, n_coarse, gtid[layer], n_visible, prefix);
+            resolve_setup(p, gtid[layer], slot_, prefix, r);
             resolve_write<DERIV>(p, r, layer, i, px, py);
         }
     }
@@ -1169,6 +1211,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.work_prefix = c->work_prefix.as<uint32_t>();
     p.scalars = c->d_cull_scalars;
     p.slot_z = c->slot_z.as<float>();
+    p.slot_first = c->slot_first.as<uint32_t>();
     memcpy(&p.proj_view, &pc.proj_view, sizeof(mat4));
     {
         const float* m = reinterpret_cast<const float*>(&pc.proj_view);  // column-major: element (row r, col k) = m[k * 4 + r]

@@ -376,7 +376,7 @@ int32_t tr_destroy(tr_ctx* c) {
     comm_release(c);
     DevBuf* bufs[] = {&c->instances, &c->primitives, &c->materials, &c->lights, &c->lut, &c->mesh_pos, &c->mesh_nrm,
                       &c->mesh_uv, &c->mesh_idx, &c->visible_ids, &c->cull_scalars, &c->draws[0], &c->draws[1],
-                      &c->draws[2], &c->draws[3], &c->work_prefix, &c->slot_z, &c->cluster_aabbs, &c->cluster_counts,
+                      &c->draws[2], &c->draws[3], &c->work_prefix, &c->slot_z, &c->slot_first, &c->cluster_aabbs, &c->cluster_counts,
                       &c->cluster_indices, &c->vis[0], &c->vis[1], &c->bin_entries, &c->bin_state, &c->tri_records, &c->dev_status, &c->band_list, &c->hdr, &c->hdr_f32, &c->pyramid,
                       &c->srgb8, &c->mip_counter, &c->shade_counter, &c->accel_tlas, &c->accel_blas, &c->accel_inst, &c->accel_tris,
                       &c->shadow_mask[0], &c->shadow_mask[1]};

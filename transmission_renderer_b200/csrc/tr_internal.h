@@ -76,7 +76,7 @@ struct tr_ctx {
     uint32_t n_vertices = 0, n_indices = 0;
 
     // cull outputs (frustum_culling + demultiplex_draws)
-    tr::DevBuf visible_ids, cull_scalars, draws[4], work_prefix, slot_z;
+    tr::DevBuf visible_ids, cull_scalars, draws[4], work_prefix, slot_z, slot_first;
     uint32_t* d_instance_counts = nullptr;  // views into cull_scalars (state block of K1)
     uint32_t* d_cull_scalars = nullptr;     // [0] n_visible [1] visible triangles [2..5] draw_counts [6,7] ~min/max bits of slot_z
     std::vector<uint32_t> h_prim_tris, h_inst_prim;  // host copies: triangles per primitive, primitive of each instance
