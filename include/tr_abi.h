@@ -545,7 +545,7 @@ TR_API int32_t tr_device_buffer(tr_ctx* ctx, int32_t what, void** device_ptr, si
 /* kernels launched by this library in this process so far */
 TR_API int32_t tr_launch_count(uint64_t* out);
 /* rasteriser work since the last reset: [0] box pixels binned to tiles, [1] box pixels left after hierarchical Z,
- * [2] exact (double) coverage evaluations, [3] reserved */
+ * [2] exact (double) coverage evaluations, [3] span pixels (fp32 depth-plane tests) */
 TR_API int32_t tr_raster_stats(tr_ctx* ctx, uint64_t out[4], int32_t reset);
 /* measured roofline denominators on the context's GPU: dependent-FFMA chains / STREAM-style copy */
 TR_API int32_t tr_measure_fp32_peak(tr_ctx* ctx, float* tflops);

@@ -633,10 +633,12 @@ struct TileRecs {
     uint32_t clip_mat[ROUND];  // material id of an alpha-clip triangle, 0xffffffff otherwise
     uint2 entry[ROUND];        // (slot, tri): the alpha test re-reads the triangle's uvs
     uint32_t box[ROUND];   // x_lo | y_lo << 6 | (bw - 1) << 12
-    uint32_t magic[ROUND]; // ceil(2^20 / bw): row of a box sample = (k * magic) >> 20
-    uint32_t off[ROUND + 1];
+    uint32_t off[ROUND + 1];   // exclusive prefix of the clipped boxes' heights: the rows of a round, end to end
+    uint4 span[TILE_THREADS / 32][32];     // per warp: the spans of 32 rows (first sample, first pixel's queue word, depth plane)
+    float span_mg[TILE_THREADS / 32][32];
     uint32_t queue[TILE_THREADS / 32][64];
     uint32_t warp_tot[TILE_THREADS / 32];
+    uint32_t row_ticket;
     float zmin_blk[64];    // hierarchical Z: min depth of each 8x8 pixel block, refreshed after every round
 };
 
@@ -709,11 +711,14 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
     // otherwise every access in the sample loop re-derives its address (S2R + LEA + ...), which costs more than the loads
     uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(&R), keys_s = (uint32_t)__cvta_generic_to_shared(keys);
     uint32_t queue_s = (uint32_t)__cvta_generic_to_shared(queue), lane_p = lane;
+    uint32_t span_s = (uint32_t)__cvta_generic_to_shared(R.span[warp]), span_mg_s = (uint32_t)__cvta_generic_to_shared(R.span_mg[warp]);
+    asm volatile("mov.u32 %0, %0;" : "+r"(span_s));
+    asm volatile("mov.u32 %0, %0;" : "+r"(span_mg_s));
     asm volatile("mov.u32 %0, %0;" : "+r"(recs_s));
     asm volatile("mov.u32 %0, %0;" : "+r"(keys_s));
     asm volatile("mov.u32 %0, %0;" : "+r"(queue_s));
     asm volatile("mov.u32 %0, %0;" : "+r"(lane_p));
-    const uint32_t lt_mask = (1u << lane_p) - 1u;
+    const uint32_t lt_mask = (1u << lane_p) - 1u, le_mask = 0xffffffffu >> (31u - lane_p);
     auto lds_u32 = [](uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
     auto lds_f32 = [](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
     auto sts_u32 = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); };
@@ -736,7 +741,23 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
 
         for (uint32_t round = 0; round < count; round += ROUND) {
             // ---- thread i: set triangle i up, park both forms in shared memory
-            uint32_t n_samples = 0, n_box = 0;
+            uint32_t n_samples = 0, n_box = 0, n_rows = 0;
+            if (tid >= TILE_THREADS / 2 && round) {
+                // the upper half of the CTA meanwhile refreshes the hierarchical Z (min depth of each 8x8 pixel block, two
+                // threads per block) from the depths the previous round left.  The set-up threads may read a block's old or new
+                // minimum: depths only ever move nearer, so either is a valid (conservative) bound.
+                constexpr uint32_t BPR = TS / 8;  // blocks per tile row
+                const uint32_t u = tid - TILE_THREADS / 2, blk = u >> 1, part = u & 1u;
+                float m = __int_as_float(0x7f800000);
+                if (blk < BPR * BPR) {
+                    const uint32_t ox = (blk % BPR) * 8u, oy = (blk / BPR) * 8u + part * 4u;
+#pragma unroll
+                    for (uint32_t k = 0; k < 32; k++)
+                        m = fminf(m, __uint_as_float(reinterpret_cast<const uint32_t*>(keys)[((oy + (k >> 3)) * TS + ox + (k & 7u)) * 2 + 1]));
+                }
+                m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                if (part == 0 && blk < BPR * BPR) R.zmin_blk[blk] = m;
+            }
             if (tid < ROUND && round + tid < count) {
                 const uint2 e = p.bin_entries[begin + round + tid];
                 const tr_instance* inst = p.instances + __ldg(p.visible_ids + e.x);
@@ -749,7 +770,6 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                         const int bw = x_hi - x_lo + 1;
                         n_samples = (uint32_t)(bw * (y_hi - y_lo + 1));
                         R.box[tid] = (uint32_t)x_lo | ((uint32_t)y_lo << 6) | ((uint32_t)(bw - 1) << 12);
-                        R.magic[tid] = (1048576u + (uint32_t)bw - 1u) / (uint32_t)bw;
                         R.gtid[tid] = __ldg(p.work_prefix + e.x) + e.y;
                         if (CLIP) {
                             R.entry[tid] = e;
@@ -803,6 +823,7 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                             for (int bx = x_lo >> 3; bx <= (x_hi >> 3); bx++) zm = fminf(zm, R.zmin_blk[by * (TS / 8) + bx]);
                         n_box = n_samples;
                         if (dmax < zm) n_samples = 0;
+                        else n_rows = (uint32_t)(y_hi - y_lo + 1);
                     }
                 }
             }
@@ -813,8 +834,8 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                     atomicAdd(p.stats + 1, (unsigned long long)b);
                 }
             }
-            // ---- CTA-wide inclusive scan of the box sizes
-            uint32_t incl = n_samples;
+            // ---- CTA-wide inclusive scan of the box heights: the unit of the walk is one pixel row of one clipped box
+            uint32_t incl = n_rows;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -822,106 +843,131 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
             }
             if (lane == 31) R.warp_tot[warp] = incl;
             __syncthreads();
-            uint32_t warp_off = 0, total = 0;
+            uint32_t warp_off = 0, total_rows = 0;
 #pragma unroll
             for (uint32_t k = 0; k < TILE_THREADS / 32; k++) {
                 const uint32_t t = R.warp_tot[k];
                 if (k < warp) warp_off += t;
-                total += t;
+                total_rows += t;
             }
             if (tid < ROUND) R.off[tid + 1] = warp_off + incl;
-            if (tid == 0) R.off[0] = 0;
+            if (tid == 0) {
+                R.off[0] = 0;
+                R.row_ticket = 0;
+            }
             __syncthreads();
 
-            // ---- coarse walk over the pixels of all boxes: warp w takes samples [32 (8 i + w), +32)
-            uint32_t j = 0, j_end = 0, j_off = 0, qn = 0, n_exact = 0;
-            float a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0, t0 = 0, t1 = 0, t2 = 0;
-            float pd0 = 0, pgx = 0, pgy = 0, pmg = 0;
-            uint32_t bx = 0, by = 0, bw = 1, magic = 0;
-            bool first = true;
-            for (uint32_t sbase = warp * 32u; sbase < total; sbase += TILE_THREADS) {
-                const uint32_t sidx = sbase + lane_p;
-                bool survive = false;
-                uint32_t q = 0;
-                if (sidx < total) {
-                    if (first || sidx >= j_end) {
-                        if (first || sidx >= lds_u32(REC(off) + 4u * min(j + 9u, (uint32_t)ROUND))) {  // far jump: binary search
-                            uint32_t lo = first ? 0u : j, hi = ROUND;
-                            while (hi - lo > 1) {
-                                const uint32_t mid = (lo + hi) >> 1;
-                                if (lds_u32(REC(off) + 4u * mid) <= sidx) lo = mid; else hi = mid;
-                            }
-                            j = lo;
-                        } else {
-                            do { j++; } while (sidx >= lds_u32(REC(off) + 4u * (j + 1u)));
+            // ---- the walk.  Each warp takes 32 box rows at a time.  Step 1, one lane per row: the span of the row that passes
+            // the three fp32 edge tests.  fmaf(a, x, v) is monotone in x, so each test holds on a half line and the survivors
+            // of a row are ONE interval; its ends come from a division and are then corrected with the very predicate the
+            // pixels would have been tested with — the span is exactly the set a per-pixel test would keep (half of the box
+            // on average, which the per-pixel walk of round 1 paid for in full).  Step 2, one lane per span pixel (the spans of
+            // the 32 rows laid end to end): conservative depth plane against the tile's current depth, survivors queued.
+            uint32_t qn = 0, n_exact = 0, n_span = 0;
+            while (true) {   // 32 rows at a time, handed out by a ticket: a warp held up by exact evaluations takes fewer
+                uint32_t rbase = 0;
+                if (lane_p == 0) rbase = atomicAdd(&R.row_ticket, 32u);
+                rbase = __shfl_sync(0xffffffffu, rbase, 0);
+                if (rbase >= total_rows) break;
+                const uint32_t r = rbase + lane_p;
+                uint32_t len = 0, q0 = 0;
+                float rowbase = 0.0f, r_gx = 0.0f, r_mg = 0.0f;
+                if (r < total_rows) {
+                    uint32_t lo = 0, hi = ROUND;   // largest j with off[j] <= r
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (lds_u32(REC(off) + 4u * mid) <= r) lo = mid; else hi = mid;
+                    }
+                    const uint32_t j = lo, rj = recs_s + 4u * j;  // field [i][j] sits at offsetof(field) + 4 (ROUND i + j)
+                    const uint32_t box = lds_u32(rj + (uint32_t)offsetof(TileRecs, box));
+                    const uint32_t ly = ((box >> 6) & 63u) + (r - lds_u32(rj + (uint32_t)offsetof(TileRecs, off)));
+                    int x0 = (int)(box & 63u), x1 = x0 + (int)(box >> 12);   // inclusive
+                    const float fy = (float)ly;
+#pragma unroll
+                    for (uint32_t i = 0; i < 3; i++) {
+                        const float a = lds_f32(rj + (uint32_t)offsetof(TileRecs, ea) + 4u * ROUND * i);
+                        const float v = fmaf(lds_f32(rj + (uint32_t)offsetof(TileRecs, eb) + 4u * ROUND * i), fy,
+                                             lds_f32(rj + (uint32_t)offsetof(TileRecs, ec) + 4u * ROUND * i));
+                        const float nt = -lds_f32(rj + (uint32_t)offsetof(TileRecs, ebound) + 4u * ROUND * i);
+                        auto pass = [&](int x) { return !(fmaf(a, (float)x, v) < nt); };   // the per-pixel edge test
+                        if (a > 0.0f) {          // holds for x >= (-t - v) / a
+                            int cand = (int)fminf(fmaxf(ceilf(__fdividef(nt - v, a)), (float)x0), (float)(x1 + 1));
+                            while (cand > x0 && pass(cand - 1)) cand--;
+                            while (cand <= x1 && !pass(cand)) cand++;
+                            x0 = cand;
+                        } else if (a < 0.0f) {   // holds for x <= (-t - v) / a
+                            int cand = (int)fmaxf(fminf(floorf(__fdividef(nt - v, a)), (float)x1), (float)(x0 - 1));
+                            while (cand < x1 && pass(cand + 1)) cand++;
+                            while (cand >= x0 && !pass(cand)) cand--;
+                            x1 = cand;
+                        } else if (a == 0.0f && v < nt) {
+                            x1 = x0 - 1;
                         }
-                        first = false;
-                        const uint32_t rj = recs_s + 4u * j;  // field [i][j] sits at offsetof(field) + 4 (ROUND i + j)
-                        j_end = lds_u32(rj + (uint32_t)offsetof(TileRecs, off) + 4u);
-                        j_off = lds_u32(rj + (uint32_t)offsetof(TileRecs, off));
-                        a0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ea)); a1 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ea) + 4u * ROUND);
-                        a2 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ea) + 8u * ROUND);
-                        b0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, eb)); b1 = lds_f32(rj + (uint32_t)offsetof(TileRecs, eb) + 4u * ROUND);
-                        b2 = lds_f32(rj + (uint32_t)offsetof(TileRecs, eb) + 8u * ROUND);
-                        c0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ec)); c1 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ec) + 4u * ROUND);
-                        c2 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ec) + 8u * ROUND);
-                        t0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ebound)); t1 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ebound) + 4u * ROUND);
-                        t2 = lds_f32(rj + (uint32_t)offsetof(TileRecs, ebound) + 8u * ROUND);
-                        pd0 = lds_f32(rj + (uint32_t)offsetof(TileRecs, d0)); pgx = lds_f32(rj + (uint32_t)offsetof(TileRecs, gx));
-                        pgy = lds_f32(rj + (uint32_t)offsetof(TileRecs, gy)); pmg = lds_f32(rj + (uint32_t)offsetof(TileRecs, margin));
-                        const uint32_t box = lds_u32(rj + (uint32_t)offsetof(TileRecs, box));
-                        magic = lds_u32(rj + (uint32_t)offsetof(TileRecs, magic));
-                        bx = box & 63u;
-                        by = (box >> 6) & 63u;
-                        bw = (box >> 12) + 1u;
                     }
-                    const uint32_t k = sidx - j_off;
-                    const uint32_t ry = (k * magic) >> 20;
-                    const uint32_t lx = bx + (k - ry * bw), ly = by + ry;
-                    const float fx = (float)lx, fy = (float)ly;
-                    const float e0 = fmaf(a0, fx, fmaf(b0, fy, c0));
-                    const float e1 = fmaf(a1, fx, fmaf(b1, fy, c1));
-                    const float e2 = fmaf(a2, fx, fmaf(b2, fy, c2));
-                    if (!(e0 < -t0 || e1 < -t1 || e2 < -t2)) {
-                        const float cur = __uint_as_float(lds_u32(keys_s + (ly * TS + lx) * 8u + 4u));  // depth half of the key
-                        const float dz = fmaf(pgx, fx, fmaf(pgy, fy, pd0));
-                        survive = !(dz + pmg < cur);
-                        q = j | (lx << 8) | (ly << 14);
+                    if (x1 >= x0) {
+                        len = (uint32_t)(x1 - x0 + 1);
+                        q0 = j | ((uint32_t)x0 << 8) | (ly << 14);
+                        rowbase = fmaf(lds_f32(rj + (uint32_t)offsetof(TileRecs, gy)), fy, lds_f32(rj + (uint32_t)offsetof(TileRecs, d0)));
+                        r_gx = lds_f32(rj + (uint32_t)offsetof(TileRecs, gx));
+                        r_mg = lds_f32(rj + (uint32_t)offsetof(TileRecs, margin));
                     }
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, survive);
-                if (survive) sts_u32(queue_s + 4u * (qn + __popc(m & lt_mask)), q);
-                qn += __popc(m);
-                n_exact += __popc(m);
+                uint32_t sincl = len;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, sincl, d);
+                    if (lane >= (uint32_t)d) sincl += o;
+                }
+                const uint32_t excl = sincl - len, total = __shfl_sync(0xffffffffu, sincl, 31);
+                const uint32_t nz = __ballot_sync(0xffffffffu, len != 0u);
+                if (len) {   // the non-empty spans, compacted, in this warp's descriptor table
+                    const uint32_t at = span_s + 16u * (uint32_t)__popc(nz & lt_mask);
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(at), "r"(excl), "r"(q0), "r"(__float_as_uint(rowbase)),
+                                 "r"(__float_as_uint(r_gx)) : "memory");
+                    sts_u32(span_mg_s + 4u * (uint32_t)__popc(nz & lt_mask), __float_as_uint(r_mg));
+                }
                 __syncwarp();
-                if (qn >= 32u) {
-                    const uint32_t mine = lds_u32(queue_s + 4u * lane_p);
-                    const uint32_t spill = lane_p + 32u < qn ? lds_u32(queue_s + 4u * (lane_p + 32u)) : 0u;
+                n_span += total;
+                uint32_t before = 0;   // spans that start before the current window of 32 samples
+                for (uint32_t sb = 0; sb < total; sb += 32u) {
+                    // bit k: a span starts at sample sb + k.  The span of sample sb + lane = before + starts at or below it - 1.
+                    const uint32_t starts = __reduce_or_sync(0xffffffffu, (len != 0u && excl - sb < 32u) ? 1u << (excl - sb) : 0u);
+                    const uint32_t sidx = sb + lane_p;
+                    bool survive = false;
+                    uint32_t q = 0;
+                    if (sidx < total) {
+                        const uint32_t sp = before + (uint32_t)__popc(starts & le_mask) - 1u;
+                        uint32_t d_excl, d_q0, d_base, d_gx;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d_excl), "=r"(d_q0), "=r"(d_base), "=r"(d_gx) : "r"(span_s + 16u * sp));
+                        const float mg = lds_f32(span_mg_s + 4u * sp);
+                        q = d_q0 + ((sidx - d_excl) << 8);
+                        const uint32_t lx = (q >> 8) & 63u, ly = q >> 14;
+                        const float cur = __uint_as_float(lds_u32(keys_s + (ly * TS + lx) * 8u + 4u));  // depth half of the key
+                        const float dz = fmaf(__uint_as_float(d_gx), (float)lx, __uint_as_float(d_base));
+                        survive = !(dz + mg < cur);
+                    }
+                    before += (uint32_t)__popc(starts);
+                    const uint32_t m = __ballot_sync(0xffffffffu, survive);
+                    if (survive) sts_u32(queue_s + 4u * (qn + __popc(m & lt_mask)), q);
+                    qn += __popc(m);
+                    n_exact += __popc(m);
                     __syncwarp();
-                    sts_u32(queue_s + 4u * lane_p, spill);
-                    qn -= 32u;
-                    exact_sample<TS, CLIP>(p, R, keys, mine, tile_x0, tile_y0);
-                    __syncwarp();
+                    if (qn >= 32u) {
+                        const uint32_t mine = lds_u32(queue_s + 4u * lane_p);
+                        const uint32_t spill = lane_p + 32u < qn ? lds_u32(queue_s + 4u * (lane_p + 32u)) : 0u;
+                        __syncwarp();
+                        sts_u32(queue_s + 4u * lane_p, spill);
+                        qn -= 32u;
+                        exact_sample<TS, CLIP>(p, R, keys, mine, tile_x0, tile_y0);
+                        __syncwarp();
+                    }
                 }
+                __syncwarp();   // the descriptor table is rewritten by the next 32 rows
             }
             if (lane_p < qn) exact_sample<TS, CLIP>(p, R, keys, lds_u32(queue_s + 4u * lane_p), tile_x0, tile_y0);
             if (lane == 0 && n_exact) atomicAdd(p.stats + 2, (unsigned long long)n_exact);
+            if (lane == 0 && n_span) atomicAdd(p.stats + 3, (unsigned long long)n_span);
             __syncthreads();  // the records are rewritten by the next round
-            if (round + ROUND < count) {  // refresh the block minima: 4 threads per 8x8 block, 16 pixels each
-                constexpr uint32_t BPR = TS / 8;  // blocks per tile row
-                const uint32_t blk = tid >> 2, part = tid & 3u;
-                float m = __int_as_float(0x7f800000);
-                if (blk < BPR * BPR) {
-                    const uint32_t ox = (blk % BPR) * 8u, oy = (blk / BPR) * 8u + part * 2u;
-#pragma unroll
-                    for (uint32_t k = 0; k < 16; k++)
-                        m = fminf(m, __uint_as_float(reinterpret_cast<const uint32_t*>(keys)[((oy + (k >> 3)) * TS + ox + (k & 7u)) * 2 + 1]));
-                }
-                m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-                m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-                if (part == 0 && blk < BPR * BPR) R.zmin_blk[blk] = m;
-                __syncthreads();
-            }
         }
 
         __syncthreads();

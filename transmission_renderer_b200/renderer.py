@@ -380,7 +380,7 @@ class Renderer:
     def raster_stats(self, reset=True):
         out = (C.c_uint64 * 4)()
         _check(_lib().tr_raster_stats(self._ctx, out, C.c_int32(1 if reset else 0)))
-        return dict(box_pixels=out[0], box_pixels_after_hiz=out[1], exact_evaluations=out[2])
+        return dict(box_pixels=out[0], box_pixels_after_hiz=out[1], exact_evaluations=out[2], span_pixels=out[3])
 
     def measure_fp32_peak(self):
         v = C.c_float(0)
