@@ -69,9 +69,11 @@ struct VisParams {
     uint32_t* bin_start;          // [n_lists + 1]
     uint32_t* bin_cursor;         // [n_lists]
     uint32_t* scan_totals;        // [SCAN_CTAS] slice totals of the scan, zeroed per frame
-    uint2* bin_entries;           // (slot, tri), grouped by list
+    uint32_t* bin_entries;        // record index of each (triangle, list) pair, grouped by list
     uint32_t bin_capacity;
     uint4* records;               // surviving triangles: (slot, tri, tile range, layer)
+    struct TriRec* trirec;        // their set-up, written once by pass A1 and read by passes A3, B and C
+    uint32_t* rec_of_tri;         // [triangles of the work list] record of a surviving triangle (pass C finds the winners by it)
     uint32_t rec_capacity;
     uint32_t* rec_count;
     uint32_t* tile_ticket;
@@ -97,6 +99,46 @@ struct TriSetup {
     uint32_t vid[3];
     int x_lo, x_hi, y_lo, y_hi;
 };
+
+// The set-up of a surviving triangle, 128 bytes, computed ONCE per frame by pass A1 (round 1 recomputed it per (triangle,
+// tile) pair in pass B and per (triangle, 32x8 block) in pass C, each time behind a chain of five dependent gathers).
+struct __align__(16) TriRec {
+    double2 e[4];   // (A0 A1) (A2 B0) (B1 B2) (C0 C1)
+    uint4 c2z;      // C2 (two words), Z0, Z1
+    float4 z2w;     // Z2, W0, W1, W2
+    uint4 ids;      // vid0, vid1, vid2 (set-up order), triangle id in the work list
+    uint4 misc;     // visible slot, x_lo | x_hi << 16, y_lo | y_hi << 16, layer | depth bucket << 1
+};
+static_assert(sizeof(TriRec) == 128, "TriRec");
+
+__device__ __forceinline__ void store_trirec(TriRec* r, const TriSetup& s, uint32_t gtid, uint32_t slot, uint32_t layer) {
+    r->e[0] = make_double2(s.A[0], s.A[1]);
+    r->e[1] = make_double2(s.A[2], s.B[0]);
+    r->e[2] = make_double2(s.B[1], s.B[2]);
+    r->e[3] = make_double2(s.C[0], s.C[1]);
+    r->c2z = make_uint4((uint32_t)__double2loint(s.C[2]), (uint32_t)__double2hiint(s.C[2]), __float_as_uint(s.Z[0]), __float_as_uint(s.Z[1]));
+    r->z2w = make_float4(s.Z[2], s.W[0], s.W[1], s.W[2]);
+    r->ids = make_uint4(s.vid[0], s.vid[1], s.vid[2], gtid);
+    r->misc = make_uint4(slot, (uint32_t)s.x_lo | ((uint32_t)s.x_hi << 16), (uint32_t)s.y_lo | ((uint32_t)s.y_hi << 16), layer);
+}
+// edge functions + box (what binning needs)
+__device__ __forceinline__ void load_trirec_edges(const TriRec* r, TriSetup& s) {
+    const double2 q0 = __ldg(&r->e[0]), q1 = __ldg(&r->e[1]), q2 = __ldg(&r->e[2]), q3 = __ldg(&r->e[3]);
+    const uint4 c = __ldg(&r->c2z), m = __ldg(&r->misc);
+    s.A[0] = q0.x; s.A[1] = q0.y; s.A[2] = q1.x; s.B[0] = q1.y; s.B[1] = q2.x; s.B[2] = q2.y; s.C[0] = q3.x; s.C[1] = q3.y;
+    s.C[2] = __hiloint2double((int)c.y, (int)c.x);
+    s.Z[0] = __uint_as_float(c.z); s.Z[1] = __uint_as_float(c.w);
+    s.x_lo = (int)(m.y & 0xffffu); s.x_hi = (int)(m.y >> 16); s.y_lo = (int)(m.z & 0xffffu); s.y_hi = (int)(m.z >> 16);
+}
+__device__ __forceinline__ void load_trirec(const TriRec* r, TriSetup& s, uint32_t& gtid, uint32_t& slot) {
+    load_trirec_edges(r, s);
+    const float4 z = __ldg(&r->z2w);
+    const uint4 ids = __ldg(&r->ids);
+    s.Z[2] = z.x; s.W[0] = z.y; s.W[1] = z.z; s.W[2] = z.w;
+    s.vid[0] = ids.x; s.vid[1] = ids.y; s.vid[2] = ids.z;
+    gtid = ids.w;
+    slot = __ldg(&r->misc.x);
+}
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
@@ -279,15 +321,6 @@ __device__ __forceinline__ bool tile_may_overlap(const TriSetup& s, int x0, int 
         if (e + margin < 0.0) return false;
     }
     return true;
-}
-
-__device__ __forceinline__ uint32_t find_slot(const VisParams& p, uint32_t w, uint32_t n_visible) {
-    uint32_t lo = 0, hi = n_visible;  // largest slot with work_prefix[slot] <= w
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(p.work_prefix + mid) <= w) lo = mid; else hi = mid;
-    }
-    return lo;
 }
 
 // The bin lists a triangle goes to: every tile of its bounding box, edge-tested when the box spans more than
@@ -474,8 +507,12 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __gri
             first = __shfl_sync(0xffffffffu, first, 0);
             if (keep) {
                 const uint32_t r = first + __popc(mask & ((1u << lane) - 1u));
-                if (r < p.rec_capacity) p.records[r] = make_uint4(slot, tri, range, layer);
-                else atomicOr(p.status, 1u);
+                if (r < p.rec_capacity) {
+                    p.records[r] = make_uint4(slot, tri, range, layer);
+                    const uint32_t gtid = __ldg(p.work_prefix + slot) + tri;
+                    store_trirec(p.trirec + r, s, gtid, slot, layer);
+                    p.rec_of_tri[gtid] = r;
+                } else atomicOr(p.status, 1u);
             }
         }
     }
@@ -593,22 +630,18 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_fill_kernel(const __grid
         if (keep) {
             rec = p.records[r];
             const int tx0 = rec.z & 0xff, tx1 = (rec.z >> 8) & 0xff, ty0 = (rec.z >> 16) & 0xff, ty1 = rec.z >> 24;
-            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4) {  // the edge test needs the set-up again (large triangles only)
-                const tr_instance* inst = p.instances + __ldg(p.visible_ids + rec.x);
-                const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
-                setup_triangle(p, inst, prim, rec.y, s);
-            }
+            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4) load_trirec_edges(p.trirec + r, s);  // the edge test of large triangles
         }
-        bin_triangle(p, keep, s, rec.z, rec.w, make_uint2(rec.x, rec.y), [&](uint32_t list, uint2 slot_tri) {
+        bin_triangle(p, keep, s, rec.z, rec.w, make_uint2(r, 0u), [&](uint32_t list, uint2 pl) {
             const uint32_t pos = atomicAdd(p.bin_cursor + list, 1u);
-            if (pos < p.bin_capacity) p.bin_entries[pos] = slot_tri;
-        }, [&](uint32_t list, uint2 slot_tri, uint32_t peers) {
+            if (pos < p.bin_capacity) p.bin_entries[pos] = pl.x;
+        }, [&](uint32_t list, uint2 pl, uint32_t peers) {
             const int leader = __ffs(peers) - 1;
             uint32_t first = 0;
             if ((int)lane == leader) first = atomicAdd(p.bin_cursor + list, (uint32_t)__popc(peers));
             first = __shfl_sync(peers, first, leader);
             const uint32_t pos = first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-            if (pos < p.bin_capacity) p.bin_entries[pos] = slot_tri;
+            if (pos < p.bin_capacity) p.bin_entries[pos] = pl.x;
         });
     }
 }
@@ -759,20 +792,22 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                 if (part == 0 && blk < BPR * BPR) R.zmin_blk[blk] = m;
             }
             if (tid < ROUND && round + tid < count) {
-                const uint2 e = p.bin_entries[begin + round + tid];
-                const tr_instance* inst = p.instances + __ldg(p.visible_ids + e.x);
-                const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+                const uint32_t e = p.bin_entries[begin + round + tid];
                 TriSetup s;
-                if (setup_triangle(p, inst, prim, e.y, s)) {
+                uint32_t rec_gtid, rec_slot;
+                load_trirec(p.trirec + e, s, rec_gtid, rec_slot);
+                {
                     const int x_lo = max(s.x_lo, tile_x0) - tile_x0, x_hi = min(s.x_hi, tile_x0 + TS - 1) - tile_x0;
                     const int y_lo = max(s.y_lo, tile_y0) - tile_y0, y_hi = min(s.y_hi, tile_y0 + TS - 1) - tile_y0;
                     if (x_lo <= x_hi && y_lo <= y_hi) {
                         const int bw = x_hi - x_lo + 1;
                         n_samples = (uint32_t)(bw * (y_hi - y_lo + 1));
                         R.box[tid] = (uint32_t)x_lo | ((uint32_t)y_lo << 6) | ((uint32_t)(bw - 1) << 12);
-                        R.gtid[tid] = __ldg(p.work_prefix + e.x) + e.y;
+                        R.gtid[tid] = rec_gtid;
                         if (CLIP) {
-                            R.entry[tid] = e;
+                            const tr_instance* inst = p.instances + __ldg(p.visible_ids + rec_slot);
+                            const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+                            R.entry[tid] = make_uint2(rec_slot, rec_gtid - __ldg(p.work_prefix + rec_slot));
                             R.clip_mat[tid] = (__ldg(&prim->draw_buffer_index) & 1u) ? __ldg(&inst->material_id) : 0xffffffffu;
                         }
                         const double X0 = (double)tile_x0 + 0.5, Y0 = (double)tile_y0 + 0.5;
@@ -993,34 +1028,11 @@ struct ResolveRec {
     float scale;
 };
 
-// The slot of a triangle id: largest slot with work_prefix[slot] <= w.  The CTA keeps every `stride`-th entry of work_prefix
-// in shared memory (RES_COARSE entries), so the search is shared-memory steps plus log2(stride) dependent global loads
-// instead of log2(n_visible) of them.
-constexpr int RES_COARSE = 512;
-__device__ __forceinline__ uint32_t find_slot_coarse(const VisParams& p, const uint32_t* coarse, uint32_t stride, uint32_t n_coarse,
-                                                     uint32_t w, uint32_t n_visible, uint32_t& prefix) {
-    uint32_t lo = 0, hi = n_coarse;   // largest k with coarse[k] <= w (coarse[0] = work_prefix[0] = 0)
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (coarse[mid] <= w) lo = mid; else hi = mid;
-    }
-    prefix = coarse[lo];
-    lo *= stride;
-    hi = min(lo + stride, n_visible);
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        const uint32_t v = __ldg(p.work_prefix + mid);
-        if (v <= w) { lo = mid; prefix = v; } else hi = mid;
-    }
-    return lo;
-}
-
-__device__ __forceinline__ void resolve_setup(const VisParams& p, uint32_t gtid, uint32_t slot, uint32_t prefix, ResolveRec& r) {
-    const uint32_t tri = gtid - prefix;
-    const uint32_t first_index = __ldg(p.slot_first + slot);   // from K1: no instance -> primitive -> first_index hop
-    const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
+__device__ __forceinline__ void resolve_setup(const VisParams& p, uint32_t gtid, ResolveRec& r) {
     TriSetup s;
-    setup_triangle_at<false>(p, inst, first_index, tri, s);
+    uint32_t rec_gtid, slot;
+    load_trirec(p.trirec + __ldg(p.rec_of_tri + gtid), s, rec_gtid, slot);   // pass A1's set-up of this triangle
+    const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
     const float4 rot = __ldg(reinterpret_cast<const float4*>(inst) + 1);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -1093,11 +1105,7 @@ __global__ void __launch_bounds__(RES_W * RES_H, TR_RESOLVE_CTAS) resolve_kernel
     __shared__ uint32_t s_list[2 * RES_W * RES_H];
     __shared__ uint32_t s_count;
     __shared__ ResolveRec s_rec[RES_CAP];
-    __shared__ uint32_t s_coarse[RES_COARSE];
-    const uint32_t n_visible = p.scalars[0];
     const uint32_t tid = threadIdx.x;
-    const uint32_t stride = (n_visible + RES_COARSE - 1) / RES_COARSE, n_coarse = stride ? (n_visible + stride - 1) / stride : 0;
-    for (uint32_t k = tid; k < n_coarse; k += RES_W * RES_H) s_coarse[k] = __ldg(p.work_prefix + k * stride);
     const int px = (int)(blockIdx.x * RES_W + (tid & (RES_W - 1)));
     const int py = (int)(p.y0 + blockIdx.y * RES_H + tid / RES_W);
     const bool inside = px < (int)p.width && py < (int)p.y1;
@@ -1146,11 +1154,7 @@ __global__ void __launch_bounds__(RES_W * RES_H, TR_RESOLVE_CTAS) resolve_kernel
 
     // phase 2: one thread per distinct triangle sets it up (packed into the first warps)
     const uint32_t n_tri = s_count;
-    for (uint32_t t = tid; t < min(n_tri, (uint32_t)RES_CAP); t += RES_W * RES_H) {
-        uint32_t prefix;
-        const uint32_t slot = find_slot_coarse(p, s_coarse, stride, n_coarse, s_list[t], n_visible, prefix);
-        resolve_setup(p, s_list[t], slot, prefix, s_rec[t]);
-    }
+    for (uint32_t t = tid; t < min(n_tri, (uint32_t)RES_CAP); t += RES_W * RES_H) resolve_setup(p, s_list[t], s_rec[t]);
     __syncthreads();
 
     // phase 3: per pixel
@@ -1174,9 +1178,7 @@ __global__ void __launch_bounds__(RES_W * RES_H, TR_RESOLVE_CTAS) resolve_kernel
             resolve_write<DERIV>(p, s_rec[idx], layer, i, px, py);
         } else {  // more distinct triangles in this block than records: set this one up privately
             ResolveRec r;
-            uint32_t prefix;
-            const uint32_t slot_ = find_slot_coarse(p, s_coarse, stride, n_coarse, gtid[layer], n_visible, prefix);
-            resolve_setup(p, gtid[layer], slot_, prefix, r);
+            resolve_setup(p, gtid[layer], r);
             resolve_write<DERIV>(p, r, layer, i, px, py);
         }
     }
@@ -1222,8 +1224,9 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     // by every read-back entry point, never silently accepted
     p.bin_capacity = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(BIN_CAPACITY, 6 * c->max_triangles + 64ull * p.n_tiles), 1ull << 27);
     p.rec_capacity = (uint32_t)(c->max_triangles ? c->max_triangles : 1);
-    TR_TRY(c->bin_entries.ensure((size_t)p.bin_capacity * sizeof(uint2)));
-    TR_TRY(c->tri_records.ensure((size_t)p.rec_capacity * sizeof(uint4)));
+    TR_TRY(c->bin_entries.ensure((size_t)p.bin_capacity * sizeof(uint32_t)));
+    // per surviving triangle: the 16-byte binning record, the 128-byte set-up, and the work-list id -> record map
+    TR_TRY(c->tri_records.ensure((size_t)p.rec_capacity * (sizeof(uint4) + sizeof(TriRec) + sizeof(uint32_t))));
     // state block: [bin_count L][rec_count, ticket, pad, pad][bin_start L+1][bin_cursor L]; the first two parts are zeroed per frame
     const size_t n_lists = (size_t)2 * p.n_tiles * DEPTH_BUCKETS;
     p.n_lists = (uint32_t)n_lists;
@@ -1242,8 +1245,10 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.bin_start = st + n_lists + 4 + 32;
     p.bin_cursor = p.bin_start + n_lists + 4;  // keeps 16-byte alignment (n_lists is a multiple of 16)
     p.tile_order = p.bin_cursor + n_lists;
-    p.bin_entries = c->bin_entries.as<uint2>();
-    p.records = c->tri_records.as<uint4>();
+    p.bin_entries = c->bin_entries.as<uint32_t>();
+    p.trirec = c->tri_records.as<TriRec>();
+    p.records = reinterpret_cast<uint4*>(p.trirec + p.rec_capacity);
+    p.rec_of_tri = reinterpret_cast<uint32_t*>(p.records + p.rec_capacity);
     p.status = c->dev_status.as<uint32_t>();
     p.stats = reinterpret_cast<unsigned long long*>(c->dev_status.as<unsigned char>() + 16);
 
