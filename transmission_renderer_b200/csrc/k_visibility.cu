@@ -49,7 +49,7 @@ struct VisParams {
     const uint32_t* work_prefix;  // [n_visible + 1]
     const uint32_t* scalars;      // [0] n_visible, [1] total triangles, [6] ~min / [7] max bits of slot_z
     const float* slot_z;          // [n_visible] nearest view depth of the instance in each slot
-    const uint32_t* slot_first;   // [n_visible] first_index of the slot's primitive
+    const uint2* slot_prim;       // [n_visible] (first_index, draw_buffer_index) of the slot's primitive, from K1
     mat4 proj_view;
     float row_y_norm, row_w_norm;  // |rows 1 and 3 of proj_view (xyz)|: how far a unit world offset moves clip y / w
     uint32_t band_cull;            // the band is a strict part of the frame: the work list holds only instances that can reach it
@@ -146,13 +146,6 @@ __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a,
 
 // oracle/raster.c setup_triangle
 template <bool WITH_BOX = true>
-__device__ __forceinline__ bool setup_triangle_at(const VisParams& p, const tr_instance* inst, uint32_t first_index, uint32_t tri, TriSetup& s);
-template <bool WITH_BOX = true>
-__device__ __forceinline__ bool setup_triangle(const VisParams& p, const tr_instance* inst, const tr_primitive_info* prim,
-                                               uint32_t tri, TriSetup& s) {
-    return setup_triangle_at<WITH_BOX>(p, inst, __ldg(&prim->first_index), tri, s);
-}
-template <bool WITH_BOX>
 __device__ __forceinline__ bool setup_triangle_at(const VisParams& p, const tr_instance* inst, uint32_t first_index, uint32_t tri, TriSetup& s) {
     const float4* iq = reinterpret_cast<const float4*>(inst);
     const float4 ts = __ldg(iq), rot = __ldg(iq + 1);
@@ -476,20 +469,33 @@ __global__ void __launch_bounds__(1024) band_filter_kernel(const __grid_constant
 __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __grid_constant__ VisParams p) {
     const uint32_t n_list = p.list_scalars[0], total = p.list_scalars[1];
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < total; base += gridDim.x * blockDim.x) {
+    // a CTA takes a contiguous range of the work list, so that (i) a warp's next 32 triangles are 256 further on and the list
+    // entry is found by walking on from the last one, (ii) the records of neighbouring triangles lie together in memory —
+    // a tile's bin list is mostly runs of neighbouring triangles, and pass B gathers their records
+    const uint32_t per = ((total + gridDim.x - 1) / gridDim.x + 255u) & ~255u;
+    const uint32_t range_begin = blockIdx.x * per, range_end = min(range_begin + per, total);
+    uint32_t entry = 0;
+    bool have_entry = false;
+    for (uint32_t base = range_begin + (threadIdx.x & ~31u); base < range_end; base += 256u) {
         const uint32_t w = base + lane;
         bool keep = false;
         uint32_t slot = 0, tri = 0, range = 0, layer = 0;
         TriSetup s{};
-        const uint32_t entry = find_entry_warp(p.list_prefix, base, min(w, total - 1), n_list);
+        if (!have_entry) {
+            entry = find_entry_warp(p.list_prefix, base, min(w, total - 1), n_list);
+            have_entry = true;
+        } else {   // the warp's previous triangles were 256 before these
+            const uint32_t wc = min(w, total - 1);
+            while (entry + 1 < n_list && __ldg(p.list_prefix + entry + 1) <= wc) entry++;
+        }
         if (w < total) {
             slot = p.list_slots ? __ldg(p.list_slots + entry) : entry;
             tri = w - __ldg(p.list_prefix + entry);
             const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
-            const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
-            const uint32_t bucket = __ldg(&prim->draw_buffer_index);
+            const uint2 prim = __ldg(p.slot_prim + slot);
+            const uint32_t bucket = prim.y;
             layer = bucket >> 1;  // draw buffers 0/1 (opaque, alpha clip) -> layer 0, 2/3 -> the transmissive layer
-            if (bucket < 4u && setup_triangle(p, inst, prim, tri, s)) {
+            if (bucket < 4u && setup_triangle_at<true>(p, inst, prim.x, tri, s)) {
                 keep = true;
                 layer |= depth_bucket(p, slot) << 1;  // layer | depth bucket << 1 travels with the record
                 range = (uint32_t)(s.x_lo / p.ts) | ((uint32_t)(s.x_hi / p.ts) << 8) |
@@ -656,6 +662,12 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_fill_kernel(const __grid
 #ifndef TR_ROUND
 #define TR_ROUND 64
 #endif
+#ifndef TR_PREFETCH
+#define TR_PREFETCH 1
+#endif
+#ifndef TR_TAIL_ROWS
+#define TR_TAIL_ROWS 256
+#endif
 constexpr int ROUND = TR_ROUND;  // triangles per round (<= TILE_THREADS); smaller rounds refresh the hierarchical Z more often
 struct TileRecs {
     double A[3][ROUND], B[3][ROUND], C[3][ROUND];
@@ -672,7 +684,7 @@ struct TileRecs {
     uint32_t queue[TILE_THREADS / 32][64];
     uint32_t warp_tot[TILE_THREADS / 32];
     uint32_t row_ticket;
-    float zmin_blk[64];    // hierarchical Z: min depth of each 8x8 pixel block, refreshed after every round
+    __align__(16) float zmin_blk[64];    // hierarchical Z: min depth of each 8x8 pixel block, refreshed after every round
 };
 
 // depth_pre_pass_alpha_clip (shader/src/lib.rs:269-293): diffuse alpha (factor x texture, implicit level of detail from
@@ -757,6 +769,12 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
     auto sts_u32 = [](uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); };
 #define REC(field) (recs_s + (uint32_t)offsetof(TileRecs, field))
 
+#if TR_PHASE_CLOCKS   // experiments: where a CTA's cycles go (warp 0 = a set-up warp, warp 7 = a walker)
+    long long ck_setup = 0, ck_scan = 0, ck_walk = 0, ck_tail = 0, ck_job = 0, ck_t = clock64(), ck_rounds = 0, ck_a = 0, ck_b = 0, ck_c = 0, ck_d = 0;
+#define CK(acc) { const long long t_ = clock64(); acc += t_ - ck_t; ck_t = t_; }
+#else
+#define CK(acc)
+#endif
     while (true) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(p.tile_ticket, 1u);
@@ -772,30 +790,44 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
         const uint32_t begin = min(p.bin_start[item * DEPTH_BUCKETS], p.bin_capacity), end = min(p.bin_start[(item + 1) * DEPTH_BUCKETS], p.bin_capacity);
         const uint32_t count = end - begin;
 
+        uint32_t e_next = 0;   // this thread's entry of the coming round
+        if (tid < ROUND && tid < count) e_next = p.bin_entries[begin + tid];
+        CK(ck_job)
         for (uint32_t round = 0; round < count; round += ROUND) {
+#if TR_PHASE_CLOCKS
+            ck_rounds++;
+#endif
             // ---- thread i: set triangle i up, park both forms in shared memory
             uint32_t n_samples = 0, n_box = 0, n_rows = 0;
             if (tid >= TILE_THREADS / 2 && round) {
-                // the upper half of the CTA meanwhile refreshes the hierarchical Z (min depth of each 8x8 pixel block, two
-                // threads per block) from the depths the previous round left.  The set-up threads may read a block's old or new
-                // minimum: depths only ever move nearer, so either is a valid (conservative) bound.
-                constexpr uint32_t BPR = TS / 8;  // blocks per tile row
-                const uint32_t u = tid - TILE_THREADS / 2, blk = u >> 1, part = u & 1u;
-                float m = __int_as_float(0x7f800000);
-                if (blk < BPR * BPR) {
-                    const uint32_t ox = (blk % BPR) * 8u, oy = (blk / BPR) * 8u + part * 4u;
+                // the upper half of the CTA meanwhile refreshes the hierarchical Z (min depth of each 8x8 pixel block) from the
+                // depths the previous round left.  The set-up threads may read a block's old or new minimum: depths only ever
+                // move nearer, so either is a valid (conservative) bound.  A warp reads 32 consecutive keys of a pixel row with
+                // one 64-bit load per lane (conflict-free; the depth words alone sit on 16 banks), eight rows deep, and
+                // the minimum of every eight lanes is one block's.
+                constexpr uint32_t HALVES = TS / 32, UNITS = (TS / 8) * HALVES;   // a unit: 32 pixels x 8 rows = 4 blocks
+                for (uint32_t unit = warp - TILE_THREADS / 64; unit < UNITS; unit += TILE_THREADS / 64) {
+                    const uint32_t by = unit / HALVES, half = unit % HALVES;
+                    float m = __int_as_float(0x7f800000);
 #pragma unroll
-                    for (uint32_t k = 0; k < 32; k++)
-                        m = fminf(m, __uint_as_float(reinterpret_cast<const uint32_t*>(keys)[((oy + (k >> 3)) * TS + ox + (k & 7u)) * 2 + 1]));
+                    for (uint32_t k = 0; k < 8; k++) m = fminf(m, __uint_as_float((uint32_t)(keys[(by * 8u + k) * TS + half * 32u + lane] >> 32)));
+                    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                    if ((lane & 7u) == 0u) R.zmin_blk[by * (TS / 8) + half * 4u + (lane >> 3)] = m;
                 }
-                m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-                if (part == 0 && blk < BPR * BPR) R.zmin_blk[blk] = m;
+                CK(ck_a)
             }
             if (tid < ROUND && round + tid < count) {
-                const uint32_t e = p.bin_entries[begin + round + tid];
+                const uint32_t e = e_next;
+                if (round + ROUND + tid < count) e_next = p.bin_entries[begin + round + ROUND + tid];
                 TriSetup s;
                 uint32_t rec_gtid, rec_slot;
                 load_trirec(p.trirec + e, s, rec_gtid, rec_slot);
+#if TR_PHASE_CLOCKS
+                if (s.x_lo + s.y_lo + (int)rec_gtid + (int)__double2loint(s.A[0]) + (int)__float_as_uint(s.W[2]) == -12345) ck_rounds++;
+                CK(ck_a)
+#endif
                 {
                     const int x_lo = max(s.x_lo, tile_x0) - tile_x0, x_hi = min(s.x_hi, tile_x0 + TS - 1) - tile_x0;
                     const int y_lo = max(s.y_lo, tile_y0) - tile_y0, y_hi = min(s.y_hi, tile_y0 + TS - 1) - tile_y0;
@@ -851,12 +883,32 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                         R.gx[tid] = gx;
                         R.gy[tid] = gy;
                         R.margin[tid] = mg;
+#if TR_PHASE_CLOCKS
+                        if (mg == -12345.0f) ck_rounds++;
+                        CK(ck_b)
+#endif
                         // hierarchical Z: the whole clipped box is behind what the tile already holds
                         const float dmax = d0 + fmaxf(gx * (float)x_lo, gx * (float)x_hi) + fmaxf(gy * (float)y_lo, gy * (float)y_hi) + mg;
                         float zm = __int_as_float(0x7f800000);
-                        for (int by = y_lo >> 3; by <= (y_hi >> 3); by++)
-                            for (int bx = x_lo >> 3; bx <= (x_hi >> 3); bx++) zm = fminf(zm, R.zmin_blk[by * (TS / 8) + bx]);
+                        {   // min over the blocks the clipped box touches: whole block rows at a time (four blocks per load)
+                            const int bx0 = x_lo >> 3, bx1 = x_hi >> 3;
+                            for (int by = y_lo >> 3; by <= (y_hi >> 3); by++) {
+#pragma unroll
+                                for (int g = 0; g < TS / 32; g++) {
+                                    if (bx1 < 4 * g || bx0 > 4 * g + 3) continue;
+                                    const float4 z4 = *reinterpret_cast<const float4*>(&R.zmin_blk[by * (TS / 8) + 4 * g]);
+                                    if (bx0 <= 4 * g && 4 * g <= bx1) zm = fminf(zm, z4.x);
+                                    if (bx0 <= 4 * g + 1 && 4 * g + 1 <= bx1) zm = fminf(zm, z4.y);
+                                    if (bx0 <= 4 * g + 2 && 4 * g + 2 <= bx1) zm = fminf(zm, z4.z);
+                                    if (bx0 <= 4 * g + 3 && 4 * g + 3 <= bx1) zm = fminf(zm, z4.w);
+                                }
+                            }
+                        }
                         n_box = n_samples;
+#if TR_PHASE_CLOCKS
+                        if (zm == -12345.0f) ck_rounds++;
+                        CK(ck_c)
+#endif
                         if (dmax < zm) n_samples = 0;
                         else n_rows = (uint32_t)(y_hi - y_lo + 1);
                     }
@@ -877,7 +929,19 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                 if (lane >= (uint32_t)d) incl += o;
             }
             if (lane == 31) R.warp_tot[warp] = incl;
+#if TR_PREFETCH
+            // the coming round's records are pulled towards the SM while this round is walked: the set-up is 64 threads behind a
+            // 128-byte gather, and the other six warps of the CTA wait for it
+            if (tid < ROUND && round + ROUND + tid < count) {
+#if TR_PREFETCH == 1
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.trirec + e_next));
+#else
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.trirec + e_next));
+#endif
+            }
+#endif
             __syncthreads();
+            CK(ck_setup)
             uint32_t warp_off = 0, total_rows = 0;
 #pragma unroll
             for (uint32_t k = 0; k < TILE_THREADS / 32; k++) {
@@ -891,6 +955,7 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                 R.row_ticket = 0;
             }
             __syncthreads();
+            CK(ck_scan)
 
             // ---- the walk.  Each warp takes 32 box rows at a time.  Step 1, one lane per row: the span of the row that passes
             // the three fp32 edge tests.  fmaf(a, x, v) is monotone in x, so each test holds on a half line and the survivors
@@ -900,14 +965,18 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
             // the 32 rows laid end to end): conservative depth plane against the tile's current depth, survivors queued.
             uint32_t qn = 0, n_exact = 0, n_span = 0;
             while (true) {   // 32 rows at a time, handed out by a ticket: a warp held up by exact evaluations takes fewer
-                uint32_t rbase = 0;
-                if (lane_p == 0) rbase = atomicAdd(&R.row_ticket, 32u);
-                rbase = __shfl_sync(0xffffffffu, rbase, 0);
+                uint32_t ticket = 0;
+                if (lane_p == 0) ticket = atomicAdd(&R.row_ticket, 1u);
+                ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                // 32 rows per ticket, 16 over the last TR_TAIL_ROWS rows of the round: the round ends when its slowest warp does
+                const uint32_t full = total_rows > TR_TAIL_ROWS ? (total_rows - TR_TAIL_ROWS + 31u) >> 5 : 0u;
+                const uint32_t rbase = ticket < full ? ticket * 32u : full * 32u + (ticket - full) * 16u;
+                const uint32_t rend = min(rbase + (ticket < full ? 32u : 16u), total_rows);
                 if (rbase >= total_rows) break;
                 const uint32_t r = rbase + lane_p;
                 uint32_t len = 0, q0 = 0;
                 float rowbase = 0.0f, r_gx = 0.0f, r_mg = 0.0f;
-                if (r < total_rows) {
+                if (r < rend) {
                     uint32_t lo = 0, hi = ROUND;   // largest j with off[j] <= r
                     while (hi - lo > 1) {
                         const uint32_t mid = (lo + hi) >> 1;
@@ -1002,7 +1071,9 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
             if (lane_p < qn) exact_sample<TS, CLIP>(p, R, keys, lds_u32(queue_s + 4u * lane_p), tile_x0, tile_y0);
             if (lane == 0 && n_exact) atomicAdd(p.stats + 2, (unsigned long long)n_exact);
             if (lane == 0 && n_span) atomicAdd(p.stats + 3, (unsigned long long)n_span);
+            CK(ck_walk)
             __syncthreads();  // the records are rewritten by the next round
+            CK(ck_tail)
         }
 
         __syncthreads();
@@ -1012,6 +1083,12 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
             if (px < (int)p.width && py >= (int)p.y0 && py < (int)p.y1) out[(size_t)py * p.width + px] = keys[i];
         }
     }
+#if TR_PHASE_CLOCKS
+    CK(ck_job)
+    if ((blockIdx.x == 0 || blockIdx.x == 300) && (tid == 0 || tid == 224))
+        printf("cta %u warp %u: rounds %lld setup %lld scan %lld walk %lld tail %lld job-overhead %lld | load/refresh %lld math %lld hiz %lld\n", blockIdx.x, warp, ck_rounds, ck_setup, ck_scan,
+               ck_walk, ck_tail, ck_job, ck_a, ck_b, ck_c);
+#endif
 }
 
 // ---- pass C: resolve.  One CTA per 32x8 pixel block, both layers.  The block's distinct winning triangles (a few
@@ -1096,7 +1173,7 @@ __device__ __forceinline__ void resolve_write(const VisParams& p, const ResolveR
 }
 
 #ifndef TR_RESOLVE_CTAS
-#define TR_RESOLVE_CTAS 5
+#define TR_RESOLVE_CTAS 6
 #endif
 template <bool DERIV>
 __global__ void __launch_bounds__(RES_W * RES_H, TR_RESOLVE_CTAS) resolve_kernel(const __grid_constant__ VisParams p) {
@@ -1262,7 +1339,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.work_prefix = c->work_prefix.as<uint32_t>();
     p.scalars = c->d_cull_scalars;
     p.slot_z = c->slot_z.as<float>();
-    p.slot_first = c->slot_first.as<uint32_t>();
+    p.slot_prim = c->slot_first.as<uint2>();
     memcpy(&p.proj_view, &pc.proj_view, sizeof(mat4));
     {
         const float* m = reinterpret_cast<const float*>(&pc.proj_view);  // column-major: element (row r, col k) = m[k * 4 + r]
