@@ -77,7 +77,9 @@ struct VisParams {
     uint32_t rec_capacity;
     uint32_t* rec_count;
     uint32_t* tile_ticket;
-    uint32_t* tile_order;         // [2 * n_tiles] (layer, tile) jobs, heaviest first (tile_order_kernel)
+    uint32_t* tile_order;         // [8 * n_tiles] tile jobs, heaviest first (tile_order_kernel)
+    uint32_t* n_jobs;             // how many of them
+    uint32_t split;               // heavy tiles may be handed out as four quadrant jobs (few tiles for the GPU)
     uint32_t* status;             // bit 0: record overflow, bit 1: bin overflow
     unsigned long long* stats;    // diagnostics: [0] box pixels binned, [1] box pixels after hierarchical Z, [2] exact evaluations
     // resolve outputs
@@ -419,18 +421,24 @@ __global__ void __launch_bounds__(1024) band_filter_kernel(const __grid_constant
     const uint32_t n_visible = p.scalars[0], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (uint32_t chunk = 0; chunk < n_visible; chunk += 1024) {
-        const uint32_t slot = chunk + tid;
-        bool on = false;
-        uint32_t tris = 0;
-        if (slot < n_visible) {
-            const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
-            const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
-            on = instance_on_band(p, inst, prim);
-            if (on) tris = __ldg(p.work_prefix + slot + 1) - __ldg(p.work_prefix + slot);
+    constexpr uint32_t PER = 4;   // consecutive slots per thread: their gathers are in flight together
+    for (uint32_t chunk = 0; chunk < n_visible; chunk += 1024 * PER) {
+        unsigned long long v[PER], mine = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) {
+            const uint32_t slot = chunk + tid * PER + k;
+            bool on = false;
+            uint32_t tris = 0;
+            if (slot < n_visible) {
+                const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
+                const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
+                on = instance_on_band(p, inst, prim);
+                if (on) tris = __ldg(p.work_prefix + slot + 1) - __ldg(p.work_prefix + slot);
+            }
+            v[k] = ((unsigned long long)tris << 24) | (on ? 1ull : 0ull);
+            mine += v[k];
         }
-        const unsigned long long v = ((unsigned long long)tris << 24) | (on ? 1ull : 0ull);
-        unsigned long long incl = v;
+        unsigned long long incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -443,11 +451,15 @@ __global__ void __launch_bounds__(1024) band_filter_kernel(const __grid_constant
             if (k < warp) off += s_warp[k];
             tot += s_warp[k];
         }
-        const unsigned long long excl = off + incl - v;
-        if (on) {
-            const uint32_t k = (uint32_t)(excl & 0xffffffull);
-            p.band_slots[k] = slot;
-            p.band_prefix[k] = (uint32_t)(excl >> 24);
+        unsigned long long excl = off + incl - mine;
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) {
+            if (v[k] & 1ull) {
+                const uint32_t at = (uint32_t)(excl & 0xffffffull);
+                p.band_slots[at] = chunk + tid * PER + k;
+                p.band_prefix[at] = (uint32_t)(excl >> 24);
+            }
+            excl += v[k];
         }
         __syncthreads();
         if (tid == 0) s_carry += tot;
@@ -602,16 +614,28 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 // ---- between A2 and B: the order in which the tile jobs are handed out.  The tile kernel's CTAs take jobs from a ticket
 // counter; a heavy tile taken late is the tail of the kernel, so the jobs are sorted by their triangle count, heaviest first
 // (counting sort on the bit length of the count — longest-processing-time-first needs no finer order), empty tiles last.
+// When the band has few tiles for the GPU (a rank of a many-GPU frame: a 270-row band of a 4K frame is 600 jobs for 592 CTA
+// slots, and the pass lasts as long as its heaviest tile), a tile that holds well over the average is handed out as four
+// 32x32-pixel quadrant jobs: each walks the tile's whole list but keeps only what reaches its quadrant.  (Cutting the LIST
+// instead was tried in round 2 and lost 40 %: every part loses the other parts' occluders to the hierarchical Z.)
+// A job word: item | (1 + quadrant) << 28, or the bare item for a whole tile.
 __global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant__ VisParams p) {
     __shared__ uint32_t s_hist[33], s_base[33];
     const uint32_t tid = threadIdx.x, n = 2u * p.n_tiles;
     if (tid < 33) s_hist[tid] = 0;
     __syncthreads();
-    auto bucket = [&](uint32_t item) {
+    const uint32_t split_above = p.split ? max(128u, (uint32_t)(((unsigned long long)min(p.bin_start[p.n_lists], p.bin_capacity) * 3ull) / (2ull * n))) : 0xffffffffu;
+    auto weight = [&](uint32_t item, bool& split) {
         const uint32_t begin = min(p.bin_start[item * DEPTH_BUCKETS], p.bin_capacity), end = min(p.bin_start[(item + 1) * DEPTH_BUCKETS], p.bin_capacity);
-        return 32u - (uint32_t)__clz(end - begin);   // 0 for an empty tile
+        split = end - begin > split_above;
+        return split ? (end - begin) / 4u + 1u : end - begin;
     };
-    for (uint32_t i = tid; i < n; i += 1024) atomicAdd(&s_hist[bucket(i)], 1u);
+    auto bucket = [](uint32_t w) { return 32u - (uint32_t)__clz(w); };   // 0 for an empty tile
+    for (uint32_t i = tid; i < n; i += 1024) {
+        bool split;
+        const uint32_t w = weight(i, split);
+        atomicAdd(&s_hist[bucket(w)], split ? 4u : 1u);
+    }
     __syncthreads();
     if (tid == 0) {
         uint32_t acc = 0;
@@ -619,9 +643,19 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant_
             s_base[b] = acc;
             acc += s_hist[b];
         }
+        *p.n_jobs = acc;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += 1024) p.tile_order[atomicAdd(&s_base[bucket(i)], 1u)] = i;
+    for (uint32_t i = tid; i < n; i += 1024) {
+        bool split;
+        const uint32_t w = weight(i, split);
+        if (split) {
+            const uint32_t at = atomicAdd(&s_base[bucket(w)], 4u);
+            for (uint32_t q = 0; q < 4; q++) p.tile_order[at + q] = i | ((1u + q) << 28);
+        } else {
+            p.tile_order[atomicAdd(&s_base[bucket(w)], 1u)] = i;
+        }
+    }
 }
 
 // ---- pass A3: scatter the surviving triangles into their bin lists
@@ -781,11 +815,14 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
         for (uint32_t i = tid; i < TS * TS; i += TILE_THREADS) keys[i] = 0ull;
         if (tid < (TS / 8) * (TS / 8)) R.zmin_blk[tid] = 0.0f;
         __syncthreads();
-        if (s_item >= 2u * p.n_tiles) break;
-        const uint32_t item = p.tile_order[s_item];
+        if (s_item >= *p.n_jobs) break;
+        const uint32_t job = p.tile_order[s_item], item = job & 0x0fffffffu, quadrant = job >> 28;   // 0: the whole tile
         const uint32_t layer = item / p.n_tiles, tile = item - layer * p.n_tiles;
         const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-        const int tile_x0 = (int)tx * TS, tile_y0 = (int)(ty + p.tile_row0) * TS;
+        // the job's pixels: the tile, or one 32x32 quadrant of it (same key array, same stride, a quarter of it in use)
+        const int rs = quadrant ? TS / 2 : TS;
+        const int tile_x0 = (int)tx * TS + (quadrant ? (int)((quadrant - 1u) & 1u) * (TS / 2) : 0);
+        const int tile_y0 = (int)(ty + p.tile_row0) * TS + (quadrant ? (int)((quadrant - 1u) >> 1) * (TS / 2) : 0);
         // the tile's DEPTH_BUCKETS lists are consecutive: one sequence, nearest instances first
         const uint32_t begin = min(p.bin_start[item * DEPTH_BUCKETS], p.bin_capacity), end = min(p.bin_start[(item + 1) * DEPTH_BUCKETS], p.bin_capacity);
         const uint32_t count = end - begin;
@@ -829,8 +866,8 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                 CK(ck_a)
 #endif
                 {
-                    const int x_lo = max(s.x_lo, tile_x0) - tile_x0, x_hi = min(s.x_hi, tile_x0 + TS - 1) - tile_x0;
-                    const int y_lo = max(s.y_lo, tile_y0) - tile_y0, y_hi = min(s.y_hi, tile_y0 + TS - 1) - tile_y0;
+                    const int x_lo = max(s.x_lo, tile_x0) - tile_x0, x_hi = min(s.x_hi, tile_x0 + rs - 1) - tile_x0;
+                    const int y_lo = max(s.y_lo, tile_y0) - tile_y0, y_hi = min(s.y_hi, tile_y0 + rs - 1) - tile_y0;
                     if (x_lo <= x_hi && y_lo <= y_hi) {
                         const int bw = x_hi - x_lo + 1;
                         n_samples = (uint32_t)(bw * (y_hi - y_lo + 1));
@@ -1079,8 +1116,8 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
         __syncthreads();
         unsigned long long* out = p.vis[layer];
         for (uint32_t i = tid; i < TS * TS; i += TILE_THREADS) {
-            const int px = tile_x0 + (int)(i & (TS - 1)), py = tile_y0 + (int)(i / TS);
-            if (px < (int)p.width && py >= (int)p.y0 && py < (int)p.y1) out[(size_t)py * p.width + px] = keys[i];
+            const int lx = (int)(i & (TS - 1)), ly = (int)(i / TS), px = tile_x0 + lx, py = tile_y0 + ly;
+            if (lx < rs && ly < rs && px < (int)p.width && py >= (int)p.y0 && py < (int)p.y1) out[(size_t)py * p.width + px] = keys[i];
         }
     }
 #if TR_PHASE_CLOCKS
@@ -1308,7 +1345,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     const size_t n_lists = (size_t)2 * p.n_tiles * DEPTH_BUCKETS;
     p.n_lists = (uint32_t)n_lists;
     const size_t zero_bytes = (n_lists + 4 + 32) * 4;  // bin_count, rec_count/ticket, scan totals
-    TR_TRY(c->bin_state.ensure(zero_bytes + (2 * n_lists + 4) * 4 + (size_t)2 * p.n_tiles * 4));
+    TR_TRY(c->bin_state.ensure(zero_bytes + (2 * n_lists + 4) * 4 + (size_t)8 * p.n_tiles * 4));
     if (!c->dev_status.p) {
         TR_TRY(c->dev_status.ensure(64));
         TR_CUDA(cudaMemsetAsync(c->dev_status.p, 0, 64, c->stream));
@@ -1318,6 +1355,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.bin_count = st;
     p.rec_count = st + n_lists;
     p.tile_ticket = st + n_lists + 1;
+    p.n_jobs = st + n_lists + 2;
     p.scan_totals = st + n_lists + 4;
     p.bin_start = st + n_lists + 4 + 32;
     p.bin_cursor = p.bin_start + n_lists + 4;  // keeps 16-byte alignment (n_lists is a multiple of 16)
@@ -1380,7 +1418,10 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel, TILE_THREADS, tile_smem));
     if (per_sm < 1) return fail(TR_ERR_CUDA, "raster_tiles_kernel does not fit on an SM (smem %zu)", tile_smem);
     uint32_t tile_grid = (uint32_t)(c->sm_count * per_sm);
-    if (tile_grid > 2 * p.n_tiles) tile_grid = 2 * p.n_tiles;
+    // fewer than three jobs per CTA slot: the pass would last as long as its heaviest tile — let heavy tiles split
+    p.split = p.ts == 64 && 2 * p.n_tiles < 3 * tile_grid ? 1u : 0u;
+    if (const char* e = getenv("TR_TILE_SPLIT")) p.split = atoi(e) && p.ts == 64 ? 1u : 0u;   // experiments
+    if (tile_grid > 8 * p.n_tiles) tile_grid = 8 * p.n_tiles;
 
     p.list_prefix = p.work_prefix;
     p.list_slots = nullptr;
