@@ -69,11 +69,11 @@ struct VisParams {
     uint32_t* bin_start;          // [n_lists + 1]
     uint32_t* bin_cursor;         // [n_lists]
     uint32_t* scan_totals;        // [SCAN_CTAS] slice totals of the scan, zeroed per frame
-    uint32_t* bin_entries;        // record index of each (triangle, list) pair, grouped by list
+    uint32_t* bin_entries;        // work-list id of the triangle of each (triangle, list) pair, grouped by list
     uint32_t bin_capacity;
     uint4* records;               // surviving triangles: (slot, tri, tile range, layer)
-    struct TriRec* trirec;        // their set-up, written once by pass A1 and read by passes A3, B and C
-    uint32_t* rec_of_tri;         // [triangles of the work list] record of a surviving triangle (pass C finds the winners by it)
+    struct TriRec* trirec;        // [triangles of the work list] the set-up of a surviving triangle AT ITS WORK-LIST ID, written once
+                                  // by pass A1 and read by passes A3, B and C (pass C finds a pixel's winner by the id in its key)
     uint32_t rec_capacity;
     uint32_t* rec_count;
     uint32_t* tile_ticket;
@@ -109,11 +109,11 @@ struct __align__(16) TriRec {
     uint4 c2z;      // C2 (two words), Z0, Z1
     float4 z2w;     // Z2, W0, W1, W2
     uint4 ids;      // vid0, vid1, vid2 (set-up order), triangle id in the work list
-    uint4 misc;     // visible slot, x_lo | x_hi << 16, y_lo | y_hi << 16, layer | depth bucket << 1
+    uint4 misc;     // instance id, x_lo | x_hi << 16, y_lo | y_hi << 16, layer | depth bucket << 1
 };
 static_assert(sizeof(TriRec) == 128, "TriRec");
 
-__device__ __forceinline__ void store_trirec(TriRec* r, const TriSetup& s, uint32_t gtid, uint32_t slot, uint32_t layer) {
+__device__ __forceinline__ void store_trirec(TriRec* r, const TriSetup& s, uint32_t gtid, uint32_t inst_id, uint32_t layer) {
     r->e[0] = make_double2(s.A[0], s.A[1]);
     r->e[1] = make_double2(s.A[2], s.B[0]);
     r->e[2] = make_double2(s.B[1], s.B[2]);
@@ -121,7 +121,7 @@ __device__ __forceinline__ void store_trirec(TriRec* r, const TriSetup& s, uint3
     r->c2z = make_uint4((uint32_t)__double2loint(s.C[2]), (uint32_t)__double2hiint(s.C[2]), __float_as_uint(s.Z[0]), __float_as_uint(s.Z[1]));
     r->z2w = make_float4(s.Z[2], s.W[0], s.W[1], s.W[2]);
     r->ids = make_uint4(s.vid[0], s.vid[1], s.vid[2], gtid);
-    r->misc = make_uint4(slot, (uint32_t)s.x_lo | ((uint32_t)s.x_hi << 16), (uint32_t)s.y_lo | ((uint32_t)s.y_hi << 16), layer);
+    r->misc = make_uint4(inst_id, (uint32_t)s.x_lo | ((uint32_t)s.x_hi << 16), (uint32_t)s.y_lo | ((uint32_t)s.y_hi << 16), layer);
 }
 // edge functions + box (what binning needs)
 __device__ __forceinline__ void load_trirec_edges(const TriRec* r, TriSetup& s) {
@@ -132,23 +132,30 @@ __device__ __forceinline__ void load_trirec_edges(const TriRec* r, TriSetup& s) 
     s.Z[0] = __uint_as_float(c.z); s.Z[1] = __uint_as_float(c.w);
     s.x_lo = (int)(m.y & 0xffffu); s.x_hi = (int)(m.y >> 16); s.y_lo = (int)(m.z & 0xffffu); s.y_hi = (int)(m.z >> 16);
 }
-__device__ __forceinline__ void load_trirec(const TriRec* r, TriSetup& s, uint32_t& gtid, uint32_t& slot) {
+__device__ __forceinline__ void load_trirec(const TriRec* r, TriSetup& s, uint32_t& gtid, uint32_t& inst_id) {
     load_trirec_edges(r, s);
     const float4 z = __ldg(&r->z2w);
     const uint4 ids = __ldg(&r->ids);
     s.Z[2] = z.x; s.W[0] = z.y; s.W[1] = z.z; s.W[2] = z.w;
     s.vid[0] = ids.x; s.vid[1] = ids.y; s.vid[2] = ids.z;
     gtid = ids.w;
-    slot = __ldg(&r->misc.x);
+    inst_id = __ldg(&r->misc.x);
 }
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 
-// oracle/raster.c setup_triangle
-template <bool WITH_BOX = true>
-__device__ __forceinline__ bool setup_triangle_at(const VisParams& p, const tr_instance* inst, uint32_t first_index, uint32_t tri, TriSetup& s) {
+// oracle/raster.c setup_triangle, in three steps (the binning pass queues the triangles between them):
+//   setup_front   gather + transform the three vertices, back-face / degenerate test (exact, double)
+//   setup_box     Vulkan clip volume, screen bounding box clipped to the band
+//   setup_edges   the homogeneous edge functions
+struct FrontTri {
+    float rx[3], ry[3], Z[3], W[3];   // screen-scaled clip x and y, clip z and w, in set-up order (0, 2, 1)
+    uint32_t vid[3];
+};
+
+__device__ __forceinline__ bool setup_front(const VisParams& p, const tr_instance* inst, uint32_t first_index, uint32_t tri, FrontTri& f) {
     const float4* iq = reinterpret_cast<const float4*>(inst);
     const float4 ts = __ldg(iq), rot = __ldg(iq + 1);
     uint32_t vid[3];
@@ -174,23 +181,33 @@ __device__ __forceinline__ bool setup_triangle_at(const VisParams& p, const tr_i
     const double det = dadd(dadd(dmul(sx[0], a0), dmul(sy[0], b0)), dmul(W[0], c0));
     if (!(det < 0.0)) return false;  // back face / degenerate
     const int order[3] = {0, 2, 1};
-    float rx[3], ry[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        rx[k] = sx[order[k]];
-        ry[k] = sy[order[k]];
-        s.Z[k] = Z[order[k]];
-        s.W[k] = W[order[k]];
-        s.vid[k] = vid[order[k]];
+        f.rx[k] = sx[order[k]];
+        f.ry[k] = sy[order[k]];
+        f.Z[k] = Z[order[k]];
+        f.W[k] = W[order[k]];
+        f.vid[k] = vid[order[k]];
     }
+    return true;
+}
+
+__device__ __forceinline__ void setup_edges(const FrontTri& f, TriSetup& s) {
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int a = (i + 1) % 3, b = (i + 2) % 3;
-        s.A[i] = dsub(dmul(ry[a], s.W[b]), dmul(s.W[a], ry[b]));
-        s.B[i] = dsub(dmul(s.W[a], rx[b]), dmul(rx[a], s.W[b]));
-        s.C[i] = dsub(dmul(rx[a], ry[b]), dmul(ry[a], rx[b]));
+        s.A[i] = dsub(dmul(f.ry[a], f.W[b]), dmul(f.W[a], f.ry[b]));
+        s.B[i] = dsub(dmul(f.W[a], f.rx[b]), dmul(f.rx[a], f.W[b]));
+        s.C[i] = dsub(dmul(f.rx[a], f.ry[b]), dmul(f.ry[a], f.rx[b]));
+        s.Z[i] = f.Z[i];
+        s.W[i] = f.W[i];
+        s.vid[i] = f.vid[i];
     }
-    if (!WITH_BOX) return true;  // resolve: the triangle is known to cover the pixel, only the edge functions are needed
+}
+
+__device__ __forceinline__ bool setup_box(const VisParams& p, const FrontTri& s, int& bx_lo, int& bx_hi, int& by_lo, int& by_hi) {
+    const float* rx = s.rx;
+    const float* ry = s.ry;
     // Vulkan clip volume: w > 0 and z <= w.  Every vertex at/behind the camera plane => no fragment.
     if (!(s.W[0] > 0.0f) && !(s.W[1] > 0.0f) && !(s.W[2] > 0.0f)) return false;
     int x_lo = 0, x_hi = (int)p.width - 1, y_lo = (int)p.y0, y_hi = (int)p.y1 - 1;
@@ -256,7 +273,7 @@ __device__ __forceinline__ bool setup_triangle_at(const VisParams& p, const tr_i
         if (fy_hi < (float)y_hi) y_hi = (int)fy_hi;
     }
     if (x_lo > x_hi || y_lo > y_hi) return false;
-    s.x_lo = x_lo; s.x_hi = x_hi; s.y_lo = y_lo; s.y_hi = y_hi;
+    bx_lo = x_lo; bx_hi = x_hi; by_lo = y_lo; by_hi = y_hi;
     return true;
 }
 
@@ -316,6 +333,15 @@ __device__ __forceinline__ bool tile_may_overlap(const TriSetup& s, int x0, int 
         if (e + margin < 0.0) return false;
     }
     return true;
+}
+
+__device__ __forceinline__ uint32_t find_slot(const VisParams& p, uint32_t w, uint32_t n_visible) {
+    uint32_t lo = 0, hi = n_visible;  // largest slot with work_prefix[slot] <= w
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(p.work_prefix + mid) <= w) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
 // The bin lists a triangle goes to: every tile of its bounding box, edge-tested when the box spans more than
@@ -478,21 +504,64 @@ __global__ void __launch_bounds__(1024) band_filter_kernel(const __grid_constant
 #ifndef TR_BIN_CTAS
 #define TR_BIN_CTAS 3
 #endif
+#ifndef TR_BIN_WAVES   // CTAs of the binning pass per resident slot: their ranges cost very unequal amounts (survivors)
+#define TR_BIN_WAVES 8
+#endif
+// Two steps with a queue between them: only about one triangle in seven survives the back-face and box tests, and a warp
+// that carried its few survivors through the edge set-up, the binning and the 128-byte record store lane by lane would run
+// that half of the pass at a seventh of its lanes.  Survivors wait in the warp's shared-memory queue until 32 are there.
+constexpr int BINQ_WORDS = 20, BINQ_CAP = 64;   // per entry: rx ry Z W (12), vid (3), slot, tri, layer, box x, box y
 __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __grid_constant__ VisParams p) {
+    __shared__ uint32_t s_queue[8][BINQ_WORDS][BINQ_CAP];
     const uint32_t n_list = p.list_scalars[0], total = p.list_scalars[1];
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+    uint32_t (*q)[BINQ_CAP] = s_queue[threadIdx.x >> 5];
     // a CTA takes a contiguous range of the work list, so that (i) a warp's next 32 triangles are 256 further on and the list
     // entry is found by walking on from the last one, (ii) the records of neighbouring triangles lie together in memory —
     // a tile's bin list is mostly runs of neighbouring triangles, and pass B gathers their records
     const uint32_t per = ((total + gridDim.x - 1) / gridDim.x + 255u) & ~255u;
     const uint32_t range_begin = blockIdx.x * per, range_end = min(range_begin + per, total);
-    uint32_t entry = 0;
+    uint32_t entry = 0, qn = 0;
     bool have_entry = false;
+
+    // step 2 on the queue entries [from, from + 32) (fewer at the very end): edge functions, bin counts, the record
+    auto finish = [&](uint32_t from, uint32_t n) {
+        const bool keep = lane < n;
+        const uint32_t e = from + min(lane, n - 1u);
+        FrontTri f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            f.rx[k] = __uint_as_float(q[k][e]);
+            f.ry[k] = __uint_as_float(q[3 + k][e]);
+            f.Z[k] = __uint_as_float(q[6 + k][e]);
+            f.W[k] = __uint_as_float(q[9 + k][e]);
+            f.vid[k] = q[12 + k][e];
+        }
+        const uint32_t slot = q[15][e], tri = q[16][e], layer = q[17][e], bx = q[18][e], by = q[19][e];
+        TriSetup s;
+        setup_edges(f, s);
+        s.x_lo = (int)(bx & 0xffffu); s.x_hi = (int)(bx >> 16); s.y_lo = (int)(by & 0xffffu); s.y_hi = (int)(by >> 16);
+        const uint32_t range = (uint32_t)(s.x_lo / p.ts) | ((uint32_t)(s.x_hi / p.ts) << 8) |
+                               ((uint32_t)(s.y_lo / p.ts - (int)p.tile_row0) << 16) | ((uint32_t)(s.y_hi / p.ts - (int)p.tile_row0) << 24);
+        bin_triangle(p, keep, s, range, layer, make_uint2(0, 0), [&](uint32_t list, uint2) { atomicAdd(p.bin_count + list, 1u); },
+                     [&](uint32_t list, uint2, uint32_t peers) {
+                         if (lane == (uint32_t)__ffs(peers) - 1u) atomicAdd(p.bin_count + list, (uint32_t)__popc(peers));
+                     });
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(p.rec_count, n);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (keep) {
+            const uint32_t r = first + lane;
+            const uint32_t gtid = __ldg(p.work_prefix + slot) + tri;
+            if (r < p.rec_capacity && gtid < p.rec_capacity) {
+                p.records[r] = make_uint4(gtid, 0u, range, layer);
+                store_trirec(p.trirec + gtid, s, gtid, __ldg(p.visible_ids + slot), layer);
+            } else atomicOr(p.status, 1u);
+        }
+    };
+
     for (uint32_t base = range_begin + (threadIdx.x & ~31u); base < range_end; base += 256u) {
         const uint32_t w = base + lane;
-        bool keep = false;
-        uint32_t slot = 0, tri = 0, range = 0, layer = 0;
-        TriSetup s{};
         if (!have_entry) {
             entry = find_entry_warp(p.list_prefix, base, min(w, total - 1), n_list);
             have_entry = true;
@@ -500,6 +569,11 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __gri
             const uint32_t wc = min(w, total - 1);
             while (entry + 1 < n_list && __ldg(p.list_prefix + entry + 1) <= wc) entry++;
         }
+        // step 1: vertices, back face, clip volume and box
+        bool keep = false;
+        FrontTri f;
+        uint32_t slot = 0, tri = 0, layer = 0;
+        int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
         if (w < total) {
             slot = p.list_slots ? __ldg(p.list_slots + entry) : entry;
             tri = w - __ldg(p.list_prefix + entry);
@@ -507,33 +581,34 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __gri
             const uint2 prim = __ldg(p.slot_prim + slot);
             const uint32_t bucket = prim.y;
             layer = bucket >> 1;  // draw buffers 0/1 (opaque, alpha clip) -> layer 0, 2/3 -> the transmissive layer
-            if (bucket < 4u && setup_triangle_at<true>(p, inst, prim.x, tri, s)) {
-                keep = true;
-                layer |= depth_bucket(p, slot) << 1;  // layer | depth bucket << 1 travels with the record
-                range = (uint32_t)(s.x_lo / p.ts) | ((uint32_t)(s.x_hi / p.ts) << 8) |
-                        ((uint32_t)(s.y_lo / p.ts - (int)p.tile_row0) << 16) | ((uint32_t)(s.y_hi / p.ts - (int)p.tile_row0) << 24);
-            }
+            keep = bucket < 4u && setup_front(p, inst, prim.x, tri, f) && setup_box(p, f, x_lo, x_hi, y_lo, y_hi);
         }
-        bin_triangle(p, keep, s, range, layer, make_uint2(0, 0), [&](uint32_t list, uint2) { atomicAdd(p.bin_count + list, 1u); },
-                     [&](uint32_t list, uint2, uint32_t peers) {
-                         if (lane == (uint32_t)__ffs(peers) - 1u) atomicAdd(p.bin_count + list, (uint32_t)__popc(peers));
-                     });
         const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-        if (mask) {
-            uint32_t first = 0;
-            if (lane == 0) first = atomicAdd(p.rec_count, (uint32_t)__popc(mask));
-            first = __shfl_sync(0xffffffffu, first, 0);
-            if (keep) {
-                const uint32_t r = first + __popc(mask & ((1u << lane) - 1u));
-                if (r < p.rec_capacity) {
-                    p.records[r] = make_uint4(slot, tri, range, layer);
-                    const uint32_t gtid = __ldg(p.work_prefix + slot) + tri;
-                    store_trirec(p.trirec + r, s, gtid, slot, layer);
-                    p.rec_of_tri[gtid] = r;
-                } else atomicOr(p.status, 1u);
+        if (keep) {
+            const uint32_t e = qn + (uint32_t)__popc(mask & lt_mask);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                q[k][e] = __float_as_uint(f.rx[k]);
+                q[3 + k][e] = __float_as_uint(f.ry[k]);
+                q[6 + k][e] = __float_as_uint(f.Z[k]);
+                q[9 + k][e] = __float_as_uint(f.W[k]);
+                q[12 + k][e] = f.vid[k];
             }
+            q[15][e] = slot;
+            q[16][e] = tri;
+            q[17][e] = layer | (depth_bucket(p, slot) << 1);   // layer | depth bucket << 1 travels with the record
+            q[18][e] = (uint32_t)x_lo | ((uint32_t)x_hi << 16);
+            q[19][e] = (uint32_t)y_lo | ((uint32_t)y_hi << 16);
+        }
+        qn += (uint32_t)__popc(mask);
+        __syncwarp();
+        if (qn >= 32u) {
+            qn -= 32u;
+            finish(qn, 32u);
+            __syncwarp();
         }
     }
+    if (qn) finish(0u, qn);
 }
 
 // ---- pass A2: exclusive scan of the bin counts.  SCAN_CTAS co-resident CTAs (far fewer than SMs) each scan a contiguous
@@ -670,9 +745,9 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_fill_kernel(const __grid
         if (keep) {
             rec = p.records[r];
             const int tx0 = rec.z & 0xff, tx1 = (rec.z >> 8) & 0xff, ty0 = (rec.z >> 16) & 0xff, ty1 = rec.z >> 24;
-            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4) load_trirec_edges(p.trirec + r, s);  // the edge test of large triangles
+            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4) load_trirec_edges(p.trirec + rec.x, s);  // the edge test of large triangles
         }
-        bin_triangle(p, keep, s, rec.z, rec.w, make_uint2(r, 0u), [&](uint32_t list, uint2 pl) {
+        bin_triangle(p, keep, s, rec.z, rec.w, make_uint2(rec.x, 0u), [&](uint32_t list, uint2 pl) {
             const uint32_t pos = atomicAdd(p.bin_cursor + list, 1u);
             if (pos < p.bin_capacity) p.bin_entries[pos] = pl.x;
         }, [&](uint32_t list, uint2 pl, uint32_t peers) {
@@ -859,8 +934,8 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                 const uint32_t e = e_next;
                 if (round + ROUND + tid < count) e_next = p.bin_entries[begin + round + ROUND + tid];
                 TriSetup s;
-                uint32_t rec_gtid, rec_slot;
-                load_trirec(p.trirec + e, s, rec_gtid, rec_slot);
+                uint32_t rec_gtid, rec_inst;
+                load_trirec(p.trirec + e, s, rec_gtid, rec_inst);
 #if TR_PHASE_CLOCKS
                 if (s.x_lo + s.y_lo + (int)rec_gtid + (int)__double2loint(s.A[0]) + (int)__float_as_uint(s.W[2]) == -12345) ck_rounds++;
                 CK(ck_a)
@@ -872,11 +947,12 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                         const int bw = x_hi - x_lo + 1;
                         n_samples = (uint32_t)(bw * (y_hi - y_lo + 1));
                         R.box[tid] = (uint32_t)x_lo | ((uint32_t)y_lo << 6) | ((uint32_t)(bw - 1) << 12);
-                        R.gtid[tid] = rec_gtid;
+                        R.gtid[tid] = e;   // the bin entry is the triangle's work-list id
                         if (CLIP) {
-                            const tr_instance* inst = p.instances + __ldg(p.visible_ids + rec_slot);
+                            const tr_instance* inst = p.instances + rec_inst;
                             const tr_primitive_info* prim = p.prims + __ldg(&inst->primitive_id);
-                            R.entry[tid] = make_uint2(rec_slot, rec_gtid - __ldg(p.work_prefix + rec_slot));
+                            const uint32_t rec_slot = find_slot(p, e, p.scalars[0]);   // alpha-clip buckets only
+                            R.entry[tid] = make_uint2(rec_slot, e - __ldg(p.work_prefix + rec_slot));
                             R.clip_mat[tid] = (__ldg(&prim->draw_buffer_index) & 1u) ? __ldg(&inst->material_id) : 0xffffffffu;
                         }
                         const double X0 = (double)tile_x0 + 0.5, Y0 = (double)tile_y0 + 0.5;
@@ -1144,9 +1220,9 @@ struct ResolveRec {
 
 __device__ __forceinline__ void resolve_setup(const VisParams& p, uint32_t gtid, ResolveRec& r) {
     TriSetup s;
-    uint32_t rec_gtid, slot;
-    load_trirec(p.trirec + __ldg(p.rec_of_tri + gtid), s, rec_gtid, slot);   // pass A1's set-up of this triangle
-    const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
+    uint32_t rec_gtid, inst_id;
+    load_trirec(p.trirec + gtid, s, rec_gtid, inst_id);   // pass A1's set-up of this triangle
+    const tr_instance* inst = p.instances + inst_id;
     const float4 rot = __ldg(reinterpret_cast<const float4*>(inst) + 1);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -1339,8 +1415,8 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.bin_capacity = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(BIN_CAPACITY, 6 * c->max_triangles + 64ull * p.n_tiles), 1ull << 27);
     p.rec_capacity = (uint32_t)(c->max_triangles ? c->max_triangles : 1);
     TR_TRY(c->bin_entries.ensure((size_t)p.bin_capacity * sizeof(uint32_t)));
-    // per surviving triangle: the 16-byte binning record, the 128-byte set-up, and the work-list id -> record map
-    TR_TRY(c->tri_records.ensure((size_t)p.rec_capacity * (sizeof(uint4) + sizeof(TriRec) + sizeof(uint32_t))));
+    // per triangle of the work list: room for the 128-byte set-up (at its work-list id) and the 16-byte binning record
+    TR_TRY(c->tri_records.ensure((size_t)p.rec_capacity * (sizeof(uint4) + sizeof(TriRec))));
     // state block: [bin_count L][rec_count, ticket, pad, pad][bin_start L+1][bin_cursor L]; the first two parts are zeroed per frame
     const size_t n_lists = (size_t)2 * p.n_tiles * DEPTH_BUCKETS;
     p.n_lists = (uint32_t)n_lists;
@@ -1363,7 +1439,6 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.bin_entries = c->bin_entries.as<uint32_t>();
     p.trirec = c->tri_records.as<TriRec>();
     p.records = reinterpret_cast<uint4*>(p.trirec + p.rec_capacity);
-    p.rec_of_tri = reinterpret_cast<uint32_t*>(p.records + p.rec_capacity);
     p.status = c->dev_status.as<uint32_t>();
     p.stats = reinterpret_cast<unsigned long long*>(c->dev_status.as<unsigned char>() + 16);
 
@@ -1438,7 +1513,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
         p.list_scalars = p.band_scalars;
         extra_launch = 1;
     }
-    bin_count_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
+    bin_count_kernel<<<c->sm_count * TR_BIN_WAVES * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     bin_scan_kernel<<<SCAN_CTAS, 1024, 0, c->stream>>>(p);
     bin_fill_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     tile_order_kernel<<<1, 1024, 0, c->stream>>>(p);
