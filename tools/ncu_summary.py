@@ -22,8 +22,9 @@ WANT = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "us"), ("smsp__ins
         ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"), ("lts__t_sector_hit_rate.pct", "l2_hit_pct")]
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr = rows[0]
-out = [[n for _, n in WANT]]
+hdr, units = rows[0], rows[1]
+SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}   # -> us, MB
+out = [[n + ("_MB" if n.startswith("dram") else "") for _, n in WANT]]
 for r in rows[2:]:
     line = []
     for k, n in WANT:
@@ -32,7 +33,10 @@ for r in rows[2:]:
             v = v.replace("<unnamed>::", "").replace("void ", "")[:48]
         else:
             try:
-                v = f"{float(v):.4g}"
+                x = float(v)
+                if n in ("us", "dram_rd", "dram_wr"):
+                    x *= SCALE.get(units[hdr.index(k)], 1.0)
+                v = f"{x:.4g}"
             except ValueError:
                 pass
         line.append(v)

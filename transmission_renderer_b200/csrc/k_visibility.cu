@@ -926,7 +926,8 @@ __global__ void __launch_bounds__(TILE_THREADS, CLIP ? 2 : TR_TILE_CTAS) raster_
                     m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
                     m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
                     m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                    if ((lane & 7u) == 0u) R.zmin_blk[by * (TS / 8) + half * 4u + (lane >> 3)] = m;
+                    // (an atomic store: the concurrent readers are meant, and compute-sanitizer's racecheck is told so)
+                    if ((lane & 7u) == 0u) atomicExch(reinterpret_cast<uint32_t*>(&R.zmin_blk[by * (TS / 8) + half * 4u + (lane >> 3)]), __float_as_uint(m));
                 }
                 CK(ck_a)
             }
