@@ -14,8 +14,8 @@
 // Sort-middle, front to back, with a hierarchical Z:
 //   A1 bin_count   one thread per triangle: exact set-up, cull (back face, off band, w <= 0), count into the 64x64-pixel
 //                  tile bins (16 depth buckets per tile and layer), compact the survivors into records
-//   A2 bin_scan    exclusive scan of the bin counts;  tile_order: the tile jobs heaviest first
-//   A3 bin_fill    scatter the survivors into their bins
+//   A2 bin_scan    exclusive scan of the bin counts
+//   A3 bin_fill    scatter the survivors into their bins; its CTA 0 first orders the tile jobs, heaviest first
 //   B  raster_tiles  persistent CTAs, one tile job at a time with the tile's depth/id words in shared memory: rounds of 64
 //                  triangles (fp32 coarse form with proven bounds + exact double form), all threads walk all box pixels,
 //                  survivors evaluated exactly, winners by shared-memory atomicMax, 8x8 block minima refreshed per round
@@ -694,9 +694,10 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 // 32x32-pixel quadrant jobs: each walks the tile's whole list but keeps only what reaches its quadrant.  (Cutting the LIST
 // instead was tried in round 2 and lost 40 %: every part loses the other parts' occluders to the hierarchical Z.)
 // A job word: item | (1 + quadrant) << 28, or the bare item for a whole tile.
-__global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant__ VisParams p) {
+// Run by CTA 0 of the fill pass (pass A3) before its share of the filling: one launch fewer, and it is off the critical path.
+__device__ __forceinline__ void tile_order_block(const VisParams& p) {
     __shared__ uint32_t s_hist[33], s_base[33];
-    const uint32_t tid = threadIdx.x, n = 2u * p.n_tiles;
+    const uint32_t tid = threadIdx.x, n = 2u * p.n_tiles, nt = blockDim.x;
     if (tid < 33) s_hist[tid] = 0;
     __syncthreads();
     const uint32_t split_above = p.split ? max(128u, (uint32_t)(((unsigned long long)min(p.bin_start[p.n_lists], p.bin_capacity) * 3ull) / (2ull * n))) : 0xffffffffu;
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant_
         return split ? (end - begin) / 4u + 1u : end - begin;
     };
     auto bucket = [](uint32_t w) { return 32u - (uint32_t)__clz(w); };   // 0 for an empty tile
-    for (uint32_t i = tid; i < n; i += 1024) {
+    for (uint32_t i = tid; i < n; i += nt) {
         bool split;
         const uint32_t w = weight(i, split);
         atomicAdd(&s_hist[bucket(w)], split ? 4u : 1u);
@@ -721,7 +722,7 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant_
         *p.n_jobs = acc;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += 1024) {
+    for (uint32_t i = tid; i < n; i += nt) {
         bool split;
         const uint32_t w = weight(i, split);
         if (split) {
@@ -735,6 +736,7 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant_
 
 // ---- pass A3: scatter the surviving triangles into their bin lists
 __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_fill_kernel(const __grid_constant__ VisParams p) {
+    if (blockIdx.x == 0) tile_order_block(p);
     const uint32_t n = min(*p.rec_count, p.rec_capacity);
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
@@ -1517,12 +1519,11 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     bin_count_kernel<<<c->sm_count * TR_BIN_WAVES * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     bin_scan_kernel<<<SCAN_CTAS, 1024, 0, c->stream>>>(p);
     bin_fill_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
-    tile_order_kernel<<<1, 1024, 0, c->stream>>>(p);
     tile_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
     const dim3 res_grid((c->width + RES_W - 1) / RES_W, (c->band_y1 - c->band_y0 + RES_H - 1) / RES_H, 1);
     if (c->materials_textured) resolve_kernel<true><<<res_grid, RES_W * RES_H, 0, c->stream>>>(p);
     else resolve_kernel<false><<<res_grid, RES_W * RES_H, 0, c->stream>>>(p);
-    count_launches(6 + extra_launch);
+    count_launches(5 + extra_launch);
     TR_CUDA(cudaGetLastError());
     for (int l = 0; l < 2; l++) {
         c->layer[l].valid = true;
