@@ -153,10 +153,10 @@ TRD f3 btdf_light(const PixelShading& s, f3 l) {
 // n.h moves D by 4 ulp / f.  Everything else is well conditioned, so the light loop runs in the fast regime and
 // re-derives n.h through the exact chain (position -> direction -> halfway -> n.h, the oracle's operation order)
 // only when the fast estimate of f is below TR_EXACT_F — a few percent of the (pixel, light) pairs, all of them inside
-// highlights.  Measured on B200 (tests/test_gpu_parity.py spheres cases, worst rel-L2 of the final fp32 frame against the
-// oracle): threshold 0 (all fast) 1.0e-3, 0.02 1.9e-4, 0.04 6.7e-5, 0.08 1.2e-5; a Newton-refined rsqrt changes nothing (the
-// residual is fp32 rounding of the sums, not the MUFU approximation), so the threshold is the only knob: 0.08 keeps 8x margin
-// to the 1e-4 tolerance for ~3 % of the shading time.  There the result is bit-identical to the all-exact evaluation; elsewhere it is within ~1e-6 of it.
+// highlights.  There the lobe is bit-identical to the all-exact evaluation; elsewhere it is within ~1e-6 of it.  Measured on
+// B200 with the round-2 loop (un-normalised halfway vector) at the 0.04 below: worst rel-L2 of a final fp32 frame against the
+// oracle 7.5e-6 (tests/test_gpu_parity.py spheres cases), worst element of tests/test_gpu_hot_loop.py 0.59 of its tolerance.
+// (Round 1's loop, which took |h|^2 from 2 (1 + v.l), needed 0.08: 0 (all fast) 1.0e-3, 0.02 1.9e-4, 0.04 6.7e-5, 0.08 1.2e-5.)
 #ifndef TR_EXACT_F
 #define TR_EXACT_F 0.04f
 #endif
