@@ -1258,7 +1258,7 @@ __device__ __forceinline__ void resolve_write(const VisParams& p, const ResolveR
         s.W[k] = r.W[k];
     }
     float l[3] = {0.f, 0.f, 0.f}, d = 0.0f;
-    eval_pixel(s, px, py, l, d);  // by construction the winning triangle covers this pixel
+    eval_plane(s, px, py, l, d);  // eval_pixel's arithmetic without its coverage tests: by construction the winning triangle covers this pixel
     p.depth[layer][i] = d;
     p.normal[layer][(size_t)i * 3 + 0] = xadd(xadd(xmul(l[0], r.n[0][0]), xmul(l[1], r.n[1][0])), xmul(l[2], r.n[2][0]));
     p.normal[layer][(size_t)i * 3 + 1] = xadd(xadd(xmul(l[0], r.n[0][1]), xmul(l[1], r.n[1][1])), xmul(l[2], r.n[2][1]));
@@ -1289,59 +1289,74 @@ __device__ __forceinline__ void resolve_write(const VisParams& p, const ResolveR
 }
 
 #ifndef TR_RESOLVE_CTAS
-#define TR_RESOLVE_CTAS 6
+#define TR_RESOLVE_CTAS 5
 #endif
+#ifndef TR_RESOLVE_PX
+#define TR_RESOLVE_PX 2
+#endif
+// The pass is a chain of three dependent trips to memory per block (keys -> records -> vertex attributes) and little else, so
+// its rate is (pixels in flight per SM) / (the chain's latency): with one pixel per thread 1536 pixels were in flight per SM
+// and nothing done to the arithmetic, the set-up or the stores moved its 0.19 ms.  RES_PX pixels per thread (rows RES_H apart
+// in a 32 x (RES_H RES_PX) block) put more pixels behind every trip.
+constexpr int RES_PX = TR_RESOLVE_PX;
 template <bool DERIV>
 __global__ void __launch_bounds__(RES_W * RES_H, TR_RESOLVE_CTAS) resolve_kernel(const __grid_constant__ VisParams p) {
     __shared__ uint32_t s_key[RES_TABLE];     // triangle id, 0xffffffff = empty
     __shared__ uint16_t s_idx[RES_TABLE];     // compact index of that triangle
-    __shared__ uint32_t s_list[2 * RES_W * RES_H];
+    __shared__ uint32_t s_list[2 * RES_W * RES_H * RES_PX];
     __shared__ uint32_t s_count;
     __shared__ ResolveRec s_rec[RES_CAP];
     const uint32_t tid = threadIdx.x;
     const int px = (int)(blockIdx.x * RES_W + (tid & (RES_W - 1)));
-    const int py = (int)(p.y0 + blockIdx.y * RES_H + tid / RES_W);
-    const bool inside = px < (int)p.width && py < (int)p.y1;
-    const uint32_t i = (uint32_t)py * p.width + (uint32_t)px;
+    const int py0 = (int)(p.y0 + blockIdx.y * (RES_H * RES_PX) + tid / RES_W);
 
     for (uint32_t k = tid; k < RES_TABLE; k += RES_W * RES_H) s_key[k] = 0xffffffffu;
     if (tid == 0) s_count = 0;
     __syncthreads();
 
-    // phase 1: the winning triangle of this pixel in each layer goes into the hash set
-    uint32_t gtid[2] = {0xffffffffu, 0xffffffffu}, slot[2] = {0, 0};
-    if (inside) {
-        const unsigned long long k0 = p.vis[0][i];
-        unsigned long long k1 = p.vis[1][i];
-        // depth GREATER against the opaque depth of the shared depth buffer, applied to the nearest transmissive
-        // fragment (if that one is hidden, every other one is too)
-        if (!(__uint_as_float((uint32_t)(k1 >> 32)) > __uint_as_float((uint32_t)(k0 >> 32)))) k1 = 0ull;
-        if (k0) gtid[0] = 0xffffffffu - (uint32_t)(k0 & 0xffffffffull);
-        if (k1) gtid[1] = 0xffffffffu - (uint32_t)(k1 & 0xffffffffull);
+    // phase 1: the winning triangle of each of this thread's pixels in each layer goes into the hash set
+    uint32_t gtid[RES_PX][2], slot[RES_PX][2];
+    bool inside[RES_PX];
+    unsigned long long k0[RES_PX], k1[RES_PX];
+#pragma unroll
+    for (int q = 0; q < RES_PX; q++) {   // all the key loads first: one trip to memory for all of them
+        const int py = py0 + q * RES_H;
+        inside[q] = px < (int)p.width && py < (int)p.y1;
+        const uint32_t i = (uint32_t)py * p.width + (uint32_t)px;
+        k0[q] = inside[q] ? p.vis[0][i] : 0ull;
+        k1[q] = inside[q] ? p.vis[1][i] : 0ull;
     }
     const uint32_t lane = tid & 31u;
 #pragma unroll
-    for (int layer = 0; layer < 2; layer++) {
-        // a warp is one row of 32 pixels and usually sees one to three triangles: one lane per distinct triangle goes to
-        // the table (otherwise all lanes would fight over the same shared-memory word), the rest get its slot by shuffle
-        const uint32_t peers = __match_any_sync(0xffffffffu, gtid[layer]);
-        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
-        uint32_t h = 0;
-        if (lane == leader && gtid[layer] != 0xffffffffu) {
-            h = (gtid[layer] * 2654435761u) >> 22;  // 10 bits
-            while (true) {
-                const uint32_t old = atomicCAS(&s_key[h], 0xffffffffu, gtid[layer]);
-                if (old == 0xffffffffu) {  // first to see this triangle: give it a compact index
-                    const uint32_t idx = atomicAdd(&s_count, 1u);
-                    s_idx[h] = (uint16_t)idx;
-                    s_list[idx] = gtid[layer];
-                    break;
+    for (int q = 0; q < RES_PX; q++) {
+        // depth GREATER against the opaque depth of the shared depth buffer, applied to the nearest transmissive
+        // fragment (if that one is hidden, every other one is too)
+        if (!(__uint_as_float((uint32_t)(k1[q] >> 32)) > __uint_as_float((uint32_t)(k0[q] >> 32)))) k1[q] = 0ull;
+        gtid[q][0] = k0[q] ? 0xffffffffu - (uint32_t)(k0[q] & 0xffffffffull) : 0xffffffffu;
+        gtid[q][1] = k1[q] ? 0xffffffffu - (uint32_t)(k1[q] & 0xffffffffull) : 0xffffffffu;
+#pragma unroll
+        for (int layer = 0; layer < 2; layer++) {
+            // a warp is one row of 32 pixels and usually sees one to three triangles: one lane per distinct triangle goes to
+            // the table (otherwise all lanes would fight over the same shared-memory word), the rest get its slot by shuffle
+            const uint32_t peers = __match_any_sync(0xffffffffu, gtid[q][layer]);
+            const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+            uint32_t h = 0;
+            if (lane == leader && gtid[q][layer] != 0xffffffffu) {
+                h = (gtid[q][layer] * 2654435761u) >> 22;  // 10 bits
+                while (true) {
+                    const uint32_t old = atomicCAS(&s_key[h], 0xffffffffu, gtid[q][layer]);
+                    if (old == 0xffffffffu) {  // first to see this triangle: give it a compact index
+                        const uint32_t idx = atomicAdd(&s_count, 1u);
+                        s_idx[h] = (uint16_t)idx;
+                        s_list[idx] = gtid[q][layer];
+                        break;
+                    }
+                    if (old == gtid[q][layer]) break;
+                    h = (h + 1) & (RES_TABLE - 1);
                 }
-                if (old == gtid[layer]) break;
-                h = (h + 1) & (RES_TABLE - 1);
             }
+            slot[q][layer] = __shfl_sync(0xffffffffu, h, (int)leader);
         }
-        slot[layer] = __shfl_sync(0xffffffffu, h, (int)leader);
     }
     __syncthreads();
 
@@ -1351,28 +1366,33 @@ __global__ void __launch_bounds__(RES_W * RES_H, TR_RESOLVE_CTAS) resolve_kernel
     __syncthreads();
 
     // phase 3: per pixel
-    if (!inside) return;
 #pragma unroll
-    for (int layer = 0; layer < 2; layer++) {
-        if (gtid[layer] == 0xffffffffu) {
-            p.depth[layer][i] = 0.0f;
-            p.normal[layer][(size_t)i * 3] = 0.0f; p.normal[layer][(size_t)i * 3 + 1] = 0.0f; p.normal[layer][(size_t)i * 3 + 2] = 0.0f;
-            p.uv[layer][(size_t)i * 2] = 0.0f; p.uv[layer][(size_t)i * 2 + 1] = 0.0f;
-            p.material_id[layer][i] = 0xffffffffu;
-            if (layer == 1) p.scale1[i] = 0.0f;
-            if (DERIV) {
-                p.duv[layer][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                p.ddepth[layer][i] = make_float2(0.f, 0.f);
+    for (int q = 0; q < RES_PX; q++) {
+        if (!inside[q]) continue;
+        const int py = py0 + q * RES_H;
+        const uint32_t i = (uint32_t)py * p.width + (uint32_t)px;
+#pragma unroll
+        for (int layer = 0; layer < 2; layer++) {
+            if (gtid[q][layer] == 0xffffffffu) {
+                p.depth[layer][i] = 0.0f;
+                p.normal[layer][(size_t)i * 3] = 0.0f; p.normal[layer][(size_t)i * 3 + 1] = 0.0f; p.normal[layer][(size_t)i * 3 + 2] = 0.0f;
+                p.uv[layer][(size_t)i * 2] = 0.0f; p.uv[layer][(size_t)i * 2 + 1] = 0.0f;
+                p.material_id[layer][i] = 0xffffffffu;
+                if (layer == 1) p.scale1[i] = 0.0f;
+                if (DERIV) {
+                    p.duv[layer][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    p.ddepth[layer][i] = make_float2(0.f, 0.f);
+                }
+                continue;
             }
-            continue;
-        }
-        const uint32_t idx = s_idx[slot[layer]];
-        if (idx < (uint32_t)RES_CAP) {
-            resolve_write<DERIV>(p, s_rec[idx], layer, i, px, py);
-        } else {  // more distinct triangles in this block than records: set this one up privately
-            ResolveRec r;
-            resolve_setup(p, gtid[layer], r);
-            resolve_write<DERIV>(p, r, layer, i, px, py);
+            const uint32_t idx = s_idx[slot[q][layer]];
+            if (idx < (uint32_t)RES_CAP) {
+                resolve_write<DERIV>(p, s_rec[idx], layer, i, px, py);
+            } else {  // more distinct triangles in this block than records: set this one up privately
+                ResolveRec r;
+                resolve_setup(p, gtid[q][layer], r);
+                resolve_write<DERIV>(p, r, layer, i, px, py);
+            }
         }
     }
 }
@@ -1520,7 +1540,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     bin_scan_kernel<<<SCAN_CTAS, 1024, 0, c->stream>>>(p);
     bin_fill_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     tile_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
-    const dim3 res_grid((c->width + RES_W - 1) / RES_W, (c->band_y1 - c->band_y0 + RES_H - 1) / RES_H, 1);
+    const dim3 res_grid((c->width + RES_W - 1) / RES_W, (c->band_y1 - c->band_y0 + RES_H * RES_PX - 1) / (RES_H * RES_PX), 1);
     if (c->materials_textured) resolve_kernel<true><<<res_grid, RES_W * RES_H, 0, c->stream>>>(p);
     else resolve_kernel<false><<<res_grid, RES_W * RES_H, 0, c->stream>>>(p);
     count_launches(5 + extra_launch);
