@@ -5,6 +5,9 @@ defines.  The device side lives in csrc/tr_comm.cu; this module o
 unique id and the 64-byte CUDA-IPC handles between ranks and stitches bands for callers who want a whole image.
 Every function takes the process group to talk over, so the CPU tests can run it on `gloo`.
 """
+import os
+import sys
+
 import numpy as np
 
 from . import host
@@ -80,7 +83,10 @@ def balance_bands(renderer, run_frames, rank, world_size, group=None, iterations
     bounds = [band_rows(h, r, world_size)[0] for r in range(world_size)] + [h]
     if world_size == 1:
         return bounds
-    for _ in range(iterations):
+    log = os.environ.get("TR_BALANCE_LOG")
+    for it in range(iterations):
+        run_frames()             # untimed: the first frames after new boundaries grow buffers (cudaMalloc inside a pass)
+        renderer.sync()
         renderer.enable_timing(True)
         run_frames()
         renderer.sync()
@@ -89,6 +95,8 @@ def balance_bands(renderer, run_frames, rank, world_size, group=None, iterations
         mine = sum(totals[k] for k in ("visibility_ms", "shade_opaque_ms", "shade_transmission_ms", "tonemap_ms")) / max(n, 1)
         every = [None] * world_size
         dist.all_gather_object(every, float(mine), group=group)
+        if log and rank == 0:
+            print(f"balance_bands {it}: rows {bounds} cost ms {[round(v, 3) for v in every]}", file=sys.stderr)
         bounds = balanced_bounds(bounds, every)
         renderer.set_bands(bounds)
     return bounds
