@@ -374,7 +374,7 @@ int32_t tr_destroy(tr_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     comm_release(c);
-    DevBuf* bufs[] = {&c->instances, &c->primitives, &c->materials, &c->lights, &c->lut, &c->mesh_pos, &c->mesh_nrm,
+    DevBuf* bufs[] = {&c->instances, &c->instances_alt, &c->lights_alt, &c->primitives, &c->materials, &c->lights, &c->lut, &c->mesh_pos, &c->mesh_nrm,
                       &c->mesh_uv, &c->mesh_idx, &c->visible_ids, &c->cull_scalars, &c->draws[0], &c->draws[1],
                       &c->draws[2], &c->draws[3], &c->work_prefix, &c->slot_z, &c->slot_first, &c->cluster_aabbs, &c->cluster_counts,
                       &c->cluster_indices, &c->vis[0], &c->vis[1], &c->bin_entries, &c->bin_state, &c->tri_records, &c->dev_status, &c->band_list, &c->hdr, &c->hdr_f32, &c->pyramid,
@@ -398,6 +398,12 @@ int32_t tr_destroy(tr_ctx* c) {
         delete[] c->ev_end;
         delete[] c->ev_used;
     }
+    if (c->upload_stream) {
+        cudaStreamSynchronize(c->upload_stream);
+        cudaStreamDestroy(c->upload_stream);
+    }
+    for (cudaEvent_t e : {c->ev_frame_begin, c->ev_inst_ready, c->ev_lights_ready})
+        if (e) cudaEventDestroy(e);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamDestroy(c->copy_stream);
@@ -455,11 +461,31 @@ static int32_t upload(tr_ctx* c, DevBuf& b, const void* src, size_t bytes) {
     return TR_OK;
 }
 
+// An upload that may run ahead (see tr_internal.h).  Taken when the source is page-locked, a frame has been enqueued, and this
+// buffer has not been uploaded since: `alt` was read last by the frame before the enqueued one, so it is free once the
+// enqueued frame has BEGUN (ev_frame_begin, recorded at the top of tr_frame).  Otherwise the copy goes into the compute stream.
+static int32_t upload_ahead(tr_ctx* c, DevBuf& cur, DevBuf& alt, bool& uploaded, cudaEvent_t& ev_ready, const void* src, size_t bytes) {
+    cudaPointerAttributes attr;
+    const bool pinned = bytes && cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    if (!pinned || !c->frame_begin_valid || uploaded) return upload(c, cur, src, bytes);
+    if (!c->upload_stream) TR_CUDA(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking));
+    if (!ev_ready) TR_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+    TR_TRY(alt.ensure(bytes));
+    TR_CUDA(cudaStreamWaitEvent(c->upload_stream, c->ev_frame_begin, 0));
+    TR_CUDA(cudaMemcpyAsync(alt.p, src, bytes, cudaMemcpyHostToDevice, c->upload_stream));
+    TR_CUDA(cudaEventRecord(ev_ready, c->upload_stream));
+    TR_CUDA(cudaStreamWaitEvent(c->stream, ev_ready, 0));   // everything enqueued from here on sees the new contents
+    std::swap(cur, alt);
+    uploaded = true;
+    return TR_OK;
+}
+
 int32_t tr_set_instances(tr_ctx* c, const tr_instance* instances, uint32_t n) {
     TR_CHECK_CTX(c);
     if (n && !instances) return fail(TR_ERR_INVALID_ARG, "tr_set_instances: null");
     if (n >= (1u << 24)) return fail(TR_ERR_UNSUPPORTED, "tr_set_instances: at most 2^24-1 instances");
-    TR_TRY(upload(c, c->instances, instances, (size_t)n * sizeof(tr_instance)));
+    TR_TRY(upload_ahead(c, c->instances, c->instances_alt, c->inst_uploaded, c->ev_inst_ready, instances, (size_t)n * sizeof(tr_instance)));
     c->n_instances = n;
     c->h_inst_prim.resize(n);
     c->h_inst_mat.resize(n);
@@ -523,7 +549,7 @@ int32_t tr_set_materials(tr_ctx* c, const tr_material_info* materials, uint32_t 
 int32_t tr_set_lights(tr_ctx* c, const tr_light* lights, uint32_t n) {
     TR_CHECK_CTX(c);
     if (n && !lights) return fail(TR_ERR_INVALID_ARG, "tr_set_lights: null");
-    TR_TRY(upload(c, c->lights, lights, (size_t)n * sizeof(tr_light)));
+    TR_TRY(upload_ahead(c, c->lights, c->lights_alt, c->lights_uploaded, c->ev_lights_ready, lights, (size_t)n * sizeof(tr_light)));
     c->n_lights = n;
     c->cluster_lights_valid = false;
     return TR_OK;
@@ -809,6 +835,11 @@ int32_t tr_frame(tr_ctx* c, const tr_frame_params* f) {
     TR_CHECK_CTX(c);
     if (!f) return fail(TR_ERR_INVALID_ARG, "tr_frame: null");
     timing_next_frame(c);
+    // everything the previous frame read is free from here on: the mark the next frame's uploads wait for (upload_ahead)
+    if (!c->ev_frame_begin) TR_CUDA(cudaEventCreateWithFlags(&c->ev_frame_begin, cudaEventDisableTiming));
+    TR_CUDA(cudaEventRecord(c->ev_frame_begin, c->stream));
+    c->frame_begin_valid = true;
+    c->inst_uploaded = c->lights_uploaded = false;
     if (!(f->flags & TR_FRAME_SKIP_VISIBILITY)) {
         TR_TRY(tr_cull(c, &f->culling));
     }

@@ -112,6 +112,14 @@ struct tr_ctx {
     bool (*ev_used)[tr::P_COUNT] = nullptr;
     uint64_t timing_frame = 0, timing_first = 0;  // current frame number / first frame not yet summed
 
+    // per-frame uploads (instances, lights) from page-locked memory run ahead of the frame that uses them: on their own
+    // stream, into the buffer the frame BEFORE the enqueued one read last, while the enqueued frame is still shading
+    // (tr_api.cu upload_ahead).  A copy inside the compute stream costs two engine switches, ~40 us per upload.
+    tr::DevBuf instances_alt, lights_alt;
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t ev_frame_begin = nullptr, ev_inst_ready = nullptr, ev_lights_ready = nullptr;
+    bool frame_begin_valid = false, inst_uploaded = false, lights_uploaded = false;   // the latter two: since the last tr_frame
+
     // asynchronous read-back of the sRGB8 band (overlaps the next frame)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_frame_done = nullptr, ev_copy_done = nullptr;
