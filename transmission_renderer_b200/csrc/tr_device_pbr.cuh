@@ -179,10 +179,24 @@ TRD float exact_noh(f3 n, f3 v, f3 l) {
     return fmaxf(xdot3(n, h), TR_F32_EPSILON);
 }
 
+// sm_100a retires two fp32 FMAs per issue slot as one packed instruction (PTX fma.rn.f32x2, SASS FFMA2) when both halves
+// live in an aligned register pair.  The accumulators are kept as such pairs — (d, s0) and (s1, t1) per colour channel —
+// and the light table stores every colour channel twice, so one FFMA2 adds (colour, colour) * (w_a, w_b) to both sums.
+typedef unsigned long long f32x2;
+TRD f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+TRD void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+TRD void ffma2(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+TRD f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+TRD f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+TRD f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+TRD f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // ---- the light loop's fast regime ("lean" form) -----------------------------------------------------------
 // Everything the loop needs of a pixel, and nothing else (registers are what bounds the kernels' occupancy):
 struct LoopPixel {
     f3 pos, n, v;                           // world position, unit normal, unit view vector
+    f32x2 pos_xy, n_xy, v_xy;               // their x and y as packed pairs: the loop's vector adds / scales take x and y in one
+                                            // instruction (FADD2 / FMUL2 / FFMA2); the same registers as above, no copies
     float nov_raw, nov;                     // n.v, and Dot::new's clamp of it (lib.rs:92-99)
     float a2, a2m1, one_m_a2, s_nov;        // reflection lobe: alpha^2, alpha^2 - 1, 1 - alpha^2, sqrt(nov^2 (1 - a2) + a2)
     float omf0m, ndfm;                      // 1 - f0[m] and -(f90 - f0)[m] / 32, m = the channel with the largest f0 (see below)
@@ -205,6 +219,7 @@ TRD float pick3(f3 a, uint32_t i) { return i == 0u ? a.x : (i == 1u ? a.y : a.z)
 TRD LoopPixel make_loop_pixel(const PixelShading& s, f3 pos) {
     LoopPixel q;
     q.pos = pos; q.n = s.n; q.v = s.v;
+    q.pos_xy = pack2(pos.x, pos.y); q.n_xy = pack2(s.n.x, s.n.y); q.v_xy = pack2(s.v.x, s.v.y);
     q.nov_raw = s.nov_raw; q.nov = s.nov;
     q.a2 = s.a2; q.a2m1 = s.a2m1; q.one_m_a2 = s.one_m_a2; q.s_nov = s.s_nov;
     const uint32_t m = argmax3(s.f0);
@@ -214,13 +229,6 @@ TRD LoopPixel make_loop_pixel(const PixelShading& s, f3 pos) {
     return q;
 }
 
-// sm_100a retires two fp32 FMAs per issue slot as one packed instruction (PTX fma.rn.f32x2, SASS FFMA2) when both halves
-// live in an aligned register pair.  The accumulators are kept as such pairs — (d, s0) and (s1, t1) per colour channel —
-// and the light table stores every colour channel twice, so one FFMA2 adds (colour, colour) * (w_a, w_b) to both sums.
-typedef unsigned long long f32x2;
-TRD f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-TRD void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-TRD void ffma2(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 struct Colour2 { f32x2 r, g, b; };   // (r, r), (g, g), (b, b)
 TRD Colour2 dup_colour(f3 c) { Colour2 k; k.r = pack2(c.x, c.x); k.g = pack2(c.y, c.y); k.b = pack2(c.z, c.z); return k; }
 TRD float lo2(f32x2 v) { float a, b; unpack2(v, a, b); return a; }
@@ -250,7 +258,10 @@ struct LoopSums {
 template <bool TRANS, typename ExactDir>
 TRD void light_lean(const LoopPixel& s, ExactDir exact_dir, f3 l, float nol_raw, const Colour2& colour, float factor, LoopSums& a) {
     const float nol = fmaxf(nol_raw, TR_F32_EPSILON);
-    const f3 h = add3(s.v, l);
+    const f32x2 h_xy = add2(s.v_xy, pack2(l.x, l.y));
+    f3 h;
+    unpack2(h_xy, h.x, h.y);
+    h.z = s.v.z + l.z;
     const float h2 = fmaxf(dot3(h, h), 1e-30f);
     const float r = frsqrt(h2);
     const float noh = fmaxf((s.nov_raw + nol_raw) * r, TR_F32_EPSILON);
@@ -262,7 +273,10 @@ TRD void light_lean(const LoopPixel& s, ExactDir exact_dir, f3 l, float nol_raw,
     float nolt = 0.0f, ft = 1.0f, yt = 0.0f, ggxt = 1.0f;
     if (TRANS) {
         nolt = fmaxf(-nol_raw, TR_F32_EPSILON);
-        const f3 ht = fma3(s.n, -2.0f * nol_raw, h);
+        const float k2 = -2.0f * nol_raw;
+        f3 ht;
+        unpack2(fma2(s.n_xy, pack2(k2, k2), h_xy), ht.x, ht.y);
+        ht.z = fmaf(s.n.z, k2, h.z);
         const float ht2 = fmaxf(dot3(ht, ht), 1e-30f);
         const float rt = frsqrt(ht2);
         const float noht = fmaxf((s.nov_raw - nol_raw) * rt, TR_F32_EPSILON);
@@ -314,9 +328,13 @@ TRD void light_lean(const LoopPixel& s, ExactDir exact_dir, f3 l, float nol_raw,
 // `spot(dir, factor)` may scale the factor (Light::spotlight_factor, opaque loop only).
 template <bool TRANS, typename Spot>
 TRD void point_light_lean(const LoopPixel& lp, f3 light_position, const Colour2& colour, Spot spot, LoopSums& sums) {
-    const f3 vec = sub3(light_position, lp.pos);
+    const f32x2 vec_xy = sub2(pack2(light_position.x, light_position.y), lp.pos_xy);
+    f3 vec, dir;
+    unpack2(vec_xy, vec.x, vec.y);
+    vec.z = light_position.z - lp.pos.z;
     const float inv_d = frsqrt(dot3(vec, vec));
-    const f3 dir = scale3(vec, inv_d);
+    unpack2(mul2(vec_xy, pack2(inv_d, inv_d)), dir.x, dir.y);
+    dir.z = vec.z * inv_d;
     float factor = inv_d * inv_d;
     spot(dir, factor);
     light_lean<TRANS>(lp, [&]() { return exact_light_dir(vec); }, dir, dot3(lp.n, dir), colour, factor, sums);
