@@ -587,8 +587,10 @@ def run_b200(args, wl):
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
+        t_host = time.perf_counter()
         for i in range(args.steps):
             e2e_step(i)
+        host_submit_ms = (time.perf_counter() - t_host) * 1e3 / args.steps   # host time to ENQUEUE a step (no waiting in it)
         r.wait_readback()            # the last band is on the host before the clock stops
         ev1.record(stream)
         sync()
@@ -673,7 +675,7 @@ def run_b200(args, wl):
                                "mean_lights_opaque": work["mean_lights_opaque"], "mean_lights_transmissive": work["mean_lights_transmissive"]},
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} | {"samples": clocks["samples"]},
             "e2e": {"value": e2e_value, "unit": "Mpx/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d) * frames_per_step,
-                    "d2h_bytes_per_step": int(d2h) * frames_per_step},
+                    "d2h_bytes_per_step": int(d2h) * frames_per_step, "host_submit_ms_per_step": host_submit_ms},
             "gpu_launches": int(launches),
             "sustained": sustained,
             "passes_ms": passes,
