@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry, s_prev;
     const uint32_t n = p.n_lists, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // n is a multiple of 32
-    const uint32_t per = ((n / 4 + SCAN_CTAS - 1) / SCAN_CTAS) * 4;                      // lists per CTA, a multiple of 4
+    const uint32_t per = ((n / 4 + gridDim.x - 1) / gridDim.x) * 4;                      // lists per CTA, a multiple of 4
     const uint32_t begin = min(blockIdx.x * per, n), end = min(begin + per, n);
     // pass 1: this slice's total
     uint32_t sum = 0;
@@ -1537,7 +1537,8 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
         extra_launch = 1;
     }
     bin_count_kernel<<<c->sm_count * TR_BIN_WAVES * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
-    bin_scan_kernel<<<SCAN_CTAS, 1024, 0, c->stream>>>(p);
+    // one CTA per 8192 lists, at most SCAN_CTAS: a small band's few thousand lists are not worth a chain of 32 waiting CTAs
+    bin_scan_kernel<<<std::max(1u, std::min<uint32_t>(SCAN_CTAS, (p.n_lists + 8191u) / 8192u)), 1024, 0, c->stream>>>(p);
     bin_fill_kernel<<<c->sm_count * 2 * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     tile_kernel<<<tile_grid, TILE_THREADS, tile_smem, c->stream>>>(p);
     const dim3 res_grid((c->width + RES_W - 1) / RES_W, (c->band_y1 - c->band_y0 + RES_H * RES_PX - 1) / (RES_H * RES_PX), 1);

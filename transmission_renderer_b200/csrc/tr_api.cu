@@ -402,6 +402,12 @@ int32_t tr_destroy(tr_ctx* c) {
         cudaStreamSynchronize(c->upload_stream);
         cudaStreamDestroy(c->upload_stream);
     }
+    if (c->side_stream) {
+        cudaStreamSynchronize(c->side_stream);
+        cudaStreamDestroy(c->side_stream);
+        cudaEventDestroy(c->ev_fork);
+        cudaEventDestroy(c->ev_join);
+    }
     for (cudaEvent_t e : {c->ev_frame_begin, c->ev_inst_ready, c->ev_lights_ready})
         if (e) cudaEventDestroy(e);
     if (c->copy_stream) {
@@ -840,11 +846,29 @@ int32_t tr_frame(tr_ctx* c, const tr_frame_params* f) {
     TR_CUDA(cudaEventRecord(c->ev_frame_begin, c->stream));
     c->frame_begin_valid = true;
     c->inst_uploaded = c->lights_uploaded = false;
+    const bool side = c->n_lights && !(f->flags & TR_FRAME_SKIP_VISIBILITY);
+    if (side) {   // K2 beside K1 + K3: fork here, join before the opaque pass reads the light lists
+        if (!c->side_stream) {
+            TR_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+            TR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            TR_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+        TR_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        TR_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+        cudaStream_t main_stream = c->stream;
+        c->stream = c->side_stream;            // the pass and its timer events go to the side stream
+        const int32_t st = tr_assign_lights(c, &f->assign_lights);
+        c->stream = main_stream;
+        if (st != TR_OK) return st;
+        TR_CUDA(cudaEventRecord(c->ev_join, c->side_stream));
+    } else if (c->n_lights) {
+        TR_TRY(tr_assign_lights(c, &f->assign_lights));
+    }
     if (!(f->flags & TR_FRAME_SKIP_VISIBILITY)) {
         TR_TRY(tr_cull(c, &f->culling));
+        TR_TRY(tr_visibility(c, &f->push_constants));
     }
-    if (c->n_lights) TR_TRY(tr_assign_lights(c, &f->assign_lights));
-    if (!(f->flags & TR_FRAME_SKIP_VISIBILITY)) TR_TRY(tr_visibility(c, &f->push_constants));
+    if (side) TR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     // peer-store path: a peer's opaque pass writes into THIS rank's mip 0, which the previous frame's transmissive
     // pass may still be sampling -> cross-GPU barrier before anybody starts shading
     if (c->n_ranks > 1 && c->peers_attached) TR_TRY(comm_barrier(c));

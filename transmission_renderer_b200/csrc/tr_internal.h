@@ -120,6 +120,11 @@ struct tr_ctx {
     cudaEvent_t ev_frame_begin = nullptr, ev_inst_ready = nullptr, ev_lights_ready = nullptr;
     bool frame_begin_valid = false, inst_uploaded = false, lights_uploaded = false;   // the latter two: since the last tr_frame
 
+    // tr_frame runs the light assignment (K2) on a side stream beside the cull and the visibility pass: they share nothing,
+    // and each is a few small launches that leave most of the GPU idle
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
     // asynchronous read-back of the sRGB8 band (overlaps the next frame)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_frame_done = nullptr, ev_copy_done = nullptr;
