@@ -12,7 +12,8 @@
  * deterministic.  Transcendentals used in discrete decisions
  * (powf in slice_to_depth, cos/sin in cull_spotlight) are evaluated in double
  * and rounded to f32 on both sides (DESIGN.md "discrete decisions").
- * PARITY UNPINNED (oracle.h).
+ * PARITY: pinned bit-exact to the reference's compiled frustum_culling.spv, demultiplex_draws.spv, write_cluster_data.spv and
+ * assign_lights_to_clusters.spv (oracle.h, tests/test_reference_spirv.py).
  */
 #include "oracle.h"
 

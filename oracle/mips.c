@@ -12,7 +12,7 @@
  *       centres at +0.5, clamp-to-edge), lerp x then y in fp32,
  *   one round-to-nearest-even to fp16 per level.
  * For even source sizes the fractions are exactly 0.5 (2x2 box).
- * PARITY UNPINNED at this boundary (hardware behaviour in the reference).
+ * PARITY: NOT PINNABLE at this boundary (vkCmdBlitImage: hardware behaviour in the reference; the filter is ours, oracle.h).
  */
 #include "oracle.h"
 

@@ -6,11 +6,25 @@
  * reference legs may load it.  The product (transmission_renderer_b200/csrc)
  * never links, imports or falls back to anything in this directory.
  *
- * PARITY UNPINNED: /root/reference has no tests, golden vectors or known-answer
- * fixtures, and it cannot be built here (Rust -> SPIR-V, no cargo/rustc, no
- * Vulkan ICD).  The restatement is pinned instead by (i) known answers derived
- * from the source text (tests/test_oracle_kat.py) and
- * (ii) an independent float64 numpy restatement (tests/ref_f64.py).
+ * PARITY: PINNED TO THE REFERENCE'S OWN COMPILED CODE for every stage the reference
+ * runs in a shader.  /root/reference has no tests or golden vectors and cannot be
+ * built here (Rust -> SPIR-V, no cargo/rustc, no Vulkan ICD), but it ships its shaders
+ * compiled: compiled-shaders/normal/<stage>.spv.  oracle/spv2c.py translates those modules to
+ * C one SPIR-V instruction per statement, oracle/spv_harness.c runs them with the
+ * reference's descriptor interface (oracle/build_ref.py -> oracle/_ref/libspvref.so), and
+ * tests/test_reference_spirv.py requires this restatement to match them: bit-exact for
+ * frustum_culling, demultiplex_draws, write_cluster_data, assign_lights_to_clusters (as
+ * ascending sets), vertex_instanced_with_scale, fragment and fragment_transmission (fp32
+ * pixels of whole frames), depth_pre_pass_alpha_clip (kill decisions), fragment_tonemap
+ * (sRGB8).  The modules' outputs on the cases of tests/spirv_cases.py are committed as
+ * tests/golden/spirv_golden.npz, so the check also runs where /root/reference is absent.
+ * Also kept: known answers derived from the source text (tests/test_oracle_kat.py) and
+ * an independent float64 numpy restatement (tests/ref_f64.py).
+ * NOT pinned, because the reference used fixed-function hardware or host code there and
+ * the definition is ours: the rasterisation rules
+ * (raster.c), image sampling and RGBA16F stores, the blit filter of the mip chain
+ * (mips.c), the ray/triangle arithmetic of ray queries (shadow.c), and colstodian's baked
+ * tonemapper constants (caller input).  Those files say so.
  *
  * Third-party arithmetic absent from /root/reference and restated here from
  * its published behaviour: glam 0.19.0 (vector ops, vecmath.h), libm 0.2.1 /

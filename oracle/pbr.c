@@ -3,7 +3,8 @@
  * Restatement of /root/reference/glam-pbr/src/lib.rs (whole file) in plain C.
  * Every function cites the lines it follows; operation order follows the Rust
  * expression trees (left-to-right, operator precedence) so fp32 rounding is
- * the reference's to within libm differences.  PARITY UNPINNED (oracle.h).
+ * the reference's to within libm differences.  PARITY: pinned through shade.c's callers to the reference's compiled
+ * fragment.spv / fragment_transmission.spv, bit-equal fp32 pixels (oracle.h, tests/test_reference_spirv.py).
  */
 #include "oracle.h"
 

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY — importable from tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs.  The product package never
-imports this module.  PARITY UNPINNED (see oracle/oracle.h).
+imports this module.  Parity: pinned to the reference's compiled shader modules (see oracle/oracle.h).
 """
 import ctypes as C
 import os

@@ -13,8 +13,9 @@
  * (glTF), a top-left style tie rule that is exact for shared edges, nearest
  * fragment wins with ties broken by the smaller global triangle id, and the
  * transmissive layer is depth-tested GREATER against the final opaque depth.
- * PARITY UNPINNED (oracle.h) — only self-consistency with the CUDA kernel is
- * checked, bit for bit.
+ * PARITY: NOT PINNABLE — the reference rasterises in fixed-function hardware; the rules are ours (oracle.h), and
+ * self-consistency with the CUDA kernel is checked bit for bit.  The vertex stage that feeds it IS pinned
+ * (vertex_instanced_with_scale.spv, byte-equal).
  */
 #include "oracle.h"
 

@@ -10,7 +10,10 @@
  * rasteriser's varying interpolation, including the texture-mapped branches
  * (`textures.* != -1`: lighting.rs:222-313, lib.rs:66-77,120-124,190-194) with a
  * software restatement of the repeat sampler and implicit level of detail.
- * PARITY UNPINNED (oracle.h).
+ * PARITY: pinned to the reference's compiled fragment.spv, fragment_transmission.spv, vertex_instanced_with_scale.spv and
+ * depth_pre_pass_alpha_clip.spv: bit-equal fp32 pixels on whole frames (with a normal map <= 8e-6: the shipped module is
+ * stale there).  The sampling rules themselves (what the Vulkan implementation supplied) are OURS to define
+ * and are shared with the harness that runs the modules (oracle.h, tests/test_reference_spirv.py).
  */
 #include "oracle.h"
 

@@ -13,8 +13,8 @@
  *                                   alpha-clip geometry casts shadows, transmissive geometry does not)
  *   src/main.rs:2734-2754           instance transform = the instance's Similarity
  *
- * The ray/triangle arithmetic of VK_KHR_ray_query is implementation-defined; "parity unpinned" applies here as it does
- * to the rasteriser.  The definition used on both sides (DESIGN.md "Ray-queried shadows"):
+ * The ray/triangle arithmetic of VK_KHR_ray_query is implementation-defined (hardware in the reference): parity is NOT
+ * PINNABLE here, as for the rasteriser — the definition is ours (oracle.h).  The definition used on both sides (DESIGN.md "Ray-queried shadows"):
  *
  *   occluded(ray) :=  exists an instance i of the top-level set with  slab(world ray, world_box_i)  and a triangle k of
  *                     its primitive with  slab(object ray_i, box_k)  and  hit64(object ray_i, triangle k)

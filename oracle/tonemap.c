@@ -13,7 +13,8 @@
  * Defined behaviour for non-finite / negative input: an RGBA16F store overflows to +inf above
  * 65504 and the reference's formula then evaluates inf/inf; we clamp each input component to
  * [0, 65504] and map NaN to 0 before tonemapping.
- * PARITY UNPINNED (oracle.h).
+ * PARITY: pinned to the reference's compiled fragment_tonemap.spv + this sRGB encode (sRGB8 equal on 9 000 pixels, black
+ * excluded: 0/0 in the reference); the baked constants are caller input (oracle.h, tests/test_reference_spirv.py).
  */
 #include "oracle.h"
 

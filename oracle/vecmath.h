@@ -11,7 +11,7 @@
  *   Quat * Vec3 = v*(w*w - b.b) + b*(2*(v.b)) + (b x v)*(2w),  b = q.xyz
  *   Vec3 / f32  = three divides
  * Build with -ffp-contract=off so no FMA contraction changes the rounding.
- * PARITY UNPINNED: the reference ships no tests / golden vectors.
+ * PARITY: pinned through its users to the reference's compiled shader modules (oracle.h).
  */
 #ifndef ORACLE_VECMATH_H
 #define ORACLE_VECMATH_H
