@@ -11,9 +11,16 @@
 // needs a neighbour): level 0 is read from HBM exactly once with 128-bit
 // loads, level 1/2 are produced in registers, deeper levels in shared memory.
 // The few remaining small levels (first odd-sized source onwards, <= 240x135
-// at 4K) are finished by the last CTA to retire (atomic ticket), out of L2.
+// at 4K: 10.7 k texels in seven levels, each depending on the one before) are
+// built by a second launch of ONE thread-block cluster: eight CTAs x 1024
+// threads, a hardware cluster barrier between levels, out of L2.  (Round 1 let
+// the last CTA of the first launch do it alone: 256 threads, ~13 of the pass's
+// 40 us, and a ticket + fence in every CTA.)
+#include <cooperative_groups.h>
+
 #include "tr_internal.h"
 
+namespace cg = cooperative_groups;
 using namespace trd;
 
 namespace {
@@ -60,7 +67,6 @@ __global__ void __launch_bounds__(256) mip_kernel(const __grid_constant__ MipPar
     __shared__ uint2 s3[8][9];
     __shared__ uint2 s4[4][5];
     __shared__ uint2 s5[2][3];
-    __shared__ uint32_t s_last;
     const int tid = threadIdx.x;
 
     if (p.n_local >= 1) {
@@ -148,52 +154,28 @@ __global__ void __launch_bounds__(256) mip_kernel(const __grid_constant__ MipPar
         }
     }
 
-    if (p.n_local + 1 >= p.levels) return;  // no tail levels
+}
 
-    // ---- ticket: the last CTA to finish its tile builds the remaining small levels
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t total = gridDim.x * gridDim.y;
-        const uint32_t ticket = atomicAdd(p.counter, 1u);
-        s_last = ticket == total - 1;
-        if (s_last) *p.counter = 0;  // re-arm for the next launch
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-
+constexpr int TAIL_CLUSTER = 8, TAIL_THREADS = 1024;
+__global__ void __cluster_dims__(TAIL_CLUSTER, 1, 1) __launch_bounds__(TAIL_THREADS) mip_tail_kernel(const __grid_constant__ MipParams p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t t = cluster.block_rank() * TAIL_THREADS + threadIdx.x, nt = TAIL_CLUSTER * TAIL_THREADS;
     for (uint32_t l = p.n_local + 1; l < p.levels; l++) {
         const uint32_t sw = p.w[l - 1], sh = p.h[l - 1], dw = p.w[l], dh = p.h[l];
         const uint2* src = p.base + p.off[l - 1];
         uint2* dst = p.base + p.off[l];
-        // four texels per thread per step: their 16 source loads are in flight together (the tail runs on one CTA,
-        // so latency, not bandwidth, is what it waits for)
-        for (uint32_t i0 = tid; i0 < dw * dh; i0 += blockDim.x * 4) {
-            uint2 t[4][4];
-            float fxs[4], fys[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t i = i0 + u * blockDim.x;
-                if (i < dw * dh) {
-                    const uint32_t dy = i / dw, dx = i - dy * dw;
-                    uint32_t x0, x1, y0, y1;
-                    axis_setup(dx, sw, dw, x0, x1, fxs[u]);
-                    axis_setup(dy, sh, dh, y0, y1, fys[u]);
-                    t[u][0] = __ldcg(src + (size_t)y0 * sw + x0);
-                    t[u][1] = __ldcg(src + (size_t)y0 * sw + x1);
-                    t[u][2] = __ldcg(src + (size_t)y1 * sw + x0);
-                    t[u][3] = __ldcg(src + (size_t)y1 * sw + x1);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t i = i0 + u * blockDim.x;
-                if (i < dw * dh) dst[i] = filter4(t[u][0], t[u][1], t[u][2], t[u][3], fxs[u], fys[u]);
-            }
+        for (uint32_t i = t; i < dw * dh; i += nt) {
+            const uint32_t dy = i / dw, dx = i - dy * dw;
+            uint32_t x0, x1, y0, y1;
+            float fx, fy;
+            axis_setup(dx, sw, dw, x0, x1, fx);
+            axis_setup(dy, sh, dh, y0, y1, fy);
+            // .cg: the source level was written by other CTAs (the first launch, or this cluster one barrier ago)
+            dst[i] = filter4(__ldcg(src + (size_t)y0 * sw + x0), __ldcg(src + (size_t)y0 * sw + x1), __ldcg(src + (size_t)y1 * sw + x0),
+                             __ldcg(src + (size_t)y1 * sw + x1), fx, fy);
         }
         __threadfence();
-        __syncthreads();
+        cluster.sync();   // barrier.cluster, release / acquire: the level is complete and visible to all eight CTAs
     }
 }
 
@@ -219,8 +201,16 @@ int32_t launch_generate_mips(uint2* pyramid, uint32_t levels, const uint32_t* w,
     p.n_local = n_local;
     dim3 grid(1, 1, 1);
     if (n_local >= 1) grid = dim3((w[0] + 63) / 64, (h[0] + 63) / 64, 1);
-    mip_kernel<<<grid, 256, 0, s>>>(p);
-    count_launches(1);
+    int launches = 0;
+    if (n_local >= 1) {
+        mip_kernel<<<grid, 256, 0, s>>>(p);
+        launches++;
+    }
+    if (n_local + 1 < levels) {
+        mip_tail_kernel<<<TAIL_CLUSTER, TAIL_THREADS, 0, s>>>(p);
+        launches++;
+    }
+    count_launches(launches);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
