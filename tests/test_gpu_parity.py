@@ -405,14 +405,19 @@ def _upload_scene(r, lut, s):
     r.build_clusters(s["camera"].write_cluster_data())
 
 
-@pytest.mark.parametrize("kind,size,tile_edge,split", [("grid", (640, 360), None, None), ("instanced", (480, 270), None, None),
-                                                       ("instanced", (333, 187), None, None), ("instanced", (480, 270), 64, 0),
-                                                       ("grid", (640, 360), 64, 0), ("instanced", (960, 540), 32, None),
-                                                       ("instanced", (960, 540), 64, 1), ("grid", (640, 360), 64, 1)])
-def test_visibility_bit_exact(oracle, ggx_lut, kind, size, tile_edge, split, monkeypatch):
+@pytest.mark.parametrize("kind,size,tile_edge,split,front", [("grid", (640, 360), None, None, None), ("instanced", (480, 270), None, None, None),
+                                                             ("instanced", (333, 187), None, None, None), ("instanced", (480, 270), 64, 0, None),
+                                                             ("grid", (640, 360), 64, 0, None), ("instanced", (960, 540), 32, None, None),
+                                                             ("instanced", (960, 540), 64, 1, None), ("grid", (640, 360), 64, 1, None),
+                                                             ("instanced", (960, 540), None, None, "TR_NO_CHUNK_CULL"),
+                                                             ("instanced", (960, 540), None, None, "TR_NO_BLOCK_ENTRY")])
+def test_visibility_bit_exact(oracle, ggx_lut, kind, size, tile_edge, split, front, monkeypatch):
     """tile_edge forces the rasteriser's 64- or 32-pixel tile instantiation (it otherwise follows the frame size, so the
     small test frames would only ever run the 32-pixel one and the 4K benchmark only the 64-pixel one); split forces the
-    quadrant jobs of heavy tiles on (a many-GPU band's path) or off."""
+    quadrant jobs of heavy tiles on (a many-GPU band's path) or off; front switches one shortcut of the binning front end
+    off (the chunk-sphere test against the frame / band planes, the 256-triangle entry table), so both forms stay pinned."""
+    if front is not None:
+        monkeypatch.setenv(front, "1")
     if tile_edge is not None:
         monkeypatch.setenv("TR_TILE_EDGE", str(tile_edge))
     if split is not None:

@@ -31,7 +31,11 @@ struct CullParams {
     uint32_t* work_prefix;      // [n_inst + 1] exclusive triangle prefix per visible slot
     uint32_t* scalars;          // [0] n_visible, [1] total triangles (low 32), [2..5] draw_counts, [6] ~min / [7] max bits of slot_z
     float* slot_z;              // [n_inst] nearest view-space depth of each visible instance (front-to-back binning in K3)
-    uint2* slot_prim;           // [n_inst] (first_index, draw_buffer_index) of the slot's primitive: K3 skips the instance -> primitive hop
+    uint4* slot_prim;           // [n_inst] (first_index, draw_buffer_index, first culling chunk, 0) of the slot's primitive: K3 skips the
+                                // instance -> primitive hop
+    uint32_t* block_entry;      // [work-list triangles / 256 + 1] the slot that holds triangle 256 b: K3's binning pass starts there instead of
+                                // searching the prefix (twelve dependent loads per warp)
+    const uint32_t* prim_chunk_base;   // [n_prims + 1] first culling chunk of each primitive (ensure_chunks)
 };
 
 // shader/src/lib.rs:442-469, exact regime
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(CULL_THREADS) cull_kernel(const __grid_constan
     const uint32_t i = bid * CULL_THREADS + tid;
 
     bool visible = false;
-    uint32_t tris = 0, first_index = 0, draw_buffer = 0;
+    uint32_t tris = 0, first_index = 0, draw_buffer = 0, chunk_base = 0;
     float nearest_z = 0.0f;
     if (i < p.n_inst) {
         const float4* q = reinterpret_cast<const float4*>(p.inst + i);
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(CULL_THREADS) cull_kernel(const __grid_constan
             tris = pinfo.y / 3u;
             first_index = pinfo.z;
             draw_buffer = pinfo.x;
+            chunk_base = __ldg(p.prim_chunk_base + prim);
             atomicAdd(p.instance_counts + prim, 1u);  // lib.rs:437-439
         }
     }
@@ -134,7 +139,9 @@ __global__ void __launch_bounds__(CULL_THREADS) cull_kernel(const __grid_constan
         p.visible_ids[slot] = i;
         p.work_prefix[slot] = (uint32_t)(base >> VIS_BITS);
         p.slot_z[slot] = nearest_z;
-        p.slot_prim[slot] = make_uint2(first_index, draw_buffer);
+        p.slot_prim[slot] = make_uint4(first_index, draw_buffer, chunk_base, 0u);
+        const uint32_t t0 = (uint32_t)(base >> VIS_BITS);
+        for (uint32_t b = (t0 + 255u) >> 8; (b << 8) < t0 + tris; b++) p.block_entry[b] = slot;
     }
     // depth range of the visible set (positive floats order like their bit patterns)
     const uint32_t zb = visible ? __float_as_uint(nearest_z) : 0u;
@@ -219,8 +226,14 @@ int32_t launch_cull(tr_ctx* c, const tr_culling_push_constants& pc) {
     TR_TRY(c->cull_scalars.ensure(state_bytes));
     TR_TRY(c->visible_ids.ensure((size_t)c->n_instances * 4));
     TR_TRY(c->work_prefix.ensure(((size_t)c->n_instances + 1) * 4));
+    {   // one table for K1's list, one behind it for a band's own list (band_filter_kernel)
+        uint64_t tris = 0;
+        for (uint32_t pid : c->h_inst_prim) tris += c->h_prim_tris[pid];
+        TR_TRY(c->block_entry.ensure((size_t)(tris / 256 + 2) * 2 * 4));
+    }
     TR_TRY(c->slot_z.ensure((size_t)c->n_instances * 4));
-    TR_TRY(c->slot_first.ensure((size_t)c->n_instances * 8));
+    TR_TRY(c->slot_first.ensure((size_t)c->n_instances * 16));
+    TR_TRY(ensure_chunks(c));
     for (int b = 0; b < 4; b++) TR_TRY(c->draws[b].ensure((size_t)c->n_primitives * sizeof(tr_draw_indexed_indirect_command)));
     unsigned char* st = c->cull_scalars.as<unsigned char>();
     // zeroing the instance count / draw count buffers, main.rs:1669-1700
@@ -238,8 +251,10 @@ int32_t launch_cull(tr_ctx* c, const tr_culling_push_constants& pc) {
     p.instance_counts = reinterpret_cast<uint32_t*>(st + counts_off);
     p.visible_ids = c->visible_ids.as<uint32_t>();
     p.work_prefix = c->work_prefix.as<uint32_t>();
+    p.block_entry = c->block_entry.as<uint32_t>();
     p.slot_z = c->slot_z.as<float>();
-    p.slot_prim = c->slot_first.as<uint2>();
+    p.slot_prim = c->slot_first.as<uint4>();
+    p.prim_chunk_base = c->prim_chunk_base.as<uint32_t>();
     p.scalars = reinterpret_cast<uint32_t*>(st + scalars_off);
     cull_kernel<<<n_blocks, CULL_THREADS, 0, c->stream>>>(p);
     count_launches(2);

@@ -49,13 +49,18 @@ struct VisParams {
     const uint32_t* work_prefix;  // [n_visible + 1]
     const uint32_t* scalars;      // [0] n_visible, [1] total triangles, [6] ~min / [7] max bits of slot_z
     const float* slot_z;          // [n_visible] nearest view depth of the instance in each slot
-    const uint2* slot_prim;       // [n_visible] (first_index, draw_buffer_index) of the slot's primitive, from K1
+    const uint4* slot_prim;       // [n_visible] (first_index, draw_buffer_index, first culling chunk, 0) of the slot's primitive, from K1
+    const float4* chunk_spheres;  // object-space bounding sphere per TR_CHUNK_TRIS triangles of every primitive; nullptr: no chunk culling
+    float4 cull_plane[4];         // world-space planes (xyz, w) whose negative side is off the frame / off the band: left, right, above, below
+    float cull_plane_norm[4];     // |xyz| of each, rounded up
     mat4 proj_view;
     float row_y_norm, row_w_norm;  // |rows 1 and 3 of proj_view (xyz)|: how far a unit world offset moves clip y / w
     uint32_t band_cull;            // the band is a strict part of the frame: the work list holds only instances that can reach it
     const uint32_t* list_prefix;   // [n_list + 1] exclusive triangle prefix of the work list (K1's, or the band's own)
     const uint32_t* list_slots;    // [n_list] visible slot of each entry; nullptr = identity
     const uint32_t* list_scalars;  // [0] n_list, [1] triangles in the list
+    const uint32_t* list_block_entry;   // [triangles in the list / 256 + 1] the entry that holds triangle 256 b of the list
+    uint32_t* band_block_entry;    // the band list's table, written by band_filter_kernel
     uint32_t* band_prefix;         // outputs of band_filter_kernel
     uint32_t* band_slots;
     uint32_t* band_scalars;
@@ -483,7 +488,9 @@ __global__ void __launch_bounds__(1024) band_filter_kernel(const __grid_constant
             if (v[k] & 1ull) {
                 const uint32_t at = (uint32_t)(excl & 0xffffffull);
                 p.band_slots[at] = chunk + tid * PER + k;
-                p.band_prefix[at] = (uint32_t)(excl >> 24);
+                const uint32_t t0 = (uint32_t)(excl >> 24), tris = (uint32_t)(v[k] >> 24);
+                p.band_prefix[at] = t0;
+                for (uint32_t b = (t0 + 255u) >> 8; (b << 8) < t0 + tris; b++) p.band_block_entry[b] = at;
             }
             excl += v[k];
         }
@@ -562,10 +569,12 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __gri
 
     for (uint32_t base = range_begin + (threadIdx.x & ~31u); base < range_end; base += 256u) {
         const uint32_t w = base + lane;
-        if (!have_entry) {
-            entry = find_entry_warp(p.list_prefix, base, min(w, total - 1), n_list);
-            have_entry = true;
-        } else {   // the warp's previous triangles were 256 before these
+        {   // the entry of the range's first triangle comes from K1's (or the band filter's) table; from there, and from the
+            // warp's previous triangles 256 before these, it is a short walk
+            if (!have_entry) {
+                entry = p.list_block_entry ? __ldg(p.list_block_entry + (base >> 8)) : find_entry_warp(p.list_prefix, base, min(w, total - 1), n_list);
+                have_entry = true;
+            }
             const uint32_t wc = min(w, total - 1);
             while (entry + 1 < n_list && __ldg(p.list_prefix + entry + 1) <= wc) entry++;
         }
@@ -578,10 +587,27 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_count_kernel(const __gri
             slot = p.list_slots ? __ldg(p.list_slots + entry) : entry;
             tri = w - __ldg(p.list_prefix + entry);
             const tr_instance* inst = p.instances + __ldg(p.visible_ids + slot);
-            const uint2 prim = __ldg(p.slot_prim + slot);
+            const uint4 prim = __ldg(p.slot_prim + slot);
             const uint32_t bucket = prim.y;
             layer = bucket >> 1;  // draw buffers 0/1 (opaque, alpha clip) -> layer 0, 2/3 -> the transmissive layer
-            keep = bucket < 4u && setup_front(p, inst, prim.x, tri, f) && setup_box(p, f, x_lo, x_hi, y_lo, y_hi);
+            // The chunk of 64 triangles this one belongs to (the warp's 32 share it, so the branch is uniform): when its
+            // bounding sphere lies wholly on the outer side of a frame / band plane, no pixel of the band can see it.  Half of
+            // the triangles of the VISIBLE instances of the 10 k-instance scene go this way, before any vertex is fetched.
+            bool chunk_on = true;
+            if (p.chunk_spheres) {
+                const float4 sph = __ldg(p.chunk_spheres + prim.z + tri / TR_CHUNK_TRIS);
+                const float4 ts = __ldg(reinterpret_cast<const float4*>(inst)), rot = __ldg(reinterpret_cast<const float4*>(inst) + 1);
+                const f3 wc = xadd3(mk3(ts.x, ts.y, ts.z), xscale3(xquat_mul3(rot.x, rot.y, rot.z, rot.w, mk3(sph.x, sph.y, sph.z)), ts.w));
+                const float r = fabsf(sph.w * ts.w) * 1.01f + 1e-3f;   // generous against the fp32 rounding of the centre and the planes
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 pl = p.cull_plane[q];
+                    const float d = fmaf(pl.x, wc.x, fmaf(pl.y, wc.y, fmaf(pl.z, wc.z, pl.w)));
+                    const float slack = r * p.cull_plane_norm[q] + 1e-4f * (fabsf(pl.x * wc.x) + fabsf(pl.y * wc.y) + fabsf(pl.z * wc.z) + fabsf(pl.w));
+                    if (d < -slack) chunk_on = false;
+                }
+            }
+            keep = chunk_on && bucket < 4u && setup_front(p, inst, prim.x, tri, f) && setup_box(p, f, x_lo, x_hi, y_lo, y_hi);
         }
         const uint32_t mask = __ballot_sync(0xffffffffu, keep);
         if (keep) {
@@ -1475,7 +1501,20 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.work_prefix = c->work_prefix.as<uint32_t>();
     p.scalars = c->d_cull_scalars;
     p.slot_z = c->slot_z.as<float>();
-    p.slot_prim = c->slot_first.as<uint2>();
+    p.slot_prim = c->slot_first.as<uint4>();
+    p.chunk_spheres = c->chunk_cull ? c->chunk_spheres.as<float4>() : nullptr;
+    {   // clip-space half spaces x >= -w, x <= w and the band's rows (two pixels of slack) as world-space planes, in double
+        const float* m = reinterpret_cast<const float*>(&pc.proj_view);   // column-major: element (row r, col k) = m[k * 4 + r]
+        auto row = [&](int r, int k) { return (double)m[k * 4 + r]; };
+        const double y_lo = 2.0 * ((double)c->band_y0 - 2.0) / (double)c->height - 1.0, y_hi = 2.0 * ((double)c->band_y1 + 2.0) / (double)c->height - 1.0;
+        for (int q = 0; q < 4; q++) {
+            double pl[4];
+            for (int k = 0; k < 4; k++)
+                pl[k] = q == 0 ? row(3, k) + row(0, k) : q == 1 ? row(3, k) - row(0, k) : q == 2 ? row(1, k) - y_lo * row(3, k) : y_hi * row(3, k) - row(1, k);
+            p.cull_plane[q] = make_float4((float)pl[0], (float)pl[1], (float)pl[2], (float)pl[3]);
+            p.cull_plane_norm[q] = (float)(sqrt(pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2]) * 1.0001);
+        }
+    }
     memcpy(&p.proj_view, &pc.proj_view, sizeof(mat4));
     {
         const float* m = reinterpret_cast<const float*>(&pc.proj_view);  // column-major: element (row r, col k) = m[k * 4 + r]
@@ -1523,7 +1562,10 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
 
     p.list_prefix = p.work_prefix;
     p.list_slots = nullptr;
+    p.list_block_entry = c->block_entry.as<uint32_t>();
+    p.band_block_entry = c->block_entry.as<uint32_t>() + c->max_triangles / 256 + 2;
     p.list_scalars = p.scalars;
+    const bool no_table = getenv("TR_NO_BLOCK_ENTRY") != nullptr;   // A/B switch: search the prefix instead
     int extra_launch = 0;
     if (p.band_cull && c->n_instances <= (1u << 17)) {  // the single-CTA filter is meant for visible sets of this size
         TR_TRY(c->band_list.ensure(((size_t)c->n_instances * 2 + 1 + 4) * 4));
@@ -1533,9 +1575,11 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
         band_filter_kernel<<<1, 1024, 0, c->stream>>>(p);
         p.list_prefix = p.band_prefix;
         p.list_slots = p.band_slots;
+        p.list_block_entry = p.band_block_entry;
         p.list_scalars = p.band_scalars;
         extra_launch = 1;
     }
+    if (no_table) p.list_block_entry = nullptr;
     bin_count_kernel<<<c->sm_count * TR_BIN_WAVES * TR_BIN_CTAS, 256, 0, c->stream>>>(p);
     // one CTA per 8192 lists, at most SCAN_CTAS: a small band's few thousand lists are not worth a chain of 32 waiting CTAs
     bin_scan_kernel<<<std::max(1u, std::min<uint32_t>(SCAN_CTAS, (p.n_lists + 8191u) / 8192u)), 1024, 0, c->stream>>>(p);

@@ -298,6 +298,53 @@ int32_t validate_scene(tr_ctx* c, const char* who) {
     return TR_OK;
 }
 
+// A bounding sphere (object space) per TR_CHUNK_TRIS consecutive triangles of every primitive: the binning pass tests it
+// against the frustum and the band before it touches the chunk's vertices.  Centre = centre of the chunk's box, radius = the
+// farthest vertex (double, rounded up).  Without a mesh, or with a primitive that leaves the index buffer, the test is off.
+int32_t ensure_chunks(tr_ctx* c) {
+    if (c->chunks_valid) return TR_OK;
+    std::vector<uint32_t> base((size_t)c->n_primitives + 1, 0u);
+    std::vector<float> spheres;
+    bool ok = c->n_indices != 0 && c->h_indices.size() == c->n_indices && c->h_positions.size() == (size_t)c->n_vertices * 3;
+    for (uint32_t p = 0; ok && p < c->n_primitives; p++) {
+        const uint64_t first = c->h_prim_first[p], tris = c->h_prim_count[p] / 3;
+        if (first + tris * 3 > c->n_indices) { ok = false; break; }   // validate_scene reports it
+        base[p] = (uint32_t)(spheres.size() / 4);
+        for (uint64_t t0 = 0; t0 < tris; t0 += TR_CHUNK_TRIS) {
+            const uint64_t t1 = std::min<uint64_t>(t0 + TR_CHUNK_TRIS, tris);
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (uint64_t i = first + t0 * 3; i < first + t1 * 3; i++)
+                for (int k = 0; k < 3; k++) {
+                    const double v = c->h_positions[(size_t)c->h_indices[i] * 3 + k];
+                    lo[k] = std::min(lo[k], v);
+                    hi[k] = std::max(hi[k], v);
+                }
+            const double cx = 0.5 * (lo[0] + hi[0]), cy = 0.5 * (lo[1] + hi[1]), cz = 0.5 * (lo[2] + hi[2]);
+            double r2 = 0.0;
+            for (uint64_t i = first + t0 * 3; i < first + t1 * 3; i++) {
+                const float* v = &c->h_positions[(size_t)c->h_indices[i] * 3];
+                const double dx = v[0] - cx, dy = v[1] - cy, dz = v[2] - cz;
+                r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+            }
+            const float fc[3] = {(float)cx, (float)cy, (float)cz};
+            // the centre was rounded to float: widen the radius by that much and by its own rounding
+            const double shift = fabs(fc[0] - cx) + fabs(fc[1] - cy) + fabs(fc[2] - cz);
+            float r = (float)((sqrt(r2) + shift) * (1.0 + 1e-6));
+            if (!(r == r) || !std::isfinite(r)) r = INFINITY;   // non-finite vertices: never culled
+            spheres.insert(spheres.end(), {fc[0], fc[1], fc[2], r});
+        }
+    }
+    base[c->n_primitives] = (uint32_t)(spheres.size() / 4);
+    TR_TRY(c->prim_chunk_base.ensure(base.size() * 4));
+    TR_TRY(c->chunk_spheres.ensure(std::max<size_t>(spheres.size() * 4, 16)));
+    TR_CUDA(cudaMemcpyAsync(c->prim_chunk_base.p, base.data(), base.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (ok && !spheres.empty()) TR_CUDA(cudaMemcpyAsync(c->chunk_spheres.p, spheres.data(), spheres.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    TR_CUDA(cudaStreamSynchronize(c->stream));   // the sources are locals
+    c->chunk_cull = ok && !getenv("TR_NO_CHUNK_CULL");
+    c->chunks_valid = true;
+    return TR_OK;
+}
+
 int32_t check_device_status(tr_ctx* c, const char* who) {
     if (!c->dev_status.p) return TR_OK;
     uint32_t bits = 0;
@@ -376,7 +423,7 @@ int32_t tr_destroy(tr_ctx* c) {
     comm_release(c);
     DevBuf* bufs[] = {&c->instances, &c->instances_alt, &c->lights_alt, &c->primitives, &c->materials, &c->lights, &c->lut, &c->mesh_pos, &c->mesh_nrm,
                       &c->mesh_uv, &c->mesh_idx, &c->visible_ids, &c->cull_scalars, &c->draws[0], &c->draws[1],
-                      &c->draws[2], &c->draws[3], &c->work_prefix, &c->slot_z, &c->slot_first, &c->cluster_aabbs, &c->cluster_counts,
+                      &c->draws[2], &c->draws[3], &c->work_prefix, &c->slot_z, &c->slot_first, &c->block_entry, &c->chunk_spheres, &c->prim_chunk_base, &c->cluster_aabbs, &c->cluster_counts,
                       &c->cluster_indices, &c->vis[0], &c->vis[1], &c->bin_entries, &c->bin_state, &c->tri_records, &c->dev_status, &c->band_list, &c->hdr, &c->hdr_f32, &c->pyramid,
                       &c->srgb8, &c->mip_counter, &c->shade_counter, &c->accel_tlas, &c->accel_blas, &c->accel_inst, &c->accel_tris,
                       &c->shadow_mask[0], &c->shadow_mask[1]};
@@ -516,6 +563,7 @@ int32_t tr_set_primitives(tr_ctx* c, const tr_primitive_info* prims, uint32_t n)
         clip = clip || (prims[i].draw_buffer_index & 1u);
     }
     c->prims_alpha_clip = clip;
+    c->chunks_valid = false;
     TR_TRY(upload(c, c->primitives, prims, (size_t)n * sizeof(tr_primitive_info)));
     c->n_primitives = n;
     c->h_prim_tris.resize(n);
@@ -653,6 +701,9 @@ int32_t tr_set_mesh(tr_ctx* c, const float* positions, const float* normals, con
     TR_TRY(upload(c, c->mesh_idx, indices, (size_t)n_indices * 4));
     c->n_vertices = n_vertices;
     c->n_indices = n_indices;
+    c->h_positions.assign(positions, positions + (size_t)n_vertices * 3);
+    c->h_indices.assign(indices, indices + n_indices);
+    c->chunks_valid = false;
     c->scene_checked = false;
     c->accel_blas_valid = c->accel_tlas_valid = false;
     return TR_OK;

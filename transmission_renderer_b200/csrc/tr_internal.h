@@ -14,6 +14,8 @@
 #include "tr_device_accel.cuh"
 #include "tr_device_pbr.cuh"
 
+#define TR_CHUNK_TRIS 64   // triangles per culling chunk of the binning pass (a multiple of 32: a warp's 32 triangles share a chunk)
+
 namespace tr {
 
 int32_t fail(int32_t status, const char* fmt, ...);
@@ -76,10 +78,16 @@ struct tr_ctx {
     uint32_t n_vertices = 0, n_indices = 0;
 
     // cull outputs (frustum_culling + demultiplex_draws)
-    tr::DevBuf visible_ids, cull_scalars, draws[4], work_prefix, slot_z, slot_first;
+    tr::DevBuf visible_ids, cull_scalars, draws[4], work_prefix, slot_z, slot_first, block_entry;
     uint32_t* d_instance_counts = nullptr;  // views into cull_scalars (state block of K1)
     uint32_t* d_cull_scalars = nullptr;     // [0] n_visible [1] visible triangles [2..5] draw_counts [6,7] ~min/max bits of slot_z
     std::vector<uint32_t> h_prim_tris, h_inst_prim;  // host copies: triangles per primitive, primitive of each instance
+    // cluster culling in the binning pass (k_visibility.cu): a bounding sphere per 64 consecutive triangles of every primitive,
+    // built on the host when the mesh or the primitives change (ensure_chunks)
+    std::vector<float> h_positions;
+    std::vector<uint32_t> h_indices;
+    tr::DevBuf chunk_spheres, prim_chunk_base;   // float4 (object-space centre, radius) per chunk; first chunk of each primitive
+    bool chunks_valid = false, chunk_cull = false;
     std::vector<uint32_t> h_inst_mat, h_prim_first, h_prim_count;  // material of each instance; index range of each primitive
     std::vector<uint32_t> band_bounds;  // n_ranks + 1 row boundaries when the caller balances the bands itself (tr_set_bands)
     bool scene_checked = false;  // ids / index ranges validated since the last upload (validate_scene)
@@ -205,6 +213,7 @@ int32_t launch_eval_ibl(uint32_t n, const trd::mat4& pv, const tr_ibl_volume_ref
                         const trd::PyramidDesc& pyr, const trd::LutDesc& lut, cudaStream_t s);
 
 int32_t check_device_status(tr_ctx* c, const char* who);
+int32_t ensure_chunks(tr_ctx* c);   // (re)builds chunk_spheres / prim_chunk_base after a mesh or primitive upload
 int32_t validate_scene(tr_ctx* c, const char* who);  // instance -> primitive / material ids, primitive index ranges  // sticky device-side error bits -> TR_ERR_STATE
 void mat4_inverse_f64(const tr_mat4& m, tr_mat4* out);
 int32_t ensure_layer(tr_ctx* c, int layer, bool with_position);
