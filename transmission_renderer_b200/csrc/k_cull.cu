@@ -226,11 +226,9 @@ int32_t launch_cull(tr_ctx* c, const tr_culling_push_constants& pc) {
     TR_TRY(c->cull_scalars.ensure(state_bytes));
     TR_TRY(c->visible_ids.ensure((size_t)c->n_instances * 4));
     TR_TRY(c->work_prefix.ensure(((size_t)c->n_instances + 1) * 4));
-    {   // one table for K1's list, one behind it for a band's own list (band_filter_kernel)
-        uint64_t tris = 0;
-        for (uint32_t pid : c->h_inst_prim) tris += c->h_prim_tris[pid];
-        TR_TRY(c->block_entry.ensure((size_t)(tris / 256 + 2) * 2 * 4));
-    }
+    TR_TRY(ensure_tri_bound(c, "tr_cull"));
+    // one table for K1's list, one behind it for a band's own list (band_filter_kernel)
+    TR_TRY(c->block_entry.ensure((size_t)(c->max_triangles / 256 + 2) * 2 * 4));
     TR_TRY(c->slot_z.ensure((size_t)c->n_instances * 4));
     TR_TRY(c->slot_first.ensure((size_t)c->n_instances * 16));
     TR_TRY(ensure_chunks(c));

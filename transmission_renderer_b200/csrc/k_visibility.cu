@@ -721,12 +721,16 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 // instead was tried in round 2 and lost 40 %: every part loses the other parts' occluders to the hierarchical Z.)
 // A job word: item | (1 + quadrant) << 28, or the bare item for a whole tile.
 // Run by CTA 0 of the fill pass (pass A3) before its share of the filling: one launch fewer, and it is off the critical path.
+#ifndef TR_SPLIT_NUM   // a tile is split when it holds more than TR_SPLIT_NUM / TR_SPLIT_DEN of the mean
+#define TR_SPLIT_NUM 3
+#define TR_SPLIT_DEN 2
+#endif
 __device__ __forceinline__ void tile_order_block(const VisParams& p) {
     __shared__ uint32_t s_hist[33], s_base[33];
     const uint32_t tid = threadIdx.x, n = 2u * p.n_tiles, nt = blockDim.x;
     if (tid < 33) s_hist[tid] = 0;
     __syncthreads();
-    const uint32_t split_above = p.split ? max(128u, (uint32_t)(((unsigned long long)min(p.bin_start[p.n_lists], p.bin_capacity) * 3ull) / (2ull * n))) : 0xffffffffu;
+    const uint32_t split_above = p.split ? max(128u, (uint32_t)(((unsigned long long)min(p.bin_start[p.n_lists], p.bin_capacity) * (unsigned long long)TR_SPLIT_NUM) / ((unsigned long long)TR_SPLIT_DEN * n))) : 0xffffffffu;
     auto weight = [&](uint32_t item, bool& split) {
         const uint32_t begin = min(p.bin_start[item * DEPTH_BUCKETS], p.bin_capacity), end = min(p.bin_start[(item + 1) * DEPTH_BUCKETS], p.bin_capacity);
         split = end - begin > split_above;
@@ -1435,16 +1439,7 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
         TR_TRY(c->vis[l].ensure(npx * 8));
         TR_TRY(ensure_layer(c, l, false));
     }
-    if (!c->tri_bound_valid) {  // upper bound of the work list: every instance visible
-        uint64_t n = 0;
-        for (uint32_t pid : c->h_inst_prim) {
-            if (pid >= c->h_prim_tris.size()) return fail(TR_ERR_INVALID_ARG, "tr_visibility: an instance names primitive %u of %zu", pid, c->h_prim_tris.size());
-            n += c->h_prim_tris[pid];
-        }
-        if (n >= (1ull << 31)) return fail(TR_ERR_UNSUPPORTED, "tr_visibility: more than 2^31 triangles");
-        c->max_triangles = n;
-        c->tri_bound_valid = true;
-    }
+    TR_TRY(ensure_tri_bound(c, "tr_visibility"));
     VisParams p{};
     // tile edge: 64 pixels, or 32 when the band is so small that 64-pixel tiles would leave SMs idle / unbalanced
     {

@@ -345,6 +345,20 @@ int32_t ensure_chunks(tr_ctx* c) {
     return TR_OK;
 }
 
+// Upper bound of the visibility work list (every instance visible), recomputed after an instance / primitive upload.
+int32_t ensure_tri_bound(tr_ctx* c, const char* who) {
+    if (c->tri_bound_valid) return TR_OK;
+    uint64_t n = 0;
+    for (uint32_t pid : c->h_inst_prim) {
+        if (pid >= c->h_prim_tris.size()) return fail(TR_ERR_INVALID_ARG, "%s: an instance names primitive %u of %zu", who, pid, c->h_prim_tris.size());
+        n += c->h_prim_tris[pid];
+    }
+    if (n >= (1ull << 31)) return fail(TR_ERR_UNSUPPORTED, "%s: more than 2^31 triangles", who);
+    c->max_triangles = n;
+    c->tri_bound_valid = true;
+    return TR_OK;
+}
+
 int32_t check_device_status(tr_ctx* c, const char* who) {
     if (!c->dev_status.p) return TR_OK;
     uint32_t bits = 0;

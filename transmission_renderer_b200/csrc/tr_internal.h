@@ -14,7 +14,9 @@
 #include "tr_device_accel.cuh"
 #include "tr_device_pbr.cuh"
 
+#ifndef TR_CHUNK_TRIS
 #define TR_CHUNK_TRIS 64   // triangles per culling chunk of the binning pass (a multiple of 32: a warp's 32 triangles share a chunk)
+#endif
 
 namespace tr {
 
@@ -213,6 +215,7 @@ int32_t launch_eval_ibl(uint32_t n, const trd::mat4& pv, const tr_ibl_volume_ref
                         const trd::PyramidDesc& pyr, const trd::LutDesc& lut, cudaStream_t s);
 
 int32_t check_device_status(tr_ctx* c, const char* who);
+int32_t ensure_tri_bound(tr_ctx* c, const char* who);   // max_triangles: the work list's upper bound
 int32_t ensure_chunks(tr_ctx* c);   // (re)builds chunk_spheres / prim_chunk_base after a mesh or primitive upload
 int32_t validate_scene(tr_ctx* c, const char* who);  // instance -> primitive / material ids, primitive index ranges  // sticky device-side error bits -> TR_ERR_STATE
 void mat4_inverse_f64(const tr_mat4& m, tr_mat4* out);
