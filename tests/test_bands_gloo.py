@@ -92,6 +92,50 @@ def test_two_rank_bands_equal_full_frame():
     assert got == [(0, 0, H // 2), (1, H // 2, H)]
 
 
+def _group_worker(rank, world, port, out):
+    """bench.py's views x bands layout: 2 view groups of 2 band ranks, one gloo subgroup per view group."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bands = 2
+        group_id, band_rank = rank // bands, rank % bands
+        mine = None
+        for g in range(world // bands):
+            sub = dist.new_group(ranks=list(range(g * bands, (g + 1) * bands)), backend="gloo")
+            if g == group_id:
+                mine = sub
+
+        class GroupRenderer(FakeRenderer):
+            @staticmethod
+            def comm_unique_id():
+                return bytes([group_id]) * 128     # each view group has its own communicator
+
+        r = GroupRenderer(band_rank)
+        y0, y1 = parallel.init_bands(r, band_rank, bands, group=mine, exchange="peer")
+        assert r.calls[0] == ("comm_init", bytes([group_id]) * 128, band_rank, bands)
+        assert r.calls[1] == ("peer_attach", band_rank, bands, b"".join(bytes([k]) * 64 for k in range(bands)))
+        full = parallel.gather_bands(np.full((y1 - y0, 4, 1), rank, np.uint8), H, band_rank, bands, group=mine)
+        assert full.shape == (H, 4, 1) and set(np.unique(full)) == {group_id * bands, group_id * bands + 1}
+        out.put((rank, group_id, y0, y1))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_view_groups_of_band_ranks():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_group_worker, args=(r, 4, port, out)) for r in range(4)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(150)
+        assert p.exitcode == 0
+    got = sorted(out.get(timeout=5) for _ in range(4))
+    assert got == [(0, 0, 0, H // 2), (1, 0, H // 2, H), (2, 1, 0, H // 2), (3, 1, H // 2, H)]
+
+
 # ---- cost-balanced bands (tr_set_bands / parallel.balance_bands) ---------------------------------------------------------
 def test_balanced_bounds_properties():
     rng = np.random.default_rng(0)

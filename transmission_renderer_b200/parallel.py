@@ -27,7 +27,9 @@ def init_bands(renderer, rank, world_size, group=None, exchange="nccl"):
     if world_size == 1:
         return band_rows(renderer.height, 0, 1)
     uid = [type(renderer).comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0, group=group)
+    # `rank` counts inside `group` (a view group's bands); broadcast_object_list names its source by GLOBAL rank
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast_object_list(uid, src=src, group=group)
     renderer.comm_init(uid[0], rank, world_size)
     if exchange == "peer":
         handles = [None] * world_size
