@@ -12,12 +12,14 @@
 // — order independent, hence deterministic —, transmissive layer tested GREATER against the final
 // opaque depth.  Work list = the visible instances' triangles from K1's scan (no host round trip).
 // Sort-middle, front to back, with a hierarchical Z:
-//   A1 bin_count   one thread per triangle: exact set-up, cull (back face, off band, w <= 0), count into the 64x64-pixel
-//                  tile bins (16 depth buckets per tile and layer), compact the survivors into records
+//   A1 bin_count   one thread per triangle: the triangle's 64-triangle chunk against the frame / band planes (bounding sphere, before
+//                  any vertex is fetched), exact set-up, cull (back face, off band, w <= 0), count into the 64x64-pixel tile
+//                  bins (16 depth buckets per tile and layer), the survivors' 128-byte set-up records
 //   A2 bin_scan    exclusive scan of the bin counts
 //   A3 bin_fill    scatter the survivors into their bins; its CTA 0 first orders the tile jobs, heaviest first
 //   B  raster_tiles  persistent CTAs, one tile job at a time with the tile's depth/id words in shared memory: rounds of 64
-//                  triangles (fp32 coarse form with proven bounds + exact double form), all threads walk all box pixels,
+//                  triangles (fp32 coarse form with proven bounds + exact double form); the rows of the round's boxes are
+//                  handed out by a ticket, one lane solves a row's exact span, one lane per span pixel tests the depth plane,
 //                  survivors evaluated exactly, winners by shared-memory atomicMax, 8x8 block minima refreshed per round
 //   C  resolve     per pixel: the winning triangle's plane, perspective-correct varyings, the SoA G-buffer planes of both
 //                  layers
@@ -793,13 +795,14 @@ __global__ void __launch_bounds__(256, TR_BIN_CTAS) bin_fill_kernel(const __grid
     }
 }
 
-// ---- pass B: one CTA per (layer, 64x64 tile): the tile's depth/id words live in shared memory.
-// The CTA takes 256 triangles of the bin list per round: thread i sets triangle i up and parks an fp32
-// "coarse" form and the exact double form in shared memory; a CTA-wide scan of the clipped box sizes
-// then lets all 256 threads walk the pixels of all 256 boxes together (perfect balance whatever the box
-// sizes).  A pixel is dropped by fp32 edge functions with a rigorous error bound or by a conservative
-// fp32 depth plane against the tile's current depth; the survivors are queued per warp and evaluated 32
-// at a time with the exact double rule (eval_pixel), so the expensive path runs with full warps.
+// ---- pass B: persistent CTAs take (layer, tile) jobs from a ticket; the job's depth/id words live in shared memory.
+// The CTA takes ROUND (64) triangles of the bin list per round: thread i loads record i and parks an fp32 "coarse" form
+// and the exact double form in shared memory while the upper half of the CTA refreshes the 8x8-block depth minima; a
+// triangle whose nearest depth lies behind every block its box touches is dropped.  The rows of the round's boxes are laid
+// end to end and handed to the warps 32 at a time: one lane per row solves the three fp32 edge tests (rigorous error
+// bound) for their exact interval, then one lane per span pixel tests a conservative fp32 depth plane against the tile's
+// current depth; the survivors are queued per warp and evaluated 32 at a time with the exact double rule (eval_pixel), so
+// the expensive path runs with full warps.
 #ifndef TR_ROUND
 #define TR_ROUND 64
 #endif
