@@ -1500,7 +1500,8 @@ int32_t launch_visibility(tr_ctx* c, const tr_push_constants& pc) {
     p.scalars = c->d_cull_scalars;
     p.slot_z = c->slot_z.as<float>();
     p.slot_prim = c->slot_first.as<uint4>();
-    p.chunk_spheres = c->chunk_cull ? c->chunk_spheres.as<float4>() : nullptr;
+    // (a mesh uploaded between tr_cull and this call leaves K1's chunk bases pointing into the old table: no chunk test then)
+    p.chunk_spheres = c->chunk_cull && c->chunks_valid ? c->chunk_spheres.as<float4>() : nullptr;
     {   // clip-space half spaces x >= -w, x <= w and the band's rows (two pixels of slack) as world-space planes, in double
         const float* m = reinterpret_cast<const float*>(&pc.proj_view);   // column-major: element (row r, col k) = m[k * 4 + r]
         auto row = [&](int r, int k) { return (double)m[k * 4 + r]; };
