@@ -13,8 +13,13 @@
  *                                   alpha-clip geometry casts shadows, transmissive geometry does not)
  *   src/main.rs:2734-2754           instance transform = the instance's Similarity
  *
- * The ray/triangle arithmetic of VK_KHR_ray_query is implementation-defined (hardware in the reference): parity is NOT
- * PINNABLE here, as for the rasteriser — the definition is ours (oracle.h).  The definition used on both sides (DESIGN.md "Ray-queried shadows"):
+ * The ray/triangle arithmetic of VK_KHR_ray_query is implementation-defined (hardware in the reference): parity of WHICH
+ * TRIANGLE A RAY MEETS is not pinnable, as for the rasteriser — that definition is ours (oracle.h).  What the shaders do around
+ * the query (when a ray is traced, its parameters, what its answer does to the light: oracle/shade.c) is pinned to the
+ * reference's ray-tracing builds of the fragment modules, compiled-shaders/ray-tracing/{fragment,fragment_transmission}.spv,
+ * which run with orc_trace_shadow as their ray-query environment (oracle/spv_harness.c; tests/test_reference_spirv.py
+ * test_live_ray_tracing_fragments, test_golden_ray_tracing_fragments: bit-equal pixels).
+ * The definition used on both sides (DESIGN.md "Ray-queried shadows"):
  *
  *   occluded(ray) :=  exists an instance i of the top-level set with  slab(world ray, world_box_i)  and a triangle k of
  *                     its primitive with  slab(object ray_i, box_k)  and  hit64(object ray_i, triangle k)

@@ -76,6 +76,10 @@ class Module:
                 self.types[a[0]] = T("float", width=a[1])
             elif op == 23:
                 self.types[a[0]] = T("vector", elem=a[1], n=a[2])
+            elif op == 4472:
+                self.types[a[0]] = T("rayquery")      # OpTypeRayQueryKHR
+            elif op == 5341:
+                self.types[a[0]] = T("accel")         # OpTypeAccelerationStructureKHR
             elif op == 25:
                 self.types[a[0]] = T("image")
             elif op == 26:
@@ -95,7 +99,7 @@ class Module:
             elif op in (41, 42):
                 self.consts[a[1]] = (a[0], 1 if op == 41 else 0)
             elif op == 43:
-                self.consts[a[1]] = (a[0], a[2])
+                self.consts[a[1]] = (a[0], a[2] | (a[3] << 32) if len(a) > 3 else a[2])
             elif op == 44:
                 self.consts[a[1]] = (a[0], tuple(a[2:]))
             elif op == 59:
@@ -128,11 +132,17 @@ class Emitter:
         if k == "bool":
             return "int"
         if k == "int":
-            assert t.width == 32
+            assert t.width in (32, 64)
+            if t.width == 64:
+                return "int64_t" if t.signed else "uint64_t"
             return "int32_t" if t.signed else "uint32_t"
         if k == "float":
             assert t.width == 32
             return "float"
+        if k == "rayquery":
+            return "spv_rayq"
+        if k == "accel":
+            return "uint64_t"
         if k in ("image", "sampler"):
             return "spv_handle"
         if k == "sampled_image":
@@ -168,7 +178,8 @@ class Emitter:
         self.helpers[key] = (fn, None)
         lines = []
         if t.kind in ("int", "float"):
-            body = "memcpy(p, &x, 4);" if store else f"{ct} x; memcpy(&x, p, 4); return x;"
+            nb = t.width // 8
+            body = f"memcpy(p, &x, {nb});" if store else f"{ct} x; memcpy(&x, p, {nb}); return x;"
         elif t.kind == "vector":
             es = 4
             sub = self.loader(t.elem, store)
@@ -207,6 +218,8 @@ class Emitter:
         t = self.m.types[tid]
         if t.kind == "bool":
             return str(val)
+        if t.kind == "int" and t.width == 64:
+            return f"(int64_t)0x{val:016x}ull" if t.signed else f"0x{val:016x}ull"
         if t.kind == "int":
             return f"(int32_t)0x{val:08x}u" if t.signed else f"0x{val:08x}u"
         if t.kind == "float":
@@ -501,6 +514,23 @@ class Emitter:
             assert m.ext_sets[a[2]] == "GLSL.std.450"
             fmt = GLSL[inst]
             return self.elementwise(r, rt, fmt, *ops)
+        # ---- SPV_KHR_ray_query: the query object keeps what Initialize was given; traversal belongs to the environment
+        if op == 4447:   # OpConvertUToAccelerationStructureKHR
+            return f"{v(a[1])} = (uint64_t){v(a[2])};"
+        if op == 4473:   # OpRayQueryInitializeKHR: query, accel, flags, cull mask, origin, tmin, direction, tmax
+            q, acc, flags, mask, org, tmin, dr, tmax = a
+            return (f"{v(q)}->accel = {v(acc)}; {v(q)}->flags = {v(flags)}; {v(q)}->cull_mask = {v(mask)}; "
+                    f"memcpy({v(q)}->origin, {v(org)}.v, 12); {v(q)}->t_min = {v(tmin)}; memcpy({v(q)}->direction, {v(dr)}.v, 12); "
+                    f"{v(q)}->t_max = {v(tmax)}; {v(q)}->initialised = 1u;")
+        if op == 4477:   # OpRayQueryProceedKHR
+            return f"{v(a[1])} = ctx->rq_proceed(ctx, {v(a[2])});"
+        if op == 4476:   # OpRayQueryConfirmIntersectionKHR (only reached while rq_proceed reports candidates)
+            return ";"
+        if op == 4479:   # OpRayQueryGetIntersectionTypeKHR
+            assert m.consts[a[3]][1] == 1, "only the committed intersection is queried by these modules"
+            return f"{v(a[1])} = ctx->rq_committed_type(ctx, {v(a[2])});"
+        if op == 6019:   # OpRayQueryGetIntersectionInstanceCustomIndexKHR (candidate): read and dropped by the module
+            return f"{v(a[1])} = 0u;"
         if op == 232:
             rt, r, p = a[0], a[1], a[2]  # OpAtomicIIncrement; invocations run one at a time
             ld, st = self.loader(rt), self.loader(rt, store=True)
@@ -528,7 +558,7 @@ class Emitter:
 
 RESULT_OPS = {12, 59, 61, 65, 68, 79, 80, 81, 82, 86, 87, 88, 109, 110, 111, 112, 124, 126, 127, 128, 129, 130, 131, 132, 133,
               134, 136, 137, 142, 164, 165, 166, 167, 168, 169, 170, 171, 172, 174, 176, 178, 180, 182, 183, 184, 185, 186,
-              187, 188, 189, 190, 191, 194, 196, 197, 198, 199, 207, 208, 232}
+              187, 188, 189, 190, 191, 194, 196, 197, 198, 199, 207, 208, 232, 4447, 4477, 4479, 6019}
 UNARY = {109: "spv_f2u({0})", 110: "spv_f2s({0})", 111: "(float)(int32_t){0}", 112: "(float)(uint32_t){0}",
          126: "(RT)(0u - (uint32_t){0})", 127: "-{0}", 168: "!{0}"}
 BINARY = {128: "(RT)((uint32_t){0} + (uint32_t){1})", 130: "(RT)((uint32_t){0} - (uint32_t){1})",

@@ -10,6 +10,10 @@
 typedef struct { uint32_t set, binding, index; } spv_handle;        /* an image or sampler descriptor */
 typedef struct { spv_handle image, sampler; } spv_sampled;
 
+/* SPV_KHR_ray_query: what OpRayQueryInitializeKHR stored.  The traversal is the environment's (ray-tracing hardware in
+ * the reference; the shadow-ray definition of oracle/shadow.c here). */
+typedef struct { uint64_t accel; uint32_t flags, cull_mask; float origin[3], t_min, direction[3], t_max; uint32_t initialised; } spv_rayq;
+
 typedef struct spv_ctx {
     struct { uint8_t* ptr; uint64_t size; } buf[4][16];              /* [descriptor set][binding] */
     uint8_t* push;                                                   /* push-constant block */
@@ -21,6 +25,10 @@ typedef struct spv_ctx {
                    float lod, float* out4);
     /* OpDPdx / OpDPdy of a value; loc = Location of the stage input it was loaded from, or -1 */
     void (*dpd)(struct spv_ctx*, int is_y, int loc, int n, const float* value, float* out);
+    /* OpRayQueryProceedKHR: 1 while a candidate waits for the shader's verdict.  OpRayQueryGetIntersectionTypeKHR on the
+     * committed intersection: 0 = none, 1 = triangle. */
+    int (*rq_proceed)(struct spv_ctx*, spv_rayq*);
+    uint32_t (*rq_committed_type)(struct spv_ctx*, spv_rayq*);
     int killed;                                                      /* OpKill */
     void* user;
 } spv_ctx;

@@ -11,6 +11,8 @@
  *   fragment_tonemap           shader/src/lib.rs:683-697
  *   vertex_instanced_with_scale shader/src/lib.rs:364-391
  *   depth_pre_pass_alpha_clip  shader/src/lib.rs:270-293
+ *   ray-tracing/fragment, ray-tracing/fragment_transmission   the same two entry points with trace_shadow_ray
+ *                              (shader/src/lighting.rs:97-125) compiled in: SPV_KHR_ray_query
  * Together they are `oracle/_ref/libspvref.so`: outputs of the reference's own compiled code, which pin the C
  * restatement (oracle/ *.c) and, through it, the CUDA path.
  *
@@ -30,6 +32,7 @@
 DECL(frustum_culling) DECL(demultiplex_draws) DECL(write_cluster_data) DECL(assign_lights_to_clusters)
 DECL(fragment) DECL(fragment_transmission) DECL(fragment_tonemap) DECL(vertex_instanced_with_scale)
 DECL(vertex_instanced) DECL(depth_pre_pass_instanced) DECL(depth_pre_pass_alpha_clip) DECL(depth_pre_pass_vertex_alpha_clip)
+DECL(rt_fragment) DECL(rt_fragment_transmission)   /* compiled-shaders/ray-tracing/: the same entry points built with ray queries */
 
 #define EXPORT __attribute__((visibility("default")))
 
@@ -181,6 +184,24 @@ static void frag_dpd(spv_ctx* c, int is_y, int loc, int n, const float* value, f
     }
 }
 
+/* Ray queries.  The reference's loop (lighting.rs:112-118) confirms every candidate the hardware reports, so the committed
+ * intersection is "the nearest triangle in [t_min, t_max], if any" whatever the geometry's opacity flag; the module only asks
+ * whether there is one.  The environment therefore reports no candidate to the shader (rq_proceed = 0: the intersection is
+ * committed on its own, as for opaque geometry) and answers the committed-type question with the shadow-ray definition of
+ * oracle/shadow.c — which primitive/instance set is traced and how a ray meets a triangle is ours to define;
+ * WHEN a ray is traced, from where, how far, and what its answer does to the light is the module's. */
+static int frag_rq_proceed(spv_ctx* c, spv_rayq* q) {
+    (void)c; (void)q;
+    return 0;
+}
+static uint32_t frag_rq_committed_type(spv_ctx* c, spv_rayq* q) {
+    const frag_env* e = (const frag_env*)c->user;
+    /* the contract the shadow-ray definition was written to: lighting.rs:104-111 */
+    if (!q->initialised || q->flags != 0u || q->cull_mask != 0xffu || q->t_min != 0.001f || !e->s->accel) abort();
+    v3 o = {q->origin[0], q->origin[1], q->origin[2]}, d = {q->direction[0], q->direction[1], q->direction[2]};
+    return orc_trace_shadow(e->s->accel, o, d, q->t_max) == 0.0f ? 1u : 0u;   /* 1 = committed triangle */
+}
+
 static void bind_scene(spv_ctx* c, const orc_scene* s) {
     c->push = (uint8_t*)s->pc;
     bind(c, 0, 2, s->materials, (uint64_t)s->n_materials * sizeof(tr_material_info));
@@ -190,6 +211,8 @@ static void bind_scene(spv_ctx* c, const orc_scene* s) {
     bind(c, 2, 2, s->cluster_light_indices, (uint64_t)s->n_clusters * TR_MAX_LIGHTS_PER_CLUSTER * 4);
     c->sample = frag_sample;
     c->dpd = frag_dpd;
+    c->rq_proceed = frag_rq_proceed;
+    c->rq_committed_type = frag_rq_committed_type;
 }
 
 /* one invocation of `fragment`; out2 receives the second colour attachment (lib.rs:247-248) */
@@ -204,7 +227,8 @@ EXPORT v4 ref_fragment(v3 position, v3 normal, v2 uv, uint32_t material_id, v4 f
     c.in_loc[0] = &position; c.in_loc[1] = &normal; c.in_loc[2] = &uv; c.in_loc[3] = &material_id;
     c.builtin[15] = &frag_coord;
     c.out_loc[0] = &o0; c.out_loc[1] = &o1;
-    spv_fragment(&c);
+    if (s->accel) spv_rt_fragment(&c);   /* a scene with an acceleration structure runs the ray-tracing build of the module */
+    else spv_fragment(&c);
     if (out2) *out2 = o1;
     return o0;
 }
@@ -221,7 +245,8 @@ EXPORT v4 ref_fragment_transmission(v3 position, v3 normal, v2 uv, uint32_t mate
     c.in_loc[0] = &position; c.in_loc[1] = &normal; c.in_loc[2] = &uv; c.in_loc[3] = &material_id; c.in_loc[4] = &model_scale;
     c.builtin[15] = &frag_coord;
     c.out_loc[0] = &o0;
-    spv_fragment_transmission(&c);
+    if (s->accel) spv_rt_fragment_transmission(&c);
+    else spv_fragment_transmission(&c);
     return o0;
 }
 

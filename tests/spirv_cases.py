@@ -44,6 +44,11 @@ def config1(size=192):
     return scenes.config1(size, 0.25, lights=[host.light_new_point((0.5, 3.0, 1.5), (1.0, 0.8, 0.6), 8.0)])
 
 
+def shadows(width=192, height=108):
+    """N4: occluders over a ground quad, sun + point lights + a spotlight, an alpha-clip caster and a glass receiver."""
+    return scenes.shadow_scene(width, height)
+
+
 def sample_pixels(depth):
     """Flat indices of every SAMPLE_STRIDE-th covered pixel."""
     return np.nonzero(np.asarray(depth).reshape(-1) != 0)[0][::SAMPLE_STRIDE]
