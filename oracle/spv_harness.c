@@ -10,6 +10,7 @@
  *   fragment_transmission      shader/src/lib.rs:37-162
  *   fragment_tonemap           shader/src/lib.rs:683-697
  *   vertex_instanced_with_scale shader/src/lib.rs:364-391
+ *   vertex_instanced, depth_pre_pass_instanced, depth_pre_pass_vertex_alpha_clip   shader/src/lib.rs:335-362, 319-333, 295-317
  *   depth_pre_pass_alpha_clip  shader/src/lib.rs:270-293
  *   ray-tracing/fragment, ray-tracing/fragment_transmission   the same two entry points with trace_shadow_ray
  *                              (shader/src/lighting.rs:97-125) compiled in: SPV_KHR_ray_query
@@ -316,6 +317,43 @@ EXPORT void ref_vertex_instanced_with_scale(uint32_t n, const float* positions, 
         c.out_loc[4] = out_scale + i;
         spv_vertex_instanced_with_scale(&c);
     }
+}
+
+/* The other three vertex stages of the path for a batch of (vertex, instance) pairs; outputs a stage does not have are left
+ * untouched.  which = 1 vertex_instanced (lib.rs:335-362: the opaque G-buffer pass), 2 depth_pre_pass_instanced (:319-333: the
+ * clip position the visibility pass rasterises), 3 depth_pre_pass_vertex_alpha_clip (:295-317: clip, uv, material id). */
+EXPORT int ref_vertex_stage(uint32_t which, uint32_t n, const float* positions, const float* normals, const float* uvs,
+                            const uint32_t* instance_index, const tr_instance* inst, uint32_t n_inst, const tr_push_constants* pc,
+                            float* clip /*[n*4]*/, float* out_position /*[n*3]*/, float* out_normal /*[n*3]*/, float* out_uv /*[n*2]*/,
+                            uint32_t* out_material) {
+    if (which < 1 || which > 3) return -1;
+    for (uint32_t i = 0; i < n; i++) {
+        spv_ctx c;
+        memset(&c, 0, sizeof c);
+        bind(&c, 1, 0, inst, (uint64_t)n_inst * sizeof *inst);
+        c.push = (uint8_t*)pc;
+        int32_t ii = (int32_t)instance_index[i];
+        c.builtin[43] = &ii;
+        c.builtin[0] = clip + (size_t)i * 4;
+        c.in_loc[0] = (void*)(positions + (size_t)i * 3);
+        if (which == 1) {
+            c.in_loc[1] = (void*)(normals + (size_t)i * 3);
+            c.in_loc[2] = (void*)(uvs + (size_t)i * 2);
+            c.out_loc[0] = out_position + (size_t)i * 3;
+            c.out_loc[1] = out_normal + (size_t)i * 3;
+            c.out_loc[2] = out_uv + (size_t)i * 2;
+            c.out_loc[3] = out_material + i;
+            spv_vertex_instanced(&c);
+        } else if (which == 2) {
+            spv_depth_pre_pass_instanced(&c);
+        } else {
+            c.in_loc[1] = (void*)(uvs + (size_t)i * 2);
+            c.out_loc[0] = out_uv + (size_t)i * 2;
+            c.out_loc[1] = out_material + i;
+            spv_depth_pre_pass_vertex_alpha_clip(&c);
+        }
+    }
+    return 0;
 }
 
 /* depth_pre_pass_alpha_clip: 1 = the fragment was discarded */

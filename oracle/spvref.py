@@ -138,6 +138,25 @@ def vertex_instanced_with_scale(positions, normals, uvs, instance_index, instanc
     return out
 
 
+def vertex_stage(which, positions, normals, uvs, instance_index, instances, push_constants):
+    """which = "vertex_instanced" | "depth_pre_pass_instanced" | "depth_pre_pass_vertex_alpha_clip": the outputs that stage has."""
+    code = {"vertex_instanced": 1, "depth_pre_pass_instanced": 2, "depth_pre_pass_vertex_alpha_clip": 3}[which]
+    positions, normals = _c(positions, np.float32).reshape(-1, 3), _c(normals, np.float32).reshape(-1, 3)
+    uvs = _c(uvs, np.float32).reshape(-1, 2)
+    instance_index = _c(instance_index, np.uint32)
+    instances = _c(instances, abi.instance)
+    pc = _c(push_constants, abi.push_constants)
+    n = len(positions)
+    out = dict(clip=np.zeros((n, 4), np.float32), position=np.zeros((n, 3), np.float32), normal=np.zeros((n, 3), np.float32),
+               uv=np.zeros((n, 2), np.float32), material_id=np.zeros(n, np.uint32))
+    rc = lib().ref_vertex_stage(C.c_uint32(code), C.c_uint32(n), _p(positions), _p(normals), _p(uvs), _p(instance_index),
+                                _p(instances), C.c_uint32(len(instances)), _p(pc), _p(out["clip"]), _p(out["position"]),
+                                _p(out["normal"]), _p(out["uv"]), _p(out["material_id"]))
+    assert rc == 0
+    keep = {1: ("clip", "position", "normal", "uv", "material_id"), 2: ("clip",), 3: ("clip", "uv", "material_id")}[code]
+    return {k: out[k] for k in keep}
+
+
 def alpha_clip(uvs, duv, material_id, scene):
     uvs = _c(uvs, np.float32).reshape(-1, 2)
     duv = _c(duv, np.float32).reshape(-1, 4) if duv is not None else None
