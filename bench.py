@@ -222,6 +222,18 @@ class CpuShadePath:
         from oracle import pyoracle as oracle
         from transmission_renderer_b200 import abi, host
         self.oracle = oracle
+        # Which code shades: the reference's own compiled shader modules (oracle/_ref/libspvref.so: its shipped SPIR-V translated to
+        # C instruction by instruction, oracle/spv2c.py) when that library is here, else the C port of the same source.  The two
+        # agree bit for bit (tests/test_reference_spirv.py); TR_CPU_CODE=port forces the port.
+        self.code, self.code_note = "port", None
+        if os.environ.get("TR_CPU_CODE", "spirv") != "port":
+            try:
+                from oracle import spvref
+                if spvref.available():
+                    spvref.lib()
+                    self.spvref, self.code = spvref, "spirv"
+            except Exception as e:      # noqa: BLE001 - a missing / unloadable library must not fail the bench: the port is the fallback
+                self.code_note = f"reference modules not loadable ({str(e)[:120]}); the port was timed"
         # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it may run on
         oracle.set_num_threads(len(os.sched_getaffinity(0)))
         cam = scene["camera"]
@@ -260,7 +272,27 @@ class CpuShadePath:
         if g0 is None:   # config 1 has no opaque geometry: an empty opaque layer, the opaque frame is the procedural input
             g0 = dict(depth=np.zeros((self.h, self.w), np.float32), normal=np.zeros((self.h, self.w, 3), np.float32), uv=None,
                       material_id=np.zeros((self.h, self.w), np.uint32), scale=None, position=None)
-        return self.oracle.ShadePathRunner(g0, self.g1, self.sc, self.lut, host.default_tonemap_params(), self.opaque_full16)
+        cls = self.spvref.ShadePathRunner if self.code == "spirv" else self.oracle.ShadePathRunner
+        return cls(g0, self.g1, self.sc, self.lut, host.default_tonemap_params(), self.opaque_full16)
+
+    @property
+    def kind(self):
+        """cpu_baseline.kind: "reference" = the reference's own compiled shader modules, "port" = the C restatement."""
+        return "reference" if self.code == "spirv" else "port"
+
+    def time_port(self, steps):
+        """The same steps through the C port, when the primary figure is the reference's modules."""
+        if self.code != "spirv":
+            return None
+        self.code = "port"
+        try:
+            self.runner = self._runner()
+            self.step()
+            t = float(np.median([self.step() for _ in range(steps)]))
+        finally:
+            self.code = "spirv"
+            self.runner = self._runner()
+        return self.pixels / t / 1e6
 
     @property
     def pixels(self):
@@ -287,19 +319,24 @@ class CpuShadePath:
             self.oracle.select_variant("o3")
         except Exception as e:      # noqa: BLE001 - a missing compiler flag must not fail the bench
             return None, str(e)[:200]
+        code = self.code
+        self.code = "port"              # the -O3 build exists for the port only
         try:
             self.runner = self._runner()
             self.step()
             t = float(np.median([self.step() for _ in range(steps)]))
         finally:
             self.oracle.select_variant("parity")
+            self.code = code
             self.runner = self._runner()
         return self.pixels / t / 1e6, "gcc -O3 -march=native (contraction on): NOT the parity build"
 
     def describe(self):
         whole = "the whole" if (self.y0, self.y1) == (0, self.h) else f"rows [{self.y0},{self.y1}) of the"
+        code = ("the reference's shipped fragment.spv / fragment_transmission.spv translated to C (oracle/spv2c.py)" if self.code == "spirv"
+                else "the C port of shader + glam-pbr" + (f" [{self.code_note}]" if self.code_note else ""))
         return (f"{whole} {self.w}x{self.h} frame ({self.pixels} px): fragment -> mip chain (prorated) -> "
-                f"fragment_transmission -> tonemap; {self.how}")
+                f"fragment_transmission -> tonemap, shaded by {code}; {self.how}")
 
 
 def cpu_sample(scene, lut, opaque_full16=None, max_pixels=500_000, gbuffers=None):
@@ -329,11 +366,13 @@ def run_reference(args, wl):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": base_config(wl, args, world),
-        "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cpu.cores, "kind": "port", "sample": cpu.describe()},
+        "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe(),
+                         "value_port": cpu.time_port(max(1, args.steps // 2))},
         "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ms_per_full_frame_extrapolated": total / args.steps * 1e3 * (wl["width"] * wl["height"]) / cpu.pixels,
-        "note": "CPU oracle port of shader + glam-pbr (the Rust reference cannot be built here; the port reproduces the reference's "
-                "shipped SPIR-V bit for bit, tests/test_reference_spirv.py); ms_per_step is for the sampled rows",
+        "note": "the reference's per-pixel shader code on the host cores: its shipped SPIR-V modules translated to C (kind \"reference\"; the "
+                "Rust host cannot be built here), or the C port of the same source when that library is absent (kind \"port\"; the two agree "
+                "bit for bit, tests/test_reference_spirv.py); ms_per_step is for the sampled rows",
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -707,9 +746,9 @@ def run_b200(args, wl):
             b = oracle.f16_to_f32(cpu.runner.hdr16[cpu.y0:cpu.y1])[..., :3].astype(np.float64)
             ok = np.isfinite(a) & np.isfinite(b)
             rel = float(np.linalg.norm(a[ok] - b[ok]) / max(np.linalg.norm(b[ok]), 1e-30))
-            line["cpu_baseline"] = {"value": cpu.pixels / best / 1e6, "unit": "Mpx/s", "cores": cpu.cores, "kind": "port",
+            line["cpu_baseline"] = {"value": cpu.pixels / best / 1e6, "unit": "Mpx/s", "cores": cpu.cores, "kind": cpu.kind,
                                     "sample": cpu.describe(), "steps": n_cpu, "ms_per_step": best * 1e3,
-                                    "parity_rel_l2_vs_gpu": rel}
+                                    "parity_rel_l2_vs_gpu": rel, "value_port": cpu.time_port(max(2, n_cpu // 3))}
             o3, o3_note = cpu.time_o3(max(2, n_cpu // 3))
             line["cpu_baseline"]["value_o3_march_native"] = o3
             line["cpu_baseline"]["o3_note"] = o3_note

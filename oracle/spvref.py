@@ -165,3 +165,20 @@ def alpha_clip(uvs, duv, material_id, scene):
     out = np.zeros(len(uvs), np.uint8)
     lib().ref_alpha_clip(C.c_uint32(len(uvs)), _p(uvs), _p(duv), _p(material_id), C.byref(s), _p(out))
     return out
+
+
+class ShadePathRunner(po.ShadePathRunner):
+    """The oracle's shade-path runner with both fragment stages executed by the reference's own compiled modules
+    (fragment.spv / fragment_transmission.spv, or their ray-tracing builds when the scene carries an acceleration structure):
+    same buffers, same frame drivers (G-buffer decode, OpenMP over rows), same call shapes.  The mip chain (vkCmdBlitImage in the
+    reference) and the sRGB8 encode stay the oracle's.  bench.py's `--impl reference` / `cpu_baseline` legs time this when
+    oracle/_ref/libspvref.so is present: the reference's shader code itself on the host cores."""
+
+    def opaque(self, y0, y1):
+        lib().ref_shade_opaque_frame(C.byref(self._g0), C.byref(self._s), C.c_uint32(y0), C.c_uint32(y1), _p(self.hdr32),
+                                     _p(self.hdr16), _p(self.levels[0]))
+
+    def transmission(self, y0, y1):
+        if self._g1 is not None:
+            lib().ref_shade_transmission_frame(C.byref(self._g1), C.byref(self._s), C.byref(self._pyr), C.byref(self._lut),
+                                               C.c_uint32(y0), C.c_uint32(y1), _p(self.hdr32), _p(self.hdr16))
