@@ -82,32 +82,6 @@ def test_frames_match_the_reference_modules(golden, ggx_lut, name, make):
         assert e < REL_L2_TOL and worst < 1e-3
 
 
-def test_shadowed_frame_matches_the_reference_ray_tracing_modules(golden, ggx_lut):
-    """N4: one frame with ray-queried shadows (the sequence of __graft_entry__.smoke) against the pixels the reference's
-    ray-tracing builds of `fragment` / `fragment_transmission` produced (compiled-shaders/ray-tracing/*.spv, executed on the
-    CPU with the shadow-ray definition of oracle/shadow.c as their ray-query environment)."""
-    s = cases.shadows()
-    cam = s["camera"]
-    with Renderer(cam.width, cam.height, f32_debug=True) as r:
-        _upload(r, ggx_lut, s)
-        handle = r.build_acceleration_structures()
-        r.frame(cam.frame_params(host.default_tonemap_params(), acceleration_structure_address=handle))
-        g0, g1 = r.read_gbuffer(0), r.read_gbuffer(1)
-        final = r.read_hdr_f32().reshape(-1, 4)
-    px_o, px_t = golden["shadows_opaque_px"], golden["shadows_transmission_px"]
-    assert np.array_equal(cases.sample_pixels(g0["depth"]), px_o) and np.array_equal(cases.sample_pixels(g1["depth"]), px_t)
-    # the final frame holds the opaque result wherever no glass covers it, the transmissive result where it does
-    bare = np.asarray(g1["depth"]).reshape(-1)[px_o] == 0
-    assert bare.sum() > 500 and len(px_t) > 30
-    e_o = rel_l2(final[px_o[bare]][:, :3], golden["shadows_opaque_rgba"][bare][:, :3])
-    e_t = rel_l2(final[px_t][:, :3], golden["shadows_transmission_rgba"][:, :3])
-    print(f"shadows: rel-L2 vs the reference's ray-tracing modules, opaque {e_o:.2e}, transmission {e_t:.2e}")
-    # 66 glass samples only: their refracted background is fetched from the RGBA16F pyramid of the GPU's own opaque frame, where
-    # a last-bit difference of an fp32 pixel can round to the neighbouring half (2^-11); the whole-frame bound of 1e-4 is
-    # tests/test_gpu_shadows.py's and smoke()'s
-    assert e_o < REL_L2_TOL and e_t < 5e-4
-
-
 def test_config1_matches_the_reference_module(golden, ggx_lut):
     """BASELINE config 1 (synthetic G-buffer, roughness 0.25, sun + one light) against fragment_transmission.spv."""
     from oracle import pyoracle as po
