@@ -1,0 +1,109 @@
+"""The binning pass's chunk test (csrc/k_visibility.cu bin_count_kernel + csrc/tr_api.cu ensure_chunks) as a statement about
+geometry, checked on the CPU: a chunk of 64 consecutive triangles whose bounding sphere lies beyond one of the four planes
+(frame left / right, two rows above / below the band) by more than the kernel's slack contributes no pixel of the band — so
+dropping those triangles leaves every G-buffer plane of the band byte-identical.  The test restates the chunk construction and
+the plane test in numpy (the kernel's formulas and margins, float64 arithmetic), removes the chunks it rejects from the index
+buffer and lets the ORACLE's rasteriser render the band with and without them, over random cameras, bands and instances — large
+and tiny, partly behind the camera, straddling the frame's sides and the band's rows.  (One instance per primitive, as the
+reference's loader creates them, so that removing triangles from a primitive removes them for exactly one instance.)"""
+import numpy as np
+import pytest
+
+from transmission_renderer_b200 import scenes
+
+CHUNK = 64
+
+
+def chunk_spheres(pos, idx):
+    """ensure_chunks: centre of the chunk's box, radius to its farthest vertex (+ the rounding of the stored centre)."""
+    tris = idx.reshape(-1, 3)
+    out = []
+    for t0 in range(0, len(tris), CHUNK):
+        v = pos[tris[t0:t0 + CHUNK].reshape(-1)].astype(np.float64)
+        c = 0.5 * (v.min(0) + v.max(0))
+        fc = c.astype(np.float32)
+        r = (np.sqrt(((v - c) ** 2).sum(1).max()) + np.abs(fc - c).sum()) * (1.0 + 1e-6)
+        out.append((fc.astype(np.float64), float(np.float32(r))))
+    return out
+
+
+def rotate(q, v):
+    b, w = q[:3], q[3]
+    return v * (w * w - b @ b) + b * (2.0 * (v @ b)) + np.cross(b, v) * (2.0 * w)
+
+
+def band_planes(proj_view, height, y0, y1):
+    """launch_visibility: clip-space half spaces x >= -w, x <= w and the band's rows with two pixels of slack, as world planes."""
+    m = proj_view.astype(np.float64)             # math convention, m[row, col]
+    y_lo, y_hi = 2.0 * (y0 - 2.0) / height - 1.0, 2.0 * (y1 + 2.0) / height - 1.0
+    planes = [m[3] + m[0], m[3] - m[0], m[1] - y_lo * m[3], y_hi * m[3] - m[1]]
+    planes = [p.astype(np.float32).astype(np.float64) for p in planes]
+    return [(p, float(np.float32(np.linalg.norm(p[:3]) * 1.0001))) for p in planes]
+
+
+def chunk_is_rejected(centre, radius, inst, planes):
+    ts, rot = inst["translation_and_scale"].astype(np.float64), inst["rotation"].astype(np.float64)
+    wc = ts[:3] + rotate(rot, centre) * ts[3]
+    r = abs(radius * ts[3]) * 1.01 + 1e-3
+    for p, norm in planes:
+        d = p[0] * wc[0] + p[1] * wc[1] + p[2] * wc[2] + p[3]
+        slack = r * norm + 1e-4 * (abs(p[0] * wc[0]) + abs(p[1] * wc[1]) + abs(p[2] * wc[2]) + abs(p[3]))
+        if d < -slack:
+            return True
+    return False
+
+
+def random_scene(rng, w, h):
+    cam = scenes.Camera(w, h, tuple(rng.uniform([-3, 0.5, -3], [3, 6, 3])), float(rng.uniform(-180, 180)), float(rng.uniform(-50, 30)))
+    meshes = scenes.MeshSet()
+    kinds = [lambda: scenes.uv_sphere(32, 16), scenes.box_mesh, lambda: scenes.torus_knot(n_u=96, n_v=16), lambda: scenes.quad_mesh(1.0),
+             lambda: scenes.uv_sphere(64, 32)]
+    inst = []
+    for _ in range(int(rng.integers(20, 60))):
+        prim = meshes.add(kinds[int(rng.integers(0, len(kinds)))](), int(rng.choice([0, 0, 2])))
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        # near the camera, far away, huge (the camera may sit inside), tiny
+        scale = float(10.0 ** rng.uniform(-1.5, 1.3))
+        inst.append(scenes.make_instance(tuple(cam.position + rng.normal(size=3) * 10.0 ** rng.uniform(-0.5, 1.3)), scale, tuple(q), prim, 0))
+    mesh, prims = meshes.arrays()
+    return cam, mesh, prims, np.concatenate(inst)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_rejected_chunks_contribute_no_pixel_of_the_band(oracle, seed):
+    rng = np.random.default_rng(0xC0FFEE + seed)
+    w, h = int(rng.integers(96, 320)), int(rng.integers(64, 200))
+    cam, mesh, prims, inst = random_scene(rng, w, h)
+    n_bands = int(rng.choice([1, 2, 4, 8]))
+    band = int(rng.integers(0, n_bands))
+    y0, y1 = (band * h) // n_bands, ((band + 1) * h) // n_bands
+    planes = band_planes(cam.proj_view, h, y0, y1)
+    idx = mesh["indices"].copy()
+    keep = np.ones(len(idx) // 3, bool)
+    rejected = total = 0
+    for i in inst:
+        p = prims[int(i["primitive_id"])]
+        first, count = int(p["first_index"]), int(p["index_count"])
+        for k, (c, r) in enumerate(chunk_spheres(mesh["positions"], idx[first:first + count])):
+            total += 1
+            if chunk_is_rejected(c, r, i, planes):
+                rejected += 1
+                t0 = first // 3 + k * CHUNK
+                keep[t0:min(t0 + CHUNK, (first + count) // 3)] = False
+    # the filtered mesh: rejected triangles become degenerate (same vertex three times: no area, no pixel), so that every
+    # other triangle keeps its id and the tie rule of the rasteriser sees the same order
+    filtered = idx.reshape(-1, 3).copy()
+    filtered[~keep] = filtered[~keep][:, :1]
+    visible = np.arange(len(inst), dtype=np.uint32)      # no instance culling here: the chunk test stands alone
+    pc = cam.push_constants()
+    full = oracle.visibility(mesh, inst, prims, visible, pc, y0, y1)
+    part = oracle.visibility(dict(mesh, indices=filtered.reshape(-1)), inst, prims, visible, pc, y0, y1)
+    for layer, (a, b) in enumerate(zip(full, part)):
+        for k in ("depth", "normal", "uv", "material_id") + (("scale",) if layer == 1 else ()):
+            assert a[k][y0:y1].tobytes() == b[k][y0:y1].tobytes(), (seed, layer, k, rejected, total)
+    assert total > 50
+    if n_bands > 1:
+        assert rejected > 0, "a strict band always has chunks above or below it in these scenes"
+    covered = (full[0]["depth"][y0:y1] > 0).mean() + (full[1]["depth"][y0:y1] > 0).mean()
+    assert covered > 0.02, "the band shows something"
