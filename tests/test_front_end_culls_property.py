@@ -1,5 +1,7 @@
-"""The binning pass's chunk test (csrc/k_visibility.cu bin_count_kernel + csrc/tr_api.cu ensure_chunks) as a statement about
-geometry, checked on the CPU: a chunk of 64 consecutive triangles whose bounding sphere lies beyond one of the four planes
+"""The conservative culls of the visibility pass's front end as statements about geometry, checked on the CPU with the oracle's
+rasteriser: the chunk test of the binning pass (below) and the band filter's instance test (further down).
+
+The binning pass's chunk test (csrc/k_visibility.cu bin_count_kernel + csrc/tr_api.cu ensure_chunks): a chunk of 64 consecutive triangles whose bounding sphere lies beyond one of the four planes
 (frame left / right, two rows above / below the band) by more than the kernel's slack contributes no pixel of the band — so
 dropping those triangles leaves every G-buffer plane of the band byte-identical.  The test restates the chunk construction and
 the plane test in numpy (the kernel's formulas and margins, float64 arithmetic), removes the chunks it rejects from the index
@@ -107,3 +109,48 @@ def test_rejected_chunks_contribute_no_pixel_of_the_band(oracle, seed):
         assert rejected > 0, "a strict band always has chunks above or below it in these scenes"
     covered = (full[0]["depth"][y0:y1] > 0).mean() + (full[1]["depth"][y0:y1] > 0).mean()
     assert covered > 0.02, "the band shows something"
+
+
+def instance_on_band(sphere, inst, proj_view, height, y0, y1):
+    """band_filter_kernel's instance_on_band: conservative rows of the instance's bounding sphere, clip(C + d) = clip(C) + M d."""
+    m = proj_view.astype(np.float64)
+    ts, rot = inst["translation_and_scale"].astype(np.float64), inst["rotation"].astype(np.float64)
+    c = ts[:3] + rotate(rot, sphere[:3].astype(np.float64)) * ts[3]
+    cc = m @ np.append(c, 1.0)
+    r = abs(float(sphere[3]) * ts[3]) * 1.01 + 1e-3
+    ny, nw = np.linalg.norm(m[1, :3]) * 1.0001, np.linalg.norm(m[3, :3]) * 1.0001
+    w_lo, w_hi = cc[3] - r * nw, cc[3] + r * nw
+    if not w_lo > 0.0:
+        return True
+    y_lo, y_hi = cc[1] - r * ny, cc[1] + r * ny
+    n_lo, n_hi = min(y_lo / w_lo, y_lo / w_hi), max(y_hi / w_lo, y_hi / w_hi)
+    return (n_hi + 1.0) * 0.5 * height + 2.0 >= y0 and (n_lo + 1.0) * 0.5 * height - 2.0 <= y1
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_band_filter_keeps_every_instance_that_reaches_the_band(oracle, seed):
+    """The band's own work list (band_filter_kernel) drops an instance only when its bounding sphere cannot reach the band's
+    rows: rendering the band from the kept instances alone gives the same bytes.  The spheres are the primitives' true bounds,
+    as the reference's loader computes them (src/model_loading.rs:148-155) and as its own frustum cull relies on."""
+    rng = np.random.default_rng(0xBA2D + seed)
+    w, h = int(rng.integers(96, 320)), int(rng.integers(64, 200))
+    cam, mesh, prims, inst = random_scene(rng, w, h)
+    n_bands = int(rng.choice([2, 4, 8]))
+    band = int(rng.integers(0, n_bands))
+    y0, y1 = (band * h) // n_bands, ((band + 1) * h) // n_bands
+    # true bounding spheres (centre of the box, farthest vertex)
+    prims = prims.copy()
+    for p in prims:
+        v = mesh["positions"][mesh["indices"][int(p["first_index"]):int(p["first_index"]) + int(p["index_count"])]].astype(np.float64)
+        c = 0.5 * (v.min(0) + v.max(0))
+        p["packed_bounding_sphere"] = (*c, np.sqrt(((v - c) ** 2).sum(1).max()) * (1 + 1e-6))
+    every = np.arange(len(inst), dtype=np.uint32)
+    kept = np.array([i for i in every if instance_on_band(prims[int(inst[i]["primitive_id"])]["packed_bounding_sphere"], inst[i],
+                                                            cam.proj_view, h, y0, y1)], dtype=np.uint32)
+    pc = cam.push_constants()
+    full = oracle.visibility(mesh, inst, prims, every, pc, y0, y1)
+    part = oracle.visibility(mesh, inst, prims, kept, pc, y0, y1)
+    for layer, (a, b) in enumerate(zip(full, part)):
+        for k in ("depth", "normal", "uv", "material_id") + (("scale",) if layer == 1 else ()):
+            assert a[k][y0:y1].tobytes() == b[k][y0:y1].tobytes(), (seed, layer, k, len(kept), len(every))
+    assert 0 < len(kept) < len(every), "a strict band drops some instances and keeps some in these scenes"
