@@ -11,6 +11,10 @@ done
 python bench.py --workload config5 --steps 2 --warmup 3 --no-cpu-baseline --min-seconds 0 > $out/${tag}_bench_config5_n1.json 2>> $out/bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $out/${tag}_launches_bench_4k.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --min-seconds 0 > /dev/null 2>&1
+for r in 1 5; do   # one rank's share of an 8-GPU frame: where the band path's time goes
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv --log-file $out/${tag}_launches_band_${r}of8.csv \
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline --min-seconds 0 --emulate-band $r/8 > /dev/null 2>&1
+done
 ncu --set full --clock-control none --import-source on \
     -k regex:"shade_kernel|raster_tiles|resolve_kernel|mip_kernel|tonemap_kernel|bin_count|bin_fill|cull_kernel|assign_lights" -s 12 -c 11 \
     -o $out/${tag}_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline --min-seconds 0 > $out/ncu_full.log 2>&1
