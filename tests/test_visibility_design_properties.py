@@ -1,5 +1,7 @@
-"""The conservative culls of the visibility pass's front end as statements about geometry, checked on the CPU with the oracle's
-rasteriser: the chunk test of the binning pass (below) and the band filter's instance test (further down).
+"""Design rules of the visibility pass (K3) as statements that can be checked on the CPU, without the kernels: the chunk test of
+the binning pass (below) and the band filter's instance test (further down), both against the oracle's rasteriser, and the
+error bound of the tile pass's fp32 coarse edge test (last).  The kernels themselves are pinned bit for bit on the GPU
+(tests/test_gpu_parity.py); these tests pin the REASONS they may skip work.
 
 The binning pass's chunk test (csrc/k_visibility.cu bin_count_kernel + csrc/tr_api.cu ensure_chunks): a chunk of 64 consecutive triangles whose bounding sphere lies beyond one of the four planes
 (frame left / right, two rows above / below the band) by more than the kernel's slack contributes no pixel of the band — so
@@ -154,3 +156,39 @@ def test_band_filter_keeps_every_instance_that_reaches_the_band(oracle, seed):
         for k in ("depth", "normal", "uv", "material_id") + (("scale",) if layer == 1 else ()):
             assert a[k][y0:y1].tobytes() == b[k][y0:y1].tobytes(), (seed, layer, k, len(kept), len(every))
     assert 0 < len(kept) < len(every), "a strict band drops some instances and keeps some in these scenes"
+
+
+def test_coarse_edge_test_never_rejects_an_inside_pixel():
+    """The tile pass drops a pixel when an fp32 edge function is below -ebound (raster_tiles_kernel: a = (float)A, b = (float)B,
+    c = (float)(A X0 + B Y0 + C) at the tile's first pixel centre, value = fmaf(a, x, fmaf(b, y, c)) for x, y in 0..63,
+    ebound = (2^-21 (64 (|A| + |B|) + |c|) + 1e-15 (16384 (|A| + |B|) + |C|)) * 1.0001).  The exact rule evaluates
+    A px + B py + C in double at absolute pixel centres; wherever that is >= 0 the fp32 test must pass, and the fp32 value
+    must stay within ebound of it — over edge coefficients of ten decades, tiles anywhere in a 16 k frame, edges through the tile."""
+    rng = np.random.default_rng(0xED6E)
+    n = 400_000
+    mag = 10.0 ** rng.uniform(-6, 4, n)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    A, B = mag * np.cos(ang), mag * np.sin(ang)
+    A[rng.random(n) < 0.05] = 0.0
+    B[rng.random(n) < 0.05] = 0.0
+    tx, ty = rng.integers(0, 256, n) * 64.0, rng.integers(0, 256, n) * 64.0
+    X0, Y0 = tx + 0.5, ty + 0.5
+    # edges that pass near a random point of the tile (the interesting case), and some that do not
+    qx, qy = X0 + rng.uniform(-8, 72, n), Y0 + rng.uniform(-8, 72, n)
+    C = -(A * qx + B * qy) + np.where(rng.random(n) < 0.2, mag * 10.0 ** rng.uniform(-3, 3, n) * rng.choice([-1, 1], n), 0.0)
+    x, y = rng.integers(0, 64, n).astype(np.float64), rng.integers(0, 64, n).astype(np.float64)
+    cl = A * X0 + B * Y0 + C
+    a, b, c = A.astype(np.float32), B.astype(np.float32), cl.astype(np.float32)
+    f32 = lambda v: v.astype(np.float32).astype(np.float64)   # noqa: E731 - round to binary32
+    v = f32(b.astype(np.float64) * y + c.astype(np.float64))                 # fmaf(b, y, c): one rounding
+    value = f32(a.astype(np.float64) * x + v)                                # fmaf(a, x, v)
+    m = 64.0 * (np.abs(A) + np.abs(B)) + np.abs(cl)
+    m_abs = 16384.0 * (np.abs(A) + np.abs(B)) + np.abs(C)
+    ebound = ((m * 4.76837158203125e-7 + m_abs * 1e-15).astype(np.float32) * np.float32(1.0001)).astype(np.float64)
+    exact = A * (tx + x + 0.5) + B * (ty + y + 0.5) + C                      # the double rule at the absolute pixel centre
+    assert (np.abs(value - exact) <= ebound).all(), float((np.abs(value - exact) / np.maximum(ebound, 1e-300)).max())
+    inside = exact >= 0.0
+    assert 0.2 < inside.mean() < 0.8
+    assert not (value[inside] < -ebound[inside]).any()
+    # and the bound is not vacuous: it is a small fraction of the edge function's range over the tile
+    assert np.median(ebound / np.maximum(64.0 * (np.abs(A) + np.abs(B)), 1e-300)) < 1e-5
