@@ -192,3 +192,58 @@ def test_coarse_edge_test_never_rejects_an_inside_pixel():
     assert not (value[inside] < -ebound[inside]).any()
     # and the bound is not vacuous: it is a small fraction of the edge function's range over the tile
     assert np.median(ebound / np.maximum(64.0 * (np.abs(A) + np.abs(B)), 1e-300)) < 1e-5
+
+
+def test_conservative_depth_plane_bounds_the_exact_depth():
+    """The tile pass tests an fp32 depth plane d0 + gx x + gy y (+ margin) against the tile's current depth before it evaluates a
+    pixel exactly (raster_tiles_kernel).  For every pixel centre inside the triangle the exact rule's depth (eval_pixel: double
+    edge functions, fp32 barycentrics, fp32 z / w) must not exceed plane + margin — otherwise a visible fragment could be dropped —
+    and must not fall below plane - margin either (the bound is two-sided).  Random front-facing triangles from sub-pixel to
+    tile-sized, vertex w over four decades (strong perspective), anywhere in a 16 k frame."""
+    rng = np.random.default_rng(0xDE97)
+    f32 = lambda v: np.asarray(v, np.float64).astype(np.float32).astype(np.float64)   # noqa: E731 - round to binary32
+    checked = worst = 0.0
+    for _ in range(4000):
+        tile_x0, tile_y0 = int(rng.integers(0, 256)) * 64, int(rng.integers(0, 256)) * 64
+        size = 10.0 ** rng.uniform(-0.5, 2.0)
+        centre = np.array([tile_x0, tile_y0]) + rng.uniform(0, 64, 2)
+        pix = centre + rng.normal(size=(3, 2)) * size
+        W = f32(10.0 ** rng.uniform(-1.3, 2.7, 3) if rng.random() < 0.5 else 10.0 ** rng.uniform(-1.3, 2.7) * rng.uniform(0.8, 1.25, 3))
+        depth = rng.uniform(0.0005, 0.999, 3)
+        sx, sy, Z = f32(pix[:, 0] * W), f32(pix[:, 1] * W), f32(depth * W)
+        det = sx[0] * (sy[1] * W[2] - W[1] * sy[2]) + sy[0] * (W[1] * sx[2] - sx[1] * W[2]) + W[0] * (sx[1] * sy[2] - sy[1] * sx[2])
+        if det == 0.0:
+            continue
+        order = [0, 2, 1] if det < 0.0 else [0, 1, 2]       # setup_front keeps det < 0 and reorders (0, 2, 1)
+        rx, ry, Z, W = sx[order], sy[order], Z[order], W[order]
+        A = np.array([ry[(i + 1) % 3] * W[(i + 2) % 3] - W[(i + 1) % 3] * ry[(i + 2) % 3] for i in range(3)])
+        B = np.array([W[(i + 1) % 3] * rx[(i + 2) % 3] - rx[(i + 1) % 3] * W[(i + 2) % 3] for i in range(3)])
+        C = np.array([rx[(i + 1) % 3] * ry[(i + 2) % 3] - ry[(i + 1) % 3] * rx[(i + 2) % 3] for i in range(3)])
+        cl = A * (tile_x0 + 0.5) + B * (tile_y0 + 0.5) + C
+        dets, absdet = float((cl * W).sum()), float(np.abs(cl * W).sum())
+        if not (W.min() > 0.0 and dets > 0.0 and absdet < dets * 1048576.0):
+            continue                                          # the kernel switches the plane off (margin = inf) here
+        r = 1.0 / dets
+        d0, gx, gy = f32((cl * Z).sum() * r), f32((A * Z).sum() * r), f32((B * Z).sum() * r)
+        mg = float(np.float32(np.float32(abs(d0) + 64.0 * (abs(gx) + abs(gy))) * np.float32(1.9073486e-6)
+                              + np.float32(np.abs(Z).max() / W.min()) * np.float32(9.536743e-7)))
+        y, x = np.mgrid[0:64, 0:64]
+        qx, qy = tile_x0 + x + 0.5, tile_y0 + y + 0.5
+        E = A[:, None, None] * qx + B[:, None, None] * qy + C[:, None, None]
+        S = E.sum(0)
+        inside = (E >= 0.0).all(0) & (S > 0.0)
+        if not inside.any():
+            continue
+        with np.errstate(divide="ignore", invalid="ignore"):
+            l = f32(E * (1.0 / S))
+            zq = f32(f32(f32(l[0] * Z[0]) + f32(l[1] * Z[1])) + f32(l[2] * Z[2]))
+            wq = f32(f32(f32(l[0] * W[0]) + f32(l[1] * W[1])) + f32(l[2] * W[2]))
+            d = f32(zq / wq)
+        plane = f32(gx * x + f32(gy * y + d0))               # fmaf(gx, x, fmaf(gy, y, d0))
+        ok = inside & (wq > 0.0)
+        err = np.abs(plane - d)[ok]
+        assert (err <= mg).all(), (float(err.max()), mg, size, W.tolist())
+        checked += ok.sum()
+        worst = max(worst, float((err / mg).max()))
+    assert checked > 200_000
+    assert worst > 1e-3, "the margin is not orders of magnitude larger than the errors it covers"
