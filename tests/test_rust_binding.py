@@ -13,7 +13,7 @@ RS = os.path.join(ROOT, "examples", "tr_sys.rs")
 
 SIZES = {"u8": (1, 1), "u16": (2, 2), "u32": (4, 4), "i32": (4, 4), "f32": (4, 4), "u64": (8, 8), "usize": (8, 8), "[f32; 3]": (12, 4),
          "shared_structs::CullingPushConstants": (96, 16), "shared_structs::AssignLightsPushConstants": (80, 16),
-         "shared_structs::PushConstants": (96, 16), "crate::tonemapping::BakedLottesTonemapperParams": (28, 4)}
+         "shared_structs::PushConstants": (96, 16), "colstodian::tonemap::BakedLottesTonemapperParams": (28, 4)}
 
 
 def test_binding_is_in_sync_with_the_header():

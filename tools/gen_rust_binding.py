@@ -27,7 +27,7 @@ REFERENCE_TYPES = {
     "tr_push_constants": "shared_structs::PushConstants", "tr_culling_push_constants": "shared_structs::CullingPushConstants",
     "tr_write_cluster_data_push_constants": "shared_structs::WriteClusterDataPushConstants",
     "tr_assign_lights_push_constants": "shared_structs::AssignLightsPushConstants", "tr_cluster_aabb": "shared_structs::ClusterAabb",
-    "tr_baked_lottes_tonemapper_params": "crate::tonemapping::BakedLottesTonemapperParams",
+    "tr_baked_lottes_tonemapper_params": "colstodian::tonemap::BakedLottesTonemapperParams",   # what the host passes, src/main.rs:506,1547
     "tr_draw_indexed_indirect_command": "ash::vk::DrawIndexedIndirectCommand",
     "tr_mat4": "glam::Mat4", "tr_vec4": "glam::Vec4", "tr_quat": "glam::Quat", "tr_vec3a": "glam::Vec3A",
     "tr_vec2": "glam::Vec2", "tr_uvec2": "glam::UVec2", "tr_vec3": "[f32; 3]",   # glam::Vec3 is 12 bytes, align 4, like [f32; 3]
